@@ -1,0 +1,133 @@
+/* psisloo_b200.h -- C ABI of libpsisloo_b200.so (B200 / sm_100a PSIS-LOO engine).
+ *
+ * The reference (jordandeklerk/pyloo) has no FFI: its one extension point for this path is the
+ * 1-D callable handed to the per-observation Python loop (pyloo/base.py:138-166 -> pyloo/utils.py
+ * :171-176).  Each entry point below replaces that loop *for a whole batch*; the reference
+ * interface it stands in for is cited per function.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; `stream` is a cudaStream_t passed as void* (NULL = default).
+ *   - "dev" entry points take caller-owned DEVICE memory and are asynchronous on `stream`;
+ *     "host" entry points take HOST memory, stage it through the GPU in observation chunks
+ *     (H2D / kernel / D2H overlapped on internal streams) and return when results are on the host.
+ *   - return 0 on success, a negative B2L_E_* for argument errors, a positive cudaError_t for CUDA
+ *     failures; b2l_last_error() returns a thread-local message.  Nothing throws across the ABI.
+ *   - M ("tail length") and cutoffmin are computed by the caller exactly as pyloo/psis.py:89-90
+ *     does (Python floats): M = ceil(min(S/5, 3*sqrt(S/reff))), cutoffmin = log(DBL_MIN).
+ *   - all arithmetic is IEEE float64.
+ */
+#ifndef PSISLOO_B200_H
+#define PSISLOO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2L_VERSION 100 /* 0.1.0 */
+
+#define B2L_E_INVALID (-1)     /* bad pointer / size / stride */
+#define B2L_E_UNSUPPORTED (-2) /* shape not supported by this build (e.g. S too large for smem) */
+#define B2L_E_WORKSPACE (-3)   /* workspace too small */
+#define B2L_E_NODEVICE (-4)    /* no CUDA device: there is NO CPU fallback */
+
+/* flags for the loo entry points */
+#define B2L_FLAG_WAIC_ONLY 1u /* skip PSIS: only lppd_i / var_i / lppdw_i (pyloo/waic.py path) */
+
+/* fixed per-shard statistics record (doubles); combined across GPUs by b2l_stats_merge */
+#define B2L_STATS_LEN 32
+enum {
+    B2L_ST_N = 0,         /* observations in the shard */
+    B2L_ST_ELPD_MEAN = 1, /* mean of elpd_i (log scale) */
+    B2L_ST_ELPD_M2 = 2,   /* sum (elpd_i - mean)^2 */
+    B2L_ST_ELPD_SUM = 3,
+    B2L_ST_LPPD_SUM = 4,  /* sum of loo-policy lppd_i (pyloo/loo.py:329) */
+    B2L_ST_PWAIC_SUM = 5, /* sum var_i (pyloo/waic.py:160) */
+    B2L_ST_WAIC_MEAN = 6, /* mean of (lppdw_i - var_i) */
+    B2L_ST_WAIC_M2 = 7,
+    B2L_ST_WAIC_SUM = 8,
+    B2L_ST_K_GT_GOOD = 9, /* #k > good_k (inf counts, NaN does not; pyloo/loo.py:292-293) */
+    B2L_ST_K_GT_1 = 10,
+    B2L_ST_K_INF = 11,
+    B2L_ST_K_NAN = 12,
+    B2L_ST_VAR_GT_04 = 13, /* #var_i > 0.4 (pyloo/waic.py:147) */
+    B2L_ST_ELPD_MIN = 14,
+    B2L_ST_ELPD_MAX = 15,
+    B2L_ST_WAIC_MIN = 16,
+    B2L_ST_WAIC_MAX = 17,
+    B2L_ST_N_NAN_IN = 18, /* NaN entries seen in the input (pyloo/loo.py:218) */
+    B2L_ST_N_PINF_IN = 19,
+    B2L_ST_N_NINF_IN = 20,
+    B2L_ST_N_FALLBACK = 21, /* rows that took the exact bit-wise selection fallback */
+    B2L_ST_ELPD_NAN = 22    /* #elpd_i that are NaN (excluded from nothing; diagnostic) */
+};
+
+int b2l_version(void);
+const char* b2l_last_error(void);
+
+/* Number of CUDA devices visible, or B2L_E_NODEVICE. */
+int b2l_device_count(void);
+
+/* Bytes of device workspace the dev entry points need for this problem.
+ * layout_obs_fastest: 1 if the input has stride_n == 1 (ArviZ (chain, draw, obs) layout). */
+int b2l_workspace_bytes(int64_t S, int64_t N, int32_t M, int32_t layout_obs_fastest,
+                        size_t* out_bytes);
+
+/* psislw for a batch: replaces pyloo/psis.py:100-106 (wrap_xarray_ufunc(_psislw, ...)) and the
+ * PSIS branch of pyloo/base.py:160-166.
+ *   lw      : N x S log weights, element (i, s) at lw[i*stride_n + s*stride_s]; never modified
+ *   lw_out  : same logical shape, element (i, s) at lw_out[i*ostride_n + s*ostride_s]
+ *   k_out   : N Pareto shape estimates (+inf where the tail has <= 4 draws, psis.py:142-144)
+ * Fast path: stride_s == 1 and ostride_s == 1 (contiguous rows).  stride_n == 1 is supported
+ * through an on-device tile transpose.                                                          */
+int b2l_psislw_dev_f64(const double* lw, int64_t S, int64_t N, int64_t stride_s, int64_t stride_n,
+                       int32_t M, double cutoffmin, double* lw_out, int64_t ostride_s,
+                       int64_t ostride_n, double* k_out, double* diag /* nullable, N x 8 */,
+                       void* ws, size_t ws_bytes, void* stream);
+
+/* Fused pointwise PSIS-LOO + WAIC for a batch: replaces pyloo/loo.py:286-289 (weights, lw += ll),
+ * :319-337 (loo_i and lppd_i loops) and pyloo/waic.py:137-145 (lppd_i, var_i).
+ *   ll      : log-likelihood, element (s, i) at ll[s*stride_s + i*stride_n]; NaN -> -1e10
+ *             (loo.py:227); for the WAIC outputs +-inf -> +-1e10 (waic.py:129-132)
+ *   elpd_i  : N  log-scale elpd_loo_i      k_i     : N  Pareto k
+ *   lppd_i  : N  log mean exp ll (loo)     var_i   : N  var_s(ll), ddof 0 (waic policy)
+ *   lppdw_i : N  log mean exp ll (waic policy; equals lppd_i unless the row holds +-inf)
+ *   counters: nullable, 4 x uint64 device counters (NaN, +inf, -inf inputs; fallback rows), +=   */
+int b2l_loo_dev_f64(const double* ll, int64_t S, int64_t N, int64_t stride_s, int64_t stride_n,
+                    int32_t M, double cutoffmin, uint32_t flags, double* elpd_i, double* k_i,
+                    double* lppd_i, double* var_i, double* lppdw_i, unsigned long long* counters,
+                    double* diag /* nullable, N x 8 */, void* ws, size_t ws_bytes, void* stream);
+
+/* Per-shard statistics of the pointwise outputs (device pointers): replaces the NumPy reductions
+ * pyloo/loo.py:326-342 and pyloo/waic.py:147-160.  Writes B2L_STATS_LEN doubles to stats_out
+ * (device).  Deterministic (fixed reduction tree).  counters may be NULL.                       */
+int b2l_stats_dev_f64(const double* elpd_i, const double* k_i, const double* lppd_i,
+                      const double* var_i, const double* lppdw_i, int64_t N, double good_k,
+                      const unsigned long long* counters, double* stats_out, void* ws,
+                      size_t ws_bytes, void* stream);
+
+/* Merge n_shards host-side records (rank order) into one: Chan's parallel (n, mean, M2) update,
+ * so se = sqrt(N * M2 / N) is independent of the GPU count.  Pure host arithmetic.             */
+int b2l_stats_merge(const double* shards, int32_t n_shards, double* merged);
+
+/* Host-buffer variants (what a NumPy caller binds): same semantics, HOST pointers, internal
+ * chunking.  `device` selects the GPU; chunk_obs <= 0 picks a default.                          */
+int b2l_psislw_host_f64(const double* lw, int64_t S, int64_t N, int64_t stride_s, int64_t stride_n,
+                        int32_t M, double cutoffmin, double* lw_out, int64_t ostride_s,
+                        int64_t ostride_n, double* k_out, int32_t device, int64_t chunk_obs);
+
+int b2l_loo_host_f64(const double* ll, int64_t S, int64_t N, int64_t stride_s, int64_t stride_n,
+                     int32_t M, double cutoffmin, uint32_t flags, double good_k, double* elpd_i,
+                     double* k_i, double* lppd_i, double* var_i, double* lppdw_i, double* stats_out,
+                     int32_t device, int64_t chunk_obs);
+
+/* Launch-shape introspection for benchmarks / DESIGN.md (grid, block, smem, occupancy). */
+int b2l_row_launch_info(int64_t S, int32_t M, int32_t mode /*0 psislw, 1 loo*/, int32_t* grid,
+                        int32_t* block, int32_t* smem_bytes, int32_t* ctas_per_sm, int32_t* nbuf);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSISLOO_B200_H */

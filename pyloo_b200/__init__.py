@@ -1,0 +1,22 @@
+"""pyloo_b200 -- B200-native PSIS-LOO engine behind pyloo's call signatures.
+
+Drop-in for ``pl.psislw``, ``pl.compute_importance_weights`` (PSIS branch), ``pl.loo(method="psis")``,
+``pl.waic`` and ``pl.loo_compare`` (reference: jordandeklerk/pyloo).  The numerics run in hand-written
+sm_100a CUDA kernels behind a C ABI (``include/psisloo_b200.h``); there is no CPU fallback.
+"""
+
+from .rcparams import rcParams  # noqa: F401
+from .elpd import ELPDData  # noqa: F401
+from .base import ISMethod, compute_importance_weights  # noqa: F401
+from .psis import psislw  # noqa: F401
+from .loo import loo  # noqa: F401
+from .waic import waic  # noqa: F401
+from .compare import loo_compare  # noqa: F401
+from .data import InferenceDataLite, LiteDataArray, from_dict  # noqa: F401
+
+__version__ = "0.1.0"
+
+__all__ = [
+    "psislw", "compute_importance_weights", "ISMethod", "loo", "waic", "loo_compare", "ELPDData",
+    "rcParams", "InferenceDataLite", "LiteDataArray", "from_dict",
+]

@@ -1,0 +1,125 @@
+"""Build / load libpsisloo_b200.so and declare its C ABI (include/psisloo_b200.h) for ctypes.
+
+There is NO CPU fallback: if the shared library is missing or no CUDA device is visible the
+compute entry points raise ``RuntimeError``.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import shutil
+import subprocess
+import threading
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+LIB_PATH = os.path.join(_PKG, "lib", "libpsisloo_b200.so")
+SRC = os.path.join(_PKG, "csrc", "psisloo_b200.cu")
+HEADERS = [
+    os.path.join(_PKG, "csrc", "b2l_common.cuh"),
+    os.path.join(_PKG, "csrc", "b2l_row_kernel.cuh"),
+    os.path.join(_ROOT, "include", "psisloo_b200.h"),
+]
+
+STATS_LEN = 32
+FLAG_WAIC_ONLY = 1
+DIAG_STRIDE = 8
+E_NODEVICE = -4
+
+EXPORTS = [
+    "b2l_version", "b2l_last_error", "b2l_device_count", "b2l_workspace_bytes",
+    "b2l_psislw_dev_f64", "b2l_loo_dev_f64", "b2l_stats_dev_f64", "b2l_stats_merge",
+    "b2l_psislw_host_f64", "b2l_loo_host_f64", "b2l_row_launch_info",
+]
+
+_lock = threading.Lock()
+_lib = None
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; cannot build libpsisloo_b200.so")
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    built = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(p) > built for p in [SRC, *HEADERS])
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA sources for sm_100a into an in-tree shared library."""
+    if not force and not needs_build():
+        return LIB_PATH
+    os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
+    cmd = [
+        _nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+        "-Xcompiler", "-fPIC", "-shared", "-o", LIB_PATH, SRC,
+    ]
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+def _declare(lib) -> None:
+    c = ctypes
+    i32, i64, f64, vp, sz, u32 = c.c_int32, c.c_int64, c.c_double, c.c_void_p, c.c_size_t, c.c_uint32
+    lib.b2l_version.restype = c.c_int
+    lib.b2l_version.argtypes = []
+    lib.b2l_last_error.restype = c.c_char_p
+    lib.b2l_last_error.argtypes = []
+    lib.b2l_device_count.restype = c.c_int
+    lib.b2l_device_count.argtypes = []
+    lib.b2l_workspace_bytes.restype = c.c_int
+    lib.b2l_workspace_bytes.argtypes = [i64, i64, i32, i32, c.POINTER(sz)]
+    lib.b2l_psislw_dev_f64.restype = c.c_int
+    lib.b2l_psislw_dev_f64.argtypes = [vp, i64, i64, i64, i64, i32, f64, vp, i64, i64, vp, vp, vp, sz, vp]
+    lib.b2l_loo_dev_f64.restype = c.c_int
+    lib.b2l_loo_dev_f64.argtypes = [vp, i64, i64, i64, i64, i32, f64, u32, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.b2l_stats_dev_f64.restype = c.c_int
+    lib.b2l_stats_dev_f64.argtypes = [vp, vp, vp, vp, vp, i64, f64, vp, vp, vp, sz, vp]
+    lib.b2l_stats_merge.restype = c.c_int
+    lib.b2l_stats_merge.argtypes = [vp, i32, vp]
+    lib.b2l_psislw_host_f64.restype = c.c_int
+    lib.b2l_psislw_host_f64.argtypes = [vp, i64, i64, i64, i64, i32, f64, vp, i64, i64, vp, i32, i64]
+    lib.b2l_loo_host_f64.restype = c.c_int
+    lib.b2l_loo_host_f64.argtypes = [vp, i64, i64, i64, i64, i32, f64, u32, f64, vp, vp, vp, vp, vp, vp, i32, i64]
+    lib.b2l_row_launch_info.restype = c.c_int
+    lib.b2l_row_launch_info.argtypes = [i64, i32, i32] + [c.POINTER(i32)] * 5
+
+
+def load():
+    """Return the loaded library (building it first if the sources are newer)."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if needs_build():
+                build()
+            lib = ctypes.CDLL(LIB_PATH)
+            _declare(lib)
+            _lib = lib
+        return _lib
+
+
+def check(rc: int) -> None:
+    """Translate a C-ABI return code into a Python exception (never silently continue)."""
+    if rc == 0:
+        return
+    msg = load().b2l_last_error().decode("utf-8", "replace")
+    if rc == E_NODEVICE:
+        raise RuntimeError(f"pyloo_b200 needs a CUDA device and has no CPU fallback: {msg}")
+    if rc == -1:
+        raise ValueError(msg)
+    if rc == -2:
+        raise NotImplementedError(msg)
+    raise RuntimeError(f"libpsisloo_b200 error {rc}: {msg}")

@@ -1,0 +1,174 @@
+// Common device helpers for the B200 PSIS-LOO kernels (sm_100a).
+//   * order-preserving 64-bit image of a double (radix/bitonic selection works on integers)
+//   * deterministic block reductions (fixed association order => batch-invariant results)
+//   * mbarrier + 1-D bulk-TMA (cp.async.bulk) wrappers for row staging, 2-D TMA tensor loads
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b2l {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// ---------------------------------------------------------------- ordered keys
+// Monotone map double -> uint64 (total order, -inf < ... < -0 < +0 < ... < +inf).  NaNs are
+// never keyed (rows holding NaN are short-circuited, pyloo/psis.py:134-144 semantics).
+__device__ __forceinline__ uint64_t key_of(double x) {
+    uint64_t b = (uint64_t)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double val_of(uint64_t k) {
+    uint64_t b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+// ---------------------------------------------------------------- reductions
+// Butterfly reductions: both partners of every exchange add the same two numbers, so all lanes
+// end bit-identical and the association order is fixed (deterministic, batch-invariant).
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_isum(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+// `red` = shared scratch of >= NT/32 doubles.  Every thread returns the same value.
+template <int NT>
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = red[0];
+#pragma unroll
+    for (int i = 1; i < NT / 32; ++i) t += red[i];
+    return t;
+}
+template <int NT>
+__device__ __forceinline__ double block_max(double v, double* red) {
+    v = warp_max(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = red[0];
+#pragma unroll
+    for (int i = 1; i < NT / 32; ++i) t = fmax(t, red[i]);
+    return t;
+}
+template <int NT>
+__device__ __forceinline__ double block_min(double v, double* red) {
+    v = warp_min(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = red[0];
+#pragma unroll
+    for (int i = 1; i < NT / 32; ++i) t = fmin(t, red[i]);
+    return t;
+}
+template <int NT>
+__device__ __forceinline__ int block_isum(int v, double* red) {
+    int* ired = reinterpret_cast<int*>(red);
+    v = warp_isum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) ired[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int t = ired[0];
+#pragma unroll
+    for (int i = 1; i < NT / 32; ++i) t += ired[i];
+    return t;
+}
+
+// ---------------------------------------------------------------- mbarrier / bulk TMA
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared, 1-D, bytes % 16 == 0, both addresses 16 B aligned.  SASS: UBLKCP.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                         uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+// shared -> global, 1-D bulk store (bulk_group completion).
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+                 "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read0() {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait0() {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+// 2-D tiled TMA load (tensor map in param/const space).  SASS: UTMALDG.
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const void* tmap, int c0, int c1,
+                                            uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst_smem)),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ---------------------------------------------------------------- misc
+__device__ __forceinline__ int next_pow2(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+__device__ __forceinline__ bool is_finite(double x) {
+    return (((uint64_t)__double_as_longlong(x) >> 52) & 0x7ff) != 0x7ff;
+}
+__device__ __forceinline__ double nan_f64() { return __longlong_as_double(0x7ff8000000000000ll); }
+__device__ __forceinline__ double inf_f64() { return __longlong_as_double(0x7ff0000000000000ll); }
+
+}  // namespace b2l

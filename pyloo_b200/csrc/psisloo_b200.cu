@@ -1,0 +1,642 @@
+// libpsisloo_b200.so -- C ABI (include/psisloo_b200.h) over the sm_100a kernels.
+// Host side: launch planning, obs-fastest panel transposes, shard statistics, host-buffer pipelines.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/psisloo_b200.h"
+#include "b2l_row_kernel.cuh"
+
+using namespace b2l;
+
+// ------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CK(call)                                                                         \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess)                                                          \
+            return fail((int)e__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                             \
+    } while (0)
+
+// ------------------------------------------------------------------------------------ planning
+struct RowPlan {
+    int nt, cap, ns, r0, nbuf, ctas_per_sm, grid, sms;
+    size_t smem;
+};
+
+static int pow2ceil(long long v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+template <int NT, int MODE>
+static cudaError_t occupancy_of(size_t smem, int* out) {
+    cudaError_t e = cudaFuncSetAttribute(psis_row_kernel<NT, MODE>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, psis_row_kernel<NT, MODE>, NT, smem);
+}
+
+static int plan_row(long long S, int M, int mode, long long n_rows, RowPlan* pl) {
+    if (S < 1 || M < 1 || (long long)M + 1 > S)
+        return fail(B2L_E_INVALID, "need 1 <= M and M + 1 <= S (S=%lld, M=%d): the reference indexes "
+                    "x[sorted[-M-1]] (pyloo/psis.py:136)", S, M);
+    if (M > 9000) return fail(B2L_E_UNSUPPORTED, "tail length M=%d exceeds the GPD grid capacity", M);
+    if (S > (1ll << 30)) return fail(B2L_E_UNSUPPORTED, "S too large");
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    int smem_optin = 0, smem_sm = 0, sms = 0;
+    CK(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    CK(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    pl->sms = sms;
+    pl->cap = std::max(512, pow2ceil(3ll * (M + 1)));
+    pl->ns = std::min(1024, std::max(256, pow2ceil((S + 15) / 16)));
+    long long r0 = (long long)std::ceil(1.9 * (M + 1) * (double)pl->ns / (double)S);
+    pl->r0 = (int)std::min<long long>(pl->ns, std::max<long long>(1, r0));
+    // rows in flight per SM: prefer more resident CTAs (more warps), double-buffer on a tie
+    int best_ctas = 0, best_nbuf = 0, best_nt = 256;
+    size_t best_smem = 0;
+    for (int nbuf = 1; nbuf <= 2; ++nbuf) {
+        for (int nt : {256, 512}) {
+            size_t smem = row_smem_layout((int)S, M, pl->cap, pl->ns, nbuf, nt).total;
+            if (smem > (size_t)smem_optin) continue;
+            int ctas = (int)((size_t)smem_sm / (smem + 1024));
+            if (ctas < 1) continue;
+            if (nt == 512 && ctas > 1) continue;  // wide CTAs only when a single CTA owns the SM
+            bool better = ctas > best_ctas || (ctas == best_ctas && nbuf > best_nbuf) ||
+                          (ctas == best_ctas && nbuf == best_nbuf && ctas == 1 && nt > best_nt);
+            if (better) {
+                best_ctas = ctas; best_nbuf = nbuf; best_nt = nt; best_smem = smem;
+            }
+        }
+    }
+    // tuning overrides (numerics are unaffected): B2L_NBUF = 1|2, B2L_NT = 256|512
+    if (const char* ev = getenv("B2L_NBUF")) {
+        int nb = atoi(ev), nt = getenv("B2L_NT") ? atoi(getenv("B2L_NT")) : best_nt;
+        if ((nb == 1 || nb == 2) && (nt == 256 || nt == 512)) {
+            size_t smem = row_smem_layout((int)S, M, pl->cap, pl->ns, nb, nt).total;
+            if (smem <= (size_t)smem_optin) {
+                best_nbuf = nb; best_nt = nt; best_smem = smem;
+                best_ctas = std::max(1, (int)((size_t)smem_sm / (smem + 1024)));
+            }
+        }
+    }
+    if (best_ctas == 0)
+        return fail(B2L_E_UNSUPPORTED, "S=%lld draws (%lld bytes/observation) do not fit the %d-byte "
+                    "shared memory of one SM", S, S * 8, smem_optin);
+    pl->nt = best_nt; pl->nbuf = best_nbuf; pl->smem = best_smem;
+    int occ = 0;
+    cudaError_t e;
+    if (mode == MODE_PSISLW)
+        e = (best_nt == 256) ? occupancy_of<256, MODE_PSISLW>(best_smem, &occ)
+                             : occupancy_of<512, MODE_PSISLW>(best_smem, &occ);
+    else
+        e = (best_nt == 256) ? occupancy_of<256, MODE_LOO>(best_smem, &occ)
+                             : occupancy_of<512, MODE_LOO>(best_smem, &occ);
+    CK(e);
+    if (occ < 1) return fail(B2L_E_UNSUPPORTED, "row kernel does not fit on an SM (smem %zu)", best_smem);
+    pl->ctas_per_sm = occ;
+    long long g = (long long)sms * occ;
+    pl->grid = (int)std::max<long long>(1, std::min<long long>(g, n_rows));
+    return 0;
+}
+
+static int launch_rows(int mode, const RowPlan& pl, RowParams rp, cudaStream_t st) {
+    rp.cap = pl.cap; rp.ns = pl.ns; rp.r0 = pl.r0; rp.nbuf = pl.nbuf;
+    int grid = (int)std::max<long long>(1, std::min<long long>(pl.grid, rp.n_rows));
+    if (rp.n_rows == 0) return 0;
+    if (mode == MODE_PSISLW) {
+        if (pl.nt == 256) psis_row_kernel<256, MODE_PSISLW><<<grid, 256, pl.smem, st>>>(rp);
+        else psis_row_kernel<512, MODE_PSISLW><<<grid, 512, pl.smem, st>>>(rp);
+    } else {
+        if (pl.nt == 256) psis_row_kernel<256, MODE_LOO><<<grid, 256, pl.smem, st>>>(rp);
+        else psis_row_kernel<512, MODE_LOO><<<grid, 512, pl.smem, st>>>(rp);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ transpose
+// dst[c * dst_ld + r] = src[r * src_ld + c]   for r < rows, c < cols   (32 x 32 tiles, padded smem)
+__global__ void __launch_bounds__(256) transpose_f64_kernel(const double* __restrict__ src,
+                                                            long long src_ld,
+                                                            double* __restrict__ dst,
+                                                            long long dst_ld, int rows, int cols) {
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const long long c0 = (long long)blockIdx.x * 32, r0 = (long long)blockIdx.y * 32;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const long long r = r0 + ty + 8 * k, c = c0 + tx;
+        if (r < rows && c < cols) tile[ty + 8 * k][tx] = src[r * src_ld + c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const long long c = c0 + ty + 8 * k, r = r0 + tx;
+        if (r < rows && c < cols) dst[c * dst_ld + r] = tile[tx][ty + 8 * k];
+    }
+}
+
+static int launch_transpose(const double* src, long long src_ld, double* dst, long long dst_ld,
+                            long long rows, long long cols, cudaStream_t st) {
+    if (rows == 0 || cols == 0) return 0;
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+    if (grid.y > 65535u) return fail(B2L_E_UNSUPPORTED, "transpose: too many rows (%lld)", rows);
+    transpose_f64_kernel<<<grid, 256, 0, st>>>(src, src_ld, dst, dst_ld, (int)rows, (int)cols);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ statistics
+struct Welford {
+    double n, mean, m2;
+};
+__host__ __device__ inline Welford chan_merge(Welford a, Welford b) {
+    if (b.n == 0.0) return a;
+    if (a.n == 0.0) return b;
+    Welford r;
+    r.n = a.n + b.n;
+    const double d = b.mean - a.mean;
+    r.mean = a.mean + d * (b.n / r.n);
+    r.m2 = a.m2 + b.m2 + d * d * (a.n * b.n / r.n);
+    return r;
+}
+struct StatAcc {
+    Welford e, w;
+    double esum, lsum, psum, wsum;
+    double kgood, k1, kinf, knan, v04, enan;
+    double emin, emax, wmin, wmax;
+};
+__host__ __device__ inline StatAcc stat_zero() {
+    StatAcc a;
+    a.e = {0, 0, 0}; a.w = {0, 0, 0};
+    a.esum = a.lsum = a.psum = a.wsum = 0;
+    a.kgood = a.k1 = a.kinf = a.knan = a.v04 = a.enan = 0;
+    a.emin = a.wmin = INFINITY; a.emax = a.wmax = -INFINITY;
+    return a;
+}
+__host__ __device__ inline StatAcc stat_merge(const StatAcc& a, const StatAcc& b) {
+    StatAcc r;
+    r.e = chan_merge(a.e, b.e); r.w = chan_merge(a.w, b.w);
+    r.esum = a.esum + b.esum; r.lsum = a.lsum + b.lsum; r.psum = a.psum + b.psum; r.wsum = a.wsum + b.wsum;
+    r.kgood = a.kgood + b.kgood; r.k1 = a.k1 + b.k1; r.kinf = a.kinf + b.kinf; r.knan = a.knan + b.knan;
+    r.v04 = a.v04 + b.v04; r.enan = a.enan + b.enan;
+    r.emin = fmin(a.emin, b.emin); r.emax = fmax(a.emax, b.emax);
+    r.wmin = fmin(a.wmin, b.wmin); r.wmax = fmax(a.wmax, b.wmax);
+    return r;
+}
+__host__ __device__ inline void stat_push(StatAcc& a, double e, double k, double l, double v, double lw,
+                                          double good_k) {
+    const double w = lw - v;
+    Welford one = {1.0, e, 0.0};
+    a.e = chan_merge(a.e, one);
+    Welford onew = {1.0, w, 0.0};
+    a.w = chan_merge(a.w, onew);
+    a.esum += e; a.lsum += l; a.psum += v; a.wsum += w;
+    a.kgood += (k > good_k) ? 1.0 : 0.0;  // inf counts, NaN does not (loo.py:292)
+    a.k1 += (k > 1.0) ? 1.0 : 0.0;
+    a.kinf += (k == INFINITY) ? 1.0 : 0.0;
+    a.knan += (k != k) ? 1.0 : 0.0;
+    a.v04 += (v > 0.4) ? 1.0 : 0.0;
+    a.enan += (e != e) ? 1.0 : 0.0;
+    a.emin = fmin(a.emin, e); a.emax = fmax(a.emax, e);
+    a.wmin = fmin(a.wmin, w); a.wmax = fmax(a.wmax, w);
+}
+constexpr int STAT_WORDS = sizeof(StatAcc) / sizeof(double);
+
+__device__ inline StatAcc stat_shfl_xor(const StatAcc& a, int o) {
+    StatAcc r;
+    const double* s = reinterpret_cast<const double*>(&a);
+    double* d = reinterpret_cast<double*>(&r);
+#pragma unroll
+    for (int i = 0; i < STAT_WORDS; ++i) d[i] = __shfl_down_sync(FULL, s[i], o);
+    return r;
+}
+
+// stage 1: each block reduces a contiguous slab in a fixed tree; stage 2 (1 block) merges partials
+__global__ void __launch_bounds__(256) stats_partial_kernel(const double* elpd, const double* k,
+                                                            const double* lppd, const double* var,
+                                                            const double* lppdw, long long N,
+                                                            double good_k, StatAcc* partial) {
+    __shared__ StatAcc sh[8];
+    const long long per = (N + gridDim.x - 1) / gridDim.x;
+    const long long i0 = (long long)blockIdx.x * per, i1 = (i0 + per < N) ? i0 + per : N;
+    StatAcc a = stat_zero();
+    for (long long i = i0 + threadIdx.x; i < i1; i += 256)
+        stat_push(a, elpd[i], k[i], lppd[i], var[i], lppdw[i], good_k);
+    for (int o = 16; o > 0; o >>= 1) {
+        StatAcc b = stat_shfl_xor(a, o);
+        a = stat_merge(a, b);  // lanes >= o hold garbage merges; lane 0 holds the tree result
+    }
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        StatAcc t = sh[0];
+        for (int w = 1; w < 8; ++w) t = stat_merge(t, sh[w]);
+        partial[blockIdx.x] = t;
+    }
+}
+__global__ void stats_final_kernel(const StatAcc* partial, int nparts,
+                                   const unsigned long long* counters, double* out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    StatAcc t = partial[0];
+    for (int i = 1; i < nparts; ++i) t = stat_merge(t, partial[i]);
+    for (int i = 0; i < B2L_STATS_LEN; ++i) out[i] = 0.0;
+    out[B2L_ST_N] = t.e.n; out[B2L_ST_ELPD_MEAN] = t.e.mean; out[B2L_ST_ELPD_M2] = t.e.m2;
+    out[B2L_ST_ELPD_SUM] = t.esum; out[B2L_ST_LPPD_SUM] = t.lsum; out[B2L_ST_PWAIC_SUM] = t.psum;
+    out[B2L_ST_WAIC_MEAN] = t.w.mean; out[B2L_ST_WAIC_M2] = t.w.m2; out[B2L_ST_WAIC_SUM] = t.wsum;
+    out[B2L_ST_K_GT_GOOD] = t.kgood; out[B2L_ST_K_GT_1] = t.k1; out[B2L_ST_K_INF] = t.kinf;
+    out[B2L_ST_K_NAN] = t.knan; out[B2L_ST_VAR_GT_04] = t.v04; out[B2L_ST_ELPD_NAN] = t.enan;
+    out[B2L_ST_ELPD_MIN] = t.emin; out[B2L_ST_ELPD_MAX] = t.emax;
+    out[B2L_ST_WAIC_MIN] = t.wmin; out[B2L_ST_WAIC_MAX] = t.wmax;
+    if (counters) {
+        out[B2L_ST_N_NAN_IN] = (double)counters[0]; out[B2L_ST_N_PINF_IN] = (double)counters[1];
+        out[B2L_ST_N_NINF_IN] = (double)counters[2]; out[B2L_ST_N_FALLBACK] = (double)counters[3];
+    }
+}
+constexpr int STATS_BLOCKS = 148;
+
+// ------------------------------------------------------------------------------------ workspace
+// layout: [stats partials][panel A (obs-fastest input transposed to rows)][panel B (psislw rows out)]
+static long long panel_obs(long long S, long long N) {
+    long long p = (24ll << 20) / std::max<long long>(1, S * 8);  // ~24 MB panels stay L2-resident
+    p = std::max<long long>(p, 1184);                            // >= 2 waves of 148 x 4 CTAs
+    p = (p + 31) / 32 * 32;
+    return std::min(p, (N + 31) / 32 * 32);
+}
+static size_t stats_ws_bytes() { return align_up(sizeof(StatAcc) * STATS_BLOCKS, 256); }
+
+extern "C" int b2l_version(void) { return B2L_VERSION; }
+extern "C" const char* b2l_last_error(void) { return g_err; }
+extern "C" int b2l_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n < 1) {
+        cudaGetLastError();
+        return fail(B2L_E_NODEVICE, "no CUDA device visible (%s); this engine has no CPU fallback",
+                    cudaGetErrorString(e));
+    }
+    return n;
+}
+
+extern "C" int b2l_workspace_bytes(int64_t S, int64_t N, int32_t M, int32_t layout_obs_fastest,
+                                   size_t* out_bytes) {
+    (void)M;
+    if (!out_bytes || S < 1 || N < 0) return fail(B2L_E_INVALID, "bad arguments");
+    size_t b = stats_ws_bytes();
+    if (layout_obs_fastest) b += 2 * align_up((size_t)panel_obs(S, N) * (size_t)S * 8, 256);
+    *out_bytes = b;
+    return 0;
+}
+
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+extern "C" int b2l_psislw_dev_f64(const double* lw, int64_t S, int64_t N, int64_t stride_s,
+                                  int64_t stride_n, int32_t M, double cutoffmin, double* lw_out,
+                                  int64_t ostride_s, int64_t ostride_n, double* k_out, double* diag,
+                                  void* ws, size_t ws_bytes, void* stream) {
+    if (!lw || !lw_out || !k_out || N < 0) return fail(B2L_E_INVALID, "null pointer or negative N");
+    if (N == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    RowPlan pl;
+    int rc = plan_row(S, M, MODE_PSISLW, N, &pl);
+    if (rc) return rc;
+    RowParams rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.S = (int)S; rp.M = M; rp.cutoffmin = cutoffmin; rp.k_out = k_out; rp.diag = diag;
+    const bool rows_in = (stride_s == 1 || S == 1), rows_out = (ostride_s == 1 || S == 1);
+    if (rows_in && rows_out) {
+        rp.in = lw; rp.in_stride = stride_n; rp.out = lw_out; rp.out_stride = ostride_n; rp.n_rows = N;
+        rp.use_bulk = (S % 2 == 0) && aligned16(lw) && aligned16(lw_out) && (stride_n % 2 == 0) &&
+                      (ostride_n % 2 == 0);
+        return launch_rows(MODE_PSISLW, pl, rp, st);
+    }
+    if (!((stride_n == 1 || N == 1) || rows_in) || !((ostride_n == 1 || N == 1) || rows_out))
+        return fail(B2L_E_INVALID, "one of (stride_s, stride_n) must be 1 for input and output");
+    // obs-fastest on either side: go through row panels
+    const long long P = panel_obs(S, N);
+    const size_t panel_bytes = align_up((size_t)P * (size_t)S * 8, 256);
+    if (!ws || ws_bytes < stats_ws_bytes() + 2 * panel_bytes)
+        return fail(B2L_E_WORKSPACE, "workspace too small: need %zu bytes", stats_ws_bytes() + 2 * panel_bytes);
+    double* pa = reinterpret_cast<double*>((char*)ws + stats_ws_bytes());
+    double* pb = reinterpret_cast<double*>((char*)ws + stats_ws_bytes() + panel_bytes);
+    for (long long i0 = 0; i0 < N; i0 += P) {
+        const long long np = std::min<long long>(P, N - i0);
+        RowParams r = rp;
+        r.n_rows = np; r.k_out = k_out + i0; r.diag = diag ? diag + i0 * DIAG_STRIDE : nullptr;
+        if (rows_in) { r.in = lw + i0 * stride_n; r.in_stride = stride_n; }
+        else {
+            rc = launch_transpose(lw + i0, stride_s, pa, S, S, np, st);  // (S x np) -> (np x S)
+            if (rc) return rc;
+            r.in = pa; r.in_stride = S;
+        }
+        if (rows_out) { r.out = lw_out + i0 * ostride_n; r.out_stride = ostride_n; }
+        else { r.out = pb; r.out_stride = S; }
+        r.use_bulk = (S % 2 == 0) && aligned16(r.in) && aligned16(r.out) && (r.in_stride % 2 == 0) &&
+                     (r.out_stride % 2 == 0);
+        rc = launch_rows(MODE_PSISLW, pl, r, st);
+        if (rc) return rc;
+        if (!rows_out) {
+            rc = launch_transpose(pb, S, lw_out + i0, ostride_s, np, S, st);  // (np x S) -> (S x np)
+            if (rc) return rc;
+        }
+    }
+    return 0;
+}
+
+extern "C" int b2l_loo_dev_f64(const double* ll, int64_t S, int64_t N, int64_t stride_s,
+                               int64_t stride_n, int32_t M, double cutoffmin, uint32_t flags,
+                               double* elpd_i, double* k_i, double* lppd_i, double* var_i,
+                               double* lppdw_i, unsigned long long* counters, double* diag, void* ws,
+                               size_t ws_bytes, void* stream) {
+    if (!ll || !elpd_i || !k_i || !lppd_i || !var_i || !lppdw_i || N < 0)
+        return fail(B2L_E_INVALID, "null pointer or negative N");
+    if (N == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    RowPlan pl;
+    int rc = plan_row(S, M, MODE_LOO, N, &pl);
+    if (rc) return rc;
+    RowParams rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.S = (int)S; rp.M = M; rp.cutoffmin = cutoffmin; rp.counters = counters;
+    rp.waic_only = (flags & B2L_FLAG_WAIC_ONLY) ? 1 : 0;
+    if (stride_s == 1 || S == 1) {  // rows contiguous
+        rp.in = ll; rp.in_stride = stride_n; rp.n_rows = N;
+        rp.k_out = k_i; rp.elpd_i = elpd_i; rp.lppd_i = lppd_i; rp.var_i = var_i; rp.lppdw_i = lppdw_i;
+        rp.diag = diag;
+        rp.use_bulk = (S % 2 == 0) && aligned16(ll) && (stride_n % 2 == 0);
+        return launch_rows(MODE_LOO, pl, rp, st);
+    }
+    if (!(stride_n == 1 || N == 1))
+        return fail(B2L_E_INVALID, "one of (stride_s, stride_n) must be 1");
+    const long long P = panel_obs(S, N);
+    const size_t panel_bytes = align_up((size_t)P * (size_t)S * 8, 256);
+    if (!ws || ws_bytes < stats_ws_bytes() + panel_bytes)
+        return fail(B2L_E_WORKSPACE, "workspace too small: need %zu bytes", stats_ws_bytes() + panel_bytes);
+    double* pa = reinterpret_cast<double*>((char*)ws + stats_ws_bytes());
+    for (long long i0 = 0; i0 < N; i0 += P) {
+        const long long np = std::min<long long>(P, N - i0);
+        rc = launch_transpose(ll + i0, stride_s, pa, S, S, np, st);
+        if (rc) return rc;
+        RowParams r = rp;
+        r.in = pa; r.in_stride = S; r.n_rows = np;
+        r.k_out = k_i + i0; r.elpd_i = elpd_i + i0; r.lppd_i = lppd_i + i0; r.var_i = var_i + i0;
+        r.lppdw_i = lppdw_i + i0; r.diag = diag ? diag + i0 * DIAG_STRIDE : nullptr;
+        r.use_bulk = (S % 2 == 0) && aligned16(pa);
+        rc = launch_rows(MODE_LOO, pl, r, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+extern "C" int b2l_stats_dev_f64(const double* elpd_i, const double* k_i, const double* lppd_i,
+                                 const double* var_i, const double* lppdw_i, int64_t N, double good_k,
+                                 const unsigned long long* counters, double* stats_out, void* ws,
+                                 size_t ws_bytes, void* stream) {
+    if (!elpd_i || !k_i || !lppd_i || !var_i || !lppdw_i || !stats_out || N < 0)
+        return fail(B2L_E_INVALID, "null pointer or negative N");
+    if (!ws || ws_bytes < stats_ws_bytes()) return fail(B2L_E_WORKSPACE, "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    StatAcc* partial = reinterpret_cast<StatAcc*>(ws);
+    stats_partial_kernel<<<STATS_BLOCKS, 256, 0, st>>>(elpd_i, k_i, lppd_i, var_i, lppdw_i, N, good_k, partial);
+    CK(cudaGetLastError());
+    stats_final_kernel<<<1, 32, 0, st>>>(partial, STATS_BLOCKS, counters, stats_out);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b2l_stats_merge(const double* shards, int32_t n_shards, double* merged) {
+    if (!shards || !merged || n_shards < 1) return fail(B2L_E_INVALID, "bad arguments");
+    Welford e = {0, 0, 0}, w = {0, 0, 0};
+    double out[B2L_STATS_LEN];
+    for (int i = 0; i < B2L_STATS_LEN; ++i) out[i] = 0.0;
+    out[B2L_ST_ELPD_MIN] = out[B2L_ST_WAIC_MIN] = INFINITY;
+    out[B2L_ST_ELPD_MAX] = out[B2L_ST_WAIC_MAX] = -INFINITY;
+    static const int sums[] = {B2L_ST_ELPD_SUM, B2L_ST_LPPD_SUM, B2L_ST_PWAIC_SUM, B2L_ST_WAIC_SUM,
+                               B2L_ST_K_GT_GOOD, B2L_ST_K_GT_1, B2L_ST_K_INF, B2L_ST_K_NAN,
+                               B2L_ST_VAR_GT_04, B2L_ST_N_NAN_IN, B2L_ST_N_PINF_IN, B2L_ST_N_NINF_IN,
+                               B2L_ST_N_FALLBACK, B2L_ST_ELPD_NAN};
+    for (int r = 0; r < n_shards; ++r) {
+        const double* s = shards + (size_t)r * B2L_STATS_LEN;
+        e = chan_merge(e, Welford{s[B2L_ST_N], s[B2L_ST_ELPD_MEAN], s[B2L_ST_ELPD_M2]});
+        w = chan_merge(w, Welford{s[B2L_ST_N], s[B2L_ST_WAIC_MEAN], s[B2L_ST_WAIC_M2]});
+        for (int id : sums) out[id] += s[id];
+        if (s[B2L_ST_N] > 0) {
+            out[B2L_ST_ELPD_MIN] = std::fmin(out[B2L_ST_ELPD_MIN], s[B2L_ST_ELPD_MIN]);
+            out[B2L_ST_ELPD_MAX] = std::fmax(out[B2L_ST_ELPD_MAX], s[B2L_ST_ELPD_MAX]);
+            out[B2L_ST_WAIC_MIN] = std::fmin(out[B2L_ST_WAIC_MIN], s[B2L_ST_WAIC_MIN]);
+            out[B2L_ST_WAIC_MAX] = std::fmax(out[B2L_ST_WAIC_MAX], s[B2L_ST_WAIC_MAX]);
+        }
+    }
+    out[B2L_ST_N] = e.n; out[B2L_ST_ELPD_MEAN] = e.mean; out[B2L_ST_ELPD_M2] = e.m2;
+    out[B2L_ST_WAIC_MEAN] = w.mean; out[B2L_ST_WAIC_M2] = w.m2;
+    memcpy(merged, out, sizeof(out));
+    return 0;
+}
+
+extern "C" int b2l_row_launch_info(int64_t S, int32_t M, int32_t mode, int32_t* grid, int32_t* block,
+                                   int32_t* smem_bytes, int32_t* ctas_per_sm, int32_t* nbuf) {
+    RowPlan pl;
+    int rc = plan_row(S, M, mode ? MODE_LOO : MODE_PSISLW, 1ll << 40, &pl);
+    if (rc) return rc;
+    if (grid) *grid = pl.grid;
+    if (block) *block = pl.nt;
+    if (smem_bytes) *smem_bytes = (int)pl.smem;
+    if (ctas_per_sm) *ctas_per_sm = pl.ctas_per_sm;
+    if (nbuf) *nbuf = pl.nbuf;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ host pipelines
+// Per-device cache of staging buffers and streams so repeated calls do not pay cudaMalloc.
+namespace {
+constexpr int NSLOT = 3;
+struct Slot {
+    cudaStream_t st = nullptr;
+    void* buf = nullptr;
+    size_t bytes = 0;
+};
+struct DevCtx {
+    Slot slot[NSLOT];
+    bool init = false;
+};
+std::mutex g_ctx_mu;
+DevCtx g_ctx[64];
+
+int slot_reserve(Slot& s, size_t bytes) {
+    if (!s.st) CK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+    if (s.bytes < bytes) {
+        if (s.buf) CK(cudaFree(s.buf));
+        s.buf = nullptr; s.bytes = 0;
+        CK(cudaMalloc(&s.buf, bytes));
+        s.bytes = bytes;
+    }
+    return 0;
+}
+long long default_chunk(long long S, long long N) {
+    long long c = (128ll << 20) / std::max<long long>(1, S * 8);
+    c = std::max<long long>(c, 1024);
+    c = (c + 31) / 32 * 32;
+    return std::min(c, std::max<long long>(N, 1));
+}
+struct Carve {
+    char* p;
+    explicit Carve(void* b) : p((char*)b) {}
+    template <class T> T* take(size_t n) {
+        T* r = reinterpret_cast<T*>(p);
+        p += align_up(n * sizeof(T), 256);
+        return r;
+    }
+};
+}  // namespace
+
+extern "C" int b2l_psislw_host_f64(const double* lw, int64_t S, int64_t N, int64_t stride_s,
+                                   int64_t stride_n, int32_t M, double cutoffmin, double* lw_out,
+                                   int64_t ostride_s, int64_t ostride_n, double* k_out, int32_t device,
+                                   int64_t chunk_obs) {
+    if (!lw || !lw_out || !k_out || N < 0 || S < 1) return fail(B2L_E_INVALID, "bad arguments");
+    if (b2l_device_count() < 1) return B2L_E_NODEVICE;
+    if (N == 0) return 0;
+    const bool rows_in = (stride_s == 1 || S == 1), rows_out = (ostride_s == 1 || S == 1);
+    if (!rows_in && !(stride_n == 1 || N == 1)) return fail(B2L_E_INVALID, "input must have a unit stride");
+    if (!rows_out && !(ostride_n == 1 || N == 1)) return fail(B2L_E_INVALID, "output must have a unit stride");
+    std::lock_guard<std::mutex> lock(g_ctx_mu);
+    CK(cudaSetDevice(device));
+    DevCtx& cx = g_ctx[device & 63];
+    const long long chunk = chunk_obs > 0 ? std::min<long long>(chunk_obs, N) : default_chunk(S, N);
+    size_t wsb = 0;
+    b2l_workspace_bytes(S, chunk, M, (!rows_in || !rows_out) ? 1 : 0, &wsb);
+    const size_t mat = align_up((size_t)chunk * (size_t)S * 8, 256);
+    const size_t need = 2 * mat + align_up((size_t)chunk * 8, 256) + wsb + 1024;
+    for (int s = 0; s < NSLOT; ++s) {
+        int rc = slot_reserve(cx.slot[s], need);
+        if (rc) return rc;
+    }
+    int ci = 0;
+    for (long long i0 = 0; i0 < N; i0 += chunk, ++ci) {
+        const long long nc = std::min<long long>(chunk, N - i0);
+        Slot& sl = cx.slot[ci % NSLOT];
+        Carve cv(sl.buf);
+        double* d_in = cv.take<double>((size_t)chunk * S);
+        double* d_out = cv.take<double>((size_t)chunk * S);
+        double* d_k = cv.take<double>((size_t)chunk);
+        void* d_ws = cv.take<char>(wsb);
+        long long dss, dsn, oss, osn;
+        if (rows_in) {  // rows [i0, i0+nc) -> dense nc x S
+            CK(cudaMemcpy2DAsync(d_in, (size_t)S * 8, lw + i0 * stride_n, (size_t)stride_n * 8,
+                                 (size_t)S * 8, (size_t)nc, cudaMemcpyHostToDevice, sl.st));
+            dss = 1; dsn = S;
+        } else {        // columns [i0, i0+nc) of the S x N matrix -> dense S x nc
+            CK(cudaMemcpy2DAsync(d_in, (size_t)nc * 8, lw + i0, (size_t)stride_s * 8, (size_t)nc * 8,
+                                 (size_t)S, cudaMemcpyHostToDevice, sl.st));
+            dss = nc; dsn = 1;
+        }
+        if (rows_out) { oss = 1; osn = S; } else { oss = nc; osn = 1; }
+        int rc = b2l_psislw_dev_f64(d_in, S, nc, dss, dsn, M, cutoffmin, d_out, oss, osn, d_k, nullptr,
+                                    d_ws, wsb, sl.st);
+        if (rc) return rc;
+        if (rows_out)
+            CK(cudaMemcpy2DAsync(lw_out + i0 * ostride_n, (size_t)ostride_n * 8, d_out, (size_t)S * 8,
+                                 (size_t)S * 8, (size_t)nc, cudaMemcpyDeviceToHost, sl.st));
+        else
+            CK(cudaMemcpy2DAsync(lw_out + i0, (size_t)ostride_s * 8, d_out, (size_t)nc * 8,
+                                 (size_t)nc * 8, (size_t)S, cudaMemcpyDeviceToHost, sl.st));
+        CK(cudaMemcpyAsync(k_out + i0, d_k, (size_t)nc * 8, cudaMemcpyDeviceToHost, sl.st));
+    }
+    for (int s = 0; s < NSLOT; ++s) CK(cudaStreamSynchronize(cx.slot[s].st));
+    return 0;
+}
+
+extern "C" int b2l_loo_host_f64(const double* ll, int64_t S, int64_t N, int64_t stride_s,
+                                int64_t stride_n, int32_t M, double cutoffmin, uint32_t flags,
+                                double good_k, double* elpd_i, double* k_i, double* lppd_i, double* var_i,
+                                double* lppdw_i, double* stats_out, int32_t device, int64_t chunk_obs) {
+    if (!ll || !elpd_i || !k_i || !lppd_i || !var_i || !lppdw_i || N < 0 || S < 1)
+        return fail(B2L_E_INVALID, "bad arguments");
+    if (b2l_device_count() < 1) return B2L_E_NODEVICE;
+    const bool rows_in = (stride_s == 1 || S == 1);
+    if (!rows_in && !(stride_n == 1 || N == 1)) return fail(B2L_E_INVALID, "input must have a unit stride");
+    std::lock_guard<std::mutex> lock(g_ctx_mu);
+    CK(cudaSetDevice(device));
+    DevCtx& cx = g_ctx[device & 63];
+    const long long chunk = chunk_obs > 0 ? std::min<long long>(chunk_obs, std::max<long long>(N, 1))
+                                          : default_chunk(S, N);
+    size_t wsb = 0;
+    b2l_workspace_bytes(S, chunk, M, rows_in ? 0 : 1, &wsb);
+    const size_t mat = align_up((size_t)chunk * (size_t)S * 8, 256);
+    const size_t vec = align_up((size_t)chunk * 8, 256);
+    const size_t need = mat + 5 * vec + 512 + wsb + 1024;
+    for (int s = 0; s < NSLOT; ++s) {
+        int rc = slot_reserve(cx.slot[s], need);
+        if (rc) return rc;
+    }
+    const long long nchunks = N > 0 ? (N + chunk - 1) / chunk : 0;
+    std::vector<double> recs((size_t)std::max<long long>(nchunks, 1) * B2L_STATS_LEN, 0.0);
+    int ci = 0;
+    for (long long i0 = 0; i0 < N; i0 += chunk, ++ci) {
+        const long long nc = std::min<long long>(chunk, N - i0);
+        Slot& sl = cx.slot[ci % NSLOT];
+        Carve cv(sl.buf);
+        double* d_in = cv.take<double>((size_t)chunk * S);
+        double* d_e = cv.take<double>((size_t)chunk);
+        double* d_k = cv.take<double>((size_t)chunk);
+        double* d_l = cv.take<double>((size_t)chunk);
+        double* d_v = cv.take<double>((size_t)chunk);
+        double* d_lw = cv.take<double>((size_t)chunk);
+        unsigned long long* d_cnt = cv.take<unsigned long long>(4);
+        double* d_stats = cv.take<double>(B2L_STATS_LEN);
+        void* d_ws = cv.take<char>(wsb);
+        long long dss, dsn;
+        if (rows_in) {
+            CK(cudaMemcpy2DAsync(d_in, (size_t)S * 8, ll + i0 * stride_n, (size_t)stride_n * 8,
+                                 (size_t)S * 8, (size_t)nc, cudaMemcpyHostToDevice, sl.st));
+            dss = 1; dsn = S;
+        } else {
+            CK(cudaMemcpy2DAsync(d_in, (size_t)nc * 8, ll + i0, (size_t)stride_s * 8, (size_t)nc * 8,
+                                 (size_t)S, cudaMemcpyHostToDevice, sl.st));
+            dss = nc; dsn = 1;
+        }
+        CK(cudaMemsetAsync(d_cnt, 0, 4 * sizeof(unsigned long long), sl.st));
+        int rc = b2l_loo_dev_f64(d_in, S, nc, dss, dsn, M, cutoffmin, flags, d_e, d_k, d_l, d_v, d_lw, d_cnt,
+                                 nullptr, d_ws, wsb, sl.st);
+        if (rc) return rc;
+        rc = b2l_stats_dev_f64(d_e, d_k, d_l, d_v, d_lw, nc, good_k, d_cnt, d_stats, d_ws, wsb, sl.st);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(elpd_i + i0, d_e, (size_t)nc * 8, cudaMemcpyDeviceToHost, sl.st));
+        CK(cudaMemcpyAsync(k_i + i0, d_k, (size_t)nc * 8, cudaMemcpyDeviceToHost, sl.st));
+        CK(cudaMemcpyAsync(lppd_i + i0, d_l, (size_t)nc * 8, cudaMemcpyDeviceToHost, sl.st));
+        CK(cudaMemcpyAsync(var_i + i0, d_v, (size_t)nc * 8, cudaMemcpyDeviceToHost, sl.st));
+        CK(cudaMemcpyAsync(lppdw_i + i0, d_lw, (size_t)nc * 8, cudaMemcpyDeviceToHost, sl.st));
+        CK(cudaMemcpyAsync(recs.data() + (size_t)ci * B2L_STATS_LEN, d_stats, B2L_STATS_LEN * 8,
+                           cudaMemcpyDeviceToHost, sl.st));
+    }
+    for (int s = 0; s < NSLOT; ++s) CK(cudaStreamSynchronize(cx.slot[s].st));
+    if (stats_out) {
+        if (nchunks == 0) {
+            double z[B2L_STATS_LEN] = {0};
+            memcpy(stats_out, z, sizeof(z));
+        } else {
+            int rc = b2l_stats_merge(recs.data(), (int)nchunks, stats_out);
+            if (rc) return rc;
+        }
+    }
+    return 0;
+}

@@ -1,0 +1,263 @@
+"""Thin Python layer over the C ABI: NumPy (host) and torch (device-resident) entry points.
+
+The numerics live in ``csrc/``; this module only computes the two scalars the reference derives in
+Python (``M`` and ``cutoffmin``, pyloo/psis.py:89-90), normalises array layouts into
+(pointer, strides) and turns return codes into exceptions.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+from . import _native
+
+__all__ = [
+    "CUTOFFMIN", "tail_length", "good_k_threshold", "psislw_host", "loo_host", "psislw_cuda",
+    "loo_cuda", "stats_cuda", "stats_merge", "StatsRecord", "row_launch_info", "current_device",
+]
+
+CUTOFFMIN = float(np.log(np.finfo(float).tiny))  # pyloo/psis.py:90
+
+
+def tail_length(n_samples: int, reff: float) -> int:
+    """``M`` with ``cutoff_ind = -M - 1``: the reference's exact Python-float expression
+    (pyloo/psis.py:89, pyloo/base.py:139-141).  Never recomputed on the device."""
+    return int(np.ceil(min(n_samples / 5.0, 3 * (n_samples / reff) ** 0.5)))
+
+
+def good_k_threshold(n_samples: int) -> float:
+    """pyloo/loo.py:249."""
+    return float(min(1 - 1 / np.log10(n_samples), 0.7))
+
+
+def current_device() -> int:
+    """GPU this process drives: LOCAL_RANK under torchrun, else B2L_DEVICE, else 0."""
+    for key in ("B2L_DEVICE", "LOCAL_RANK"):
+        if key in os.environ:
+            return int(os.environ[key])
+    return 0
+
+
+def _check_tail(S: int, M: int) -> None:
+    if M + 1 > S:
+        # the reference fails with IndexError at x[x_sort_ind[cutoff_ind]] (pyloo/psis.py:136)
+        raise IndexError(f"index {-M - 1} is out of bounds for axis 0 with size {S}")
+
+
+class StatsRecord:
+    """Named view of the fixed 32-double shard record (include/psisloo_b200.h)."""
+
+    FIELDS = {
+        "n": 0, "elpd_mean": 1, "elpd_m2": 2, "elpd_sum": 3, "lppd_sum": 4, "p_waic_sum": 5,
+        "waic_mean": 6, "waic_m2": 7, "waic_sum": 8, "k_gt_good": 9, "k_gt_1": 10, "k_inf": 11,
+        "k_nan": 12, "var_gt_04": 13, "elpd_min": 14, "elpd_max": 15, "waic_min": 16,
+        "waic_max": 17, "n_nan_in": 18, "n_pinf_in": 19, "n_ninf_in": 20, "n_fallback": 21,
+        "elpd_nan": 22,
+    }
+
+    def __init__(self, raw):
+        self.raw = np.asarray(raw, dtype=np.float64).reshape(_native.STATS_LEN)
+
+    def __getattr__(self, name):
+        try:
+            return float(self.raw[StatsRecord.FIELDS[name]])
+        except KeyError as err:
+            raise AttributeError(name) from err
+
+    def __repr__(self):
+        return "StatsRecord(" + ", ".join(f"{k}={getattr(self, k):g}" for k in self.FIELDS) + ")"
+
+
+def stats_merge(records) -> StatsRecord:
+    """Chan merge of per-shard records in the given (rank) order -- host arithmetic in the library."""
+    recs = np.ascontiguousarray(np.asarray([np.asarray(getattr(r, "raw", r)) for r in records],
+                                           dtype=np.float64))
+    out = np.empty(_native.STATS_LEN)
+    lib = _native.load()
+    _native.check(lib.b2l_stats_merge(recs.ctypes.data, recs.shape[0], out.ctypes.data))
+    return StatsRecord(out)
+
+
+# --------------------------------------------------------------------------------- host (NumPy)
+def _elem_strides(a: np.ndarray):
+    return tuple(int(s // a.itemsize) for s in a.strides)
+
+
+def _as_strided_f64_2d(a) -> np.ndarray:
+    """float64 2-D array with one unit, non-negative-stride axis (copy only if needed)."""
+    a = np.asarray(a)
+    if a.dtype != np.float64:
+        a = a.astype(np.float64)
+    if a.ndim != 2:
+        raise ValueError("expected a 2-D array")
+    st = _elem_strides(a)
+    ok = all(s >= 0 for s in st) and all(s * a.itemsize == b for s, b in zip(st, a.strides))
+    ok = ok and (st[0] == 1 or st[1] == 1 or a.shape[0] == 1 or a.shape[1] == 1) and a.size > 0
+    # the non-unit stride must not alias rows (broadcast views)
+    if ok and min(a.shape) > 1 and 0 in st:
+        ok = False
+    return a if ok else np.ascontiguousarray(a)
+
+
+def psislw_host(lw_ns: np.ndarray, reff: float = 1.0, *, out=None, device=None, chunk_obs: int = 0):
+    """Batch PSIS on a HOST ``(N, S)`` array (samples on the last axis, any unit-stride layout).
+
+    Returns ``(lw_out, k)``: C-contiguous ``(N, S)`` smoothed log weights and ``(N,)`` Pareto k.
+    The input is never modified (pyloo/psis.py:78)."""
+    lib = _native.load()
+    a = _as_strided_f64_2d(lw_ns)
+    N, S = a.shape
+    M = tail_length(S, reff)
+    _check_tail(S, M)
+    if out is None:
+        out = np.empty((N, S), dtype=np.float64)
+    k = np.empty(N, dtype=np.float64)
+    if N == 0:
+        return out, k
+    sn, ss = _elem_strides(a)
+    osn, oss = _elem_strides(out)
+    dev = current_device() if device is None else int(device)
+    rc = lib.b2l_psislw_host_f64(a.ctypes.data, S, N, ss, sn, M, CUTOFFMIN, out.ctypes.data, oss, osn,
+                                 k.ctypes.data, dev, int(chunk_obs))
+    _native.check(rc)
+    return out, k
+
+
+def loo_host(ll_sn: np.ndarray, reff: float = 1.0, *, waic_only: bool = False, device=None,
+             chunk_obs: int = 0):
+    """Fused pointwise PSIS-LOO + WAIC on a HOST sample-major ``(S, N)`` log-likelihood
+    (ArviZ ``(chain, draw, obs)`` flattened; a transposed ``(N, S)``-contiguous view also works).
+
+    Returns ``dict(elpd_i, pareto_k, lppd_i, var_i, lppdw_i, stats=StatsRecord, M, good_k)``;
+    ``elpd_i`` is on the log scale."""
+    lib = _native.load()
+    a = _as_strided_f64_2d(ll_sn)
+    S, N = a.shape
+    M = tail_length(S, reff)
+    _check_tail(S, M)
+    gk = good_k_threshold(S)
+    outs = [np.empty(N, dtype=np.float64) for _ in range(5)]
+    stats = np.zeros(_native.STATS_LEN)
+    ss, sn = _elem_strides(a)
+    dev = current_device() if device is None else int(device)
+    rc = lib.b2l_loo_host_f64(a.ctypes.data, S, N, ss, sn, M, CUTOFFMIN,
+                              _native.FLAG_WAIC_ONLY if waic_only else 0, gk, *[o.ctypes.data for o in outs],
+                              stats.ctypes.data, dev, int(chunk_obs))
+    _native.check(rc)
+    return {"elpd_i": outs[0], "pareto_k": outs[1], "lppd_i": outs[2], "var_i": outs[3],
+            "lppdw_i": outs[4], "stats": StatsRecord(stats), "M": M, "good_k": gk, "n_samples": S}
+
+
+# --------------------------------------------------------------------------------- device (torch)
+def _torch():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("pyloo_b200 needs a CUDA device and has no CPU fallback")
+    return torch
+
+
+def _stream_ptr(torch, device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _workspace(torch, lib, S, N, M, obs_fastest, device):
+    need = ctypes.c_size_t(0)
+    _native.check(lib.b2l_workspace_bytes(S, N, M, 1 if obs_fastest else 0, ctypes.byref(need)))
+    return torch.empty(max(int(need.value), 256), dtype=torch.uint8, device=device)
+
+
+def psislw_cuda(lw, reff: float = 1.0, *, out=None, want_diag: bool = False, workspace=None):
+    """PSIS on a device-resident float64 tensor ``(N, S)`` (any unit-stride layout); asynchronous
+    on the current stream.  Returns ``(lw_out, k[, diag])`` tensors."""
+    torch = _torch()
+    lib = _native.load()
+    if lw.dtype != torch.float64 or lw.dim() != 2 or not lw.is_cuda:
+        raise ValueError("expected a 2-D float64 CUDA tensor")
+    N, S = lw.shape
+    M = tail_length(S, reff)
+    _check_tail(S, M)
+    sn, ss = lw.stride()
+    if not (ss == 1 or sn == 1 or N == 1 or S == 1):
+        lw = lw.contiguous()
+        sn, ss = lw.stride()
+    if out is None:
+        out = torch.empty((N, S), dtype=torch.float64, device=lw.device)
+    osn, oss = out.stride()
+    k = torch.empty(N, dtype=torch.float64, device=lw.device)
+    diag = torch.zeros((N, _native.DIAG_STRIDE), dtype=torch.float64, device=lw.device) if want_diag else None
+    obs_fast = not (ss == 1 or S == 1) or not (oss == 1 or S == 1)
+    ws = workspace if workspace is not None else _workspace(torch, lib, S, N, M, obs_fast, lw.device)
+    with torch.cuda.device(lw.device):
+        rc = lib.b2l_psislw_dev_f64(lw.data_ptr(), S, N, ss, sn, M, CUTOFFMIN, out.data_ptr(), oss, osn,
+                                    k.data_ptr(), diag.data_ptr() if want_diag else None,
+                                    ws.data_ptr(), ws.numel(), _stream_ptr(torch, lw.device))
+    _native.check(rc)
+    return (out, k, diag) if want_diag else (out, k)
+
+
+def loo_cuda(ll_sn, reff: float = 1.0, *, want_diag: bool = False, workspace=None, counters=None,
+             waic_only: bool = False):
+    """Fused pointwise PSIS-LOO + WAIC on a device-resident float64 ``(S, N)`` tensor (obs-fastest
+    ArviZ layout, or a transposed view of a row-contiguous ``(N, S)`` tensor).  Asynchronous.
+    Returns dict of device tensors ``elpd_i, pareto_k, lppd_i, var_i, lppdw_i, counters[, diag]``."""
+    torch = _torch()
+    lib = _native.load()
+    if ll_sn.dtype != torch.float64 or ll_sn.dim() != 2 or not ll_sn.is_cuda:
+        raise ValueError("expected a 2-D float64 CUDA tensor")
+    S, N = ll_sn.shape
+    M = tail_length(S, reff)
+    _check_tail(S, M)
+    ss, sn = ll_sn.stride()
+    if not (ss == 1 or sn == 1 or N == 1 or S == 1):
+        ll_sn = ll_sn.contiguous()
+        ss, sn = ll_sn.stride()
+    dev = ll_sn.device
+    outs = [torch.empty(N, dtype=torch.float64, device=dev) for _ in range(5)]
+    if counters is None:
+        counters = torch.zeros(4, dtype=torch.int64, device=dev)
+    diag = torch.zeros((N, _native.DIAG_STRIDE), dtype=torch.float64, device=dev) if want_diag else None
+    ws = workspace if workspace is not None else _workspace(torch, lib, S, N, M, not (ss == 1 or S == 1), dev)
+    with torch.cuda.device(dev):
+        rc = lib.b2l_loo_dev_f64(ll_sn.data_ptr(), S, N, ss, sn, M, CUTOFFMIN,
+                                 _native.FLAG_WAIC_ONLY if waic_only else 0, *[o.data_ptr() for o in outs],
+                                 counters.data_ptr(), diag.data_ptr() if want_diag else None,
+                                 ws.data_ptr(), ws.numel(), _stream_ptr(torch, dev))
+    _native.check(rc)
+    res = {"elpd_i": outs[0], "pareto_k": outs[1], "lppd_i": outs[2], "var_i": outs[3],
+           "lppdw_i": outs[4], "counters": counters, "M": M, "n_samples": S, "workspace": ws}
+    if want_diag:
+        res["diag"] = diag
+    return res
+
+
+def stats_cuda(res: dict, good_k: float | None = None, workspace=None):
+    """Shard statistics record (device tensor of 32 doubles) for the outputs of :func:`loo_cuda`."""
+    torch = _torch()
+    lib = _native.load()
+    e = res["elpd_i"]
+    N = e.numel()
+    gk = good_k_threshold(res["n_samples"]) if good_k is None else good_k
+    ws = workspace if workspace is not None else res.get("workspace")
+    if ws is None or ws.numel() < 64 * 1024:
+        ws = torch.empty(64 * 1024, dtype=torch.uint8, device=e.device)
+    stats = torch.empty(_native.STATS_LEN, dtype=torch.float64, device=e.device)
+    with torch.cuda.device(e.device):
+        rc = lib.b2l_stats_dev_f64(e.data_ptr(), res["pareto_k"].data_ptr(), res["lppd_i"].data_ptr(),
+                                   res["var_i"].data_ptr(), res["lppdw_i"].data_ptr(), N, gk,
+                                   res["counters"].data_ptr(), stats.data_ptr(), ws.data_ptr(), ws.numel(),
+                                   _stream_ptr(torch, e.device))
+    _native.check(rc)
+    return stats
+
+
+def row_launch_info(S: int, M: int, mode: str = "psislw") -> dict:
+    """Launch shape the library picks for a row kernel (needs a GPU: queries occupancy)."""
+    lib = _native.load()
+    vals = [ctypes.c_int32(0) for _ in range(5)]
+    _native.check(lib.b2l_row_launch_info(S, M, 0 if mode == "psislw" else 1, *[ctypes.byref(v) for v in vals]))
+    keys = ("grid", "block", "smem_bytes", "ctas_per_sm", "nbuf")
+    return {k: int(v.value) for k, v in zip(keys, vals)}
