@@ -139,7 +139,7 @@ def _calculate_ics(compare_dict, scale, ic, var_name):
     return out, scale, ic
 
 
-def loo_compare(compare_dict, ic=None, method="stacking", b_samples=1000, alpha=1, seed=None, scale=None,
+def loo_compare(compare_dict, ic="loo", method="stacking", b_samples=1000, alpha=1, seed=None, scale=None,
                 var_name=None, observations=None, estimator=None, K=None, folds=None, stratify=None,
                 random_seed=None):
     """Compare models by ELPD (PSIS-LOO or WAIC) -- same signature and DataFrame as ``pyloo.loo_compare``."""
@@ -155,9 +155,7 @@ def loo_compare(compare_dict, ic=None, method="stacking", b_samples=1000, alpha=
     method = method.lower()
     if method not in _METHODS:
         raise ValueError("Method must be 'stacking', 'BB-pseudo-BMA' or 'pseudo-BMA'")
-    if ic is None:
-        ic = "loo" if not any(isinstance(v, ELPDData) for v in compare_dict.values()) else None
-    if ic is not None and ic not in ("loo", "waic", "kfold"):
+    if ic not in ("loo", "waic", "kfold"):
         raise ValueError("ic must be 'loo', 'waic', or 'kfold'")
     if ic == "kfold" or observations is not None:
         raise NotImplementedError("ic='kfold' and subsampled comparison need model refits / subsampling "

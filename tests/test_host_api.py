@@ -1,0 +1,176 @@
+"""CPU-only tests: host logic of the reference-facing API (no compute calls), the C-ABI library
+loading and exporting every symbol include/psisloo_b200.h declares, data ingress, ELPDData."""
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import pyloo_b200 as pl
+from pyloo_b200 import _native, engine
+from pyloo_b200.data import LiteDataArray, from_dict, get_log_likelihood, sample_major, to_inference_data
+from pyloo_b200.ess import ess_mean
+from b2l_testutil import ROOT, has_cuda
+
+
+def test_library_builds_loads_and_exports_header_symbols():
+    _native.build()
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    header = open(os.path.join(ROOT, "include", "psisloo_b200.h")).read()
+    declared = set(re.findall(r"\b(b2l_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_native.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.b2l_version() == 100
+
+
+def test_no_cpu_fallback_without_gpu():
+    if has_cuda():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pl.psislw(np.random.default_rng(0).normal(size=(4, 100)))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        engine.loo_host(np.zeros((100, 3)))
+
+
+def test_stats_merge_is_host_arithmetic():
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=1000)
+    recs = []
+    for part in (x[:300], x[300:]):
+        r = np.zeros(32)
+        r[0] = len(part); r[1] = part.mean(); r[2] = ((part - part.mean()) ** 2).sum(); r[3] = part.sum()
+        r[6] = part.mean(); r[7] = r[2]; r[8] = part.sum()
+        r[14] = r[16] = part.min(); r[15] = r[17] = part.max()
+        recs.append(r)
+    m = engine.stats_merge(recs)
+    assert m.n == 1000
+    np.testing.assert_allclose(m.elpd_mean, x.mean(), rtol=1e-13)
+    np.testing.assert_allclose(m.elpd_m2, ((x - x.mean()) ** 2).sum(), rtol=1e-12)
+    np.testing.assert_allclose(m.elpd_sum, x.sum(), rtol=1e-13)
+    assert m.elpd_min == x.min() and m.elpd_max == x.max()
+
+
+def test_tail_length_and_good_k_follow_reference_expressions():
+    assert engine.tail_length(4000, 0.9) == 200       # pyloo/psis.py:89
+    assert engine.tail_length(2000, 1.0) == 135
+    assert engine.good_k_threshold(2000) == 0.7 - 0.0 if 1 - 1 / np.log10(2000) > 0.7 else True
+    assert engine.good_k_threshold(100) == pytest.approx(0.5)   # pyloo/loo.py:249
+    assert engine.CUTOFFMIN == pytest.approx(-708.3964185322641)
+
+
+def test_argument_errors_match_reference_classes():
+    idata = from_dict(posterior={"mu": np.zeros((2, 50))}, log_likelihood={"y": np.zeros((2, 50, 3))})
+    with pytest.raises(TypeError, match="Valid scale values"):      # test_loo.py:64-68
+        pl.loo(idata, scale="bad", reff=1.0)
+    with pytest.raises(ValueError, match="Invalid method"):          # test_loo.py:219-221
+        pl.loo(idata, method="nope", reff=1.0)
+    with pytest.raises(ValueError, match="Jacobian adjustment requires pointwise"):
+        pl.loo(idata, jacobian=np.zeros(3), pointwise=False, reff=1.0)
+    no_ll = from_dict(posterior={"mu": np.zeros((2, 50))})
+    with pytest.raises(TypeError, match="log likelihood not found"):  # test_loo.py:71-74
+        pl.loo(no_ll)
+    two = from_dict(log_likelihood={"a": np.zeros((2, 50, 3)), "b": np.zeros((2, 50, 3))})
+    with pytest.raises(TypeError, match="Found several log likelihood arrays"):  # test_loo.py:190-198
+        pl.loo(two, reff=1.0)
+    with pytest.raises(TypeError, match="No log likelihood data named"):
+        pl.loo(two, var_name="zzz", reff=1.0)
+    only_ll = from_dict(log_likelihood={"y": np.zeros((2, 50, 3))})
+    with pytest.raises(TypeError, match="Must be able to extract a posterior"):  # test_loo.py:77-86
+        pl.loo(only_ll)
+    with pytest.raises(ValueError, match="Invalid method"):          # base.py:100-107
+        pl.compute_importance_weights(np.zeros((3, 10)), method="xx")
+    with pytest.raises(ValueError, match="log_weights must be provided"):
+        pl.compute_importance_weights(None)
+    with pytest.raises(ValueError, match="__sample__"):
+        pl.compute_importance_weights(LiteDataArray(np.zeros((3, 10)), ("a", "b")))
+    with pytest.raises(TypeError, match="must be a dictionary"):     # test_compare.py:188-216
+        pl.loo_compare([1, 2])
+    with pytest.raises(ValueError, match="at least two models"):
+        pl.loo_compare({"a": idata})
+    with pytest.raises(ValueError, match="Scale must be"):
+        pl.loo_compare({"a": idata, "b": idata}, scale="x")
+    with pytest.raises(ValueError, match="Method must be"):
+        pl.loo_compare({"a": idata, "b": idata}, method="x")
+    with pytest.raises(ValueError, match="ic must be"):
+        pl.loo_compare({"a": idata, "b": idata}, ic="x")
+    with pytest.raises(ValueError, match="Lists and tuples"):
+        to_inference_data([1, 2, 3])
+
+
+def test_sample_major_is_a_view_in_stack_order():
+    rng = np.random.default_rng(1)
+    arr = rng.normal(size=(4, 25, 3, 2))
+    da = LiteDataArray(arr, ("chain", "draw", "d1", "d2"))
+    mat, obs_dims, obs_shape = sample_major(da)
+    assert mat.shape == (100, 6) and obs_dims == ("d1", "d2") and obs_shape == (3, 2)
+    assert np.shares_memory(mat, arr)
+    stacked = da.stack(__sample__=("chain", "draw"))          # (d1, d2, sample): chain outer, draw inner
+    assert stacked.dims == ("d1", "d2", "__sample__")
+    assert np.array_equal(stacked.values.reshape(6, 100).T, mat)
+    tr = da.transpose("draw", "chain", ...)                   # transposed model (helpers.py:79-83)
+    mat2, _, _ = sample_major(tr)
+    assert np.array_equal(mat2, mat)
+    assert hasattr(stacked, "__sample__") and len(stacked.__sample__) == 100   # psis.py:79-80
+
+
+def test_get_log_likelihood_rules():
+    idata = from_dict(log_likelihood={"obs": np.zeros((2, 10, 4))})
+    assert get_log_likelihood(idata).name == "obs"
+    assert get_log_likelihood(idata, "obs").shape == (2, 10, 4)
+
+
+def test_rcparams_contract():
+    rc = pl.rcParams
+    assert rc["stats.ic_pointwise"] is False and rc["stats.ic_scale"] == "log"
+    with pytest.raises(ValueError):
+        rc["stats.ic_scale"] = "bogus"
+    with pytest.raises(KeyError):
+        rc["nope"] = 1
+    with pytest.raises(TypeError):
+        del rc["stats.ic_scale"]
+    rc["stats.ic_scale"] = "Deviance"
+    assert rc["stats.ic_scale"] == "deviance"
+    rc["stats.ic_scale"] = "log"
+    assert sorted(rc) == ["plot.backend", "stats.ic_pointwise", "stats.ic_scale"]
+
+
+def test_elpddata_report_matches_reference_layout():
+    k = np.array([0.1, 0.8, 1.2, 0.3, 0.2, 0.1, 0.0, 0.5])
+    e = pl.ELPDData(
+        data=[-30.78, 1.35, 0.95, 0.48, 2000, 8, True, LiteDataArray(np.zeros(8), ("obs",)), "log", 61.56, 2.69,
+              LiteDataArray(k, ("obs",)), 0.7, 8],
+        index=["elpd_loo", "se", "p_loo", "p_loo_se", "n_samples", "n_data_points", "warning", "loo_i", "scale",
+               "looic", "looic_se", "pareto_k", "good_k", "subsample_size"])
+    text = str(e)
+    assert "Computed from 2000 posterior samples and 8 observations log-likelihood matrix." in text
+    assert "elpd_loo   -30.78      1.35" in text and "p_loo       0.95        0.48" in text
+    assert "looic      61.56       2.69" in text
+    assert "(-Inf, 0.70]   (good)      6   75.0%" in text and "(1, Inf)   (very bad)    1    12.5%" in text
+    assert "There has been a warning during the calculation." in text
+    assert e.n_samples == 2000 and e.n_data_points == 8 and e.warning
+    ref_path = "/root/reference/pyloo/elpd.py"
+    if os.path.exists(ref_path):  # same text as the reference's own class (build container only)
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("ref_elpd", ref_path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        ref = mod.ELPDData(data=list(e.values), index=list(e.index))
+        assert str(ref) == text
+        e2 = pl.ELPDData(data=list(e.values)[:11] + [0.7, 8], index=list(e.index)[:11] + ["good_k", "subsample_size"])
+        ref2 = mod.ELPDData(data=list(e2.values), index=list(e2.index))
+        assert str(ref2) == str(e2)
+
+
+def test_ess_mean_sane():
+    rng = np.random.default_rng(3)
+    iid = rng.normal(size=(4, 1000))
+    assert 0.7 * 4000 < ess_mean(iid) < 1.4 * 4000
+    ar = np.zeros((4, 2000))
+    eps = rng.normal(size=(4, 2000))
+    for t in range(1, 2000):
+        ar[:, t] = 0.9 * ar[:, t - 1] + eps[:, t]
+    # AR(1) with phi = 0.9: ESS ~ N (1 - phi) / (1 + phi) ~ 0.053 N
+    assert 0.02 * 8000 < ess_mean(ar) < 0.12 * 8000
