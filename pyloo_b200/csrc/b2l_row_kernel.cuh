@@ -5,10 +5,13 @@
 // (`_gpdfit`), :211-231 (`_gpinv`) and pyloo/utils.py:344-359 (`_logsumexp`); in LOO mode also
 // pyloo/loo.py:286-289,319-337 (`lw += ll`, `loo_i`, `lppd_i`) and pyloo/waic.py:137-145.
 //
-// Selection is exact: draws are keyed by the order-preserving 64-bit image of x = fl(r - max r)
-// (formed exactly as psis.py:134 does), a sampled threshold isolates a candidate set that is
-// bitonic-sorted in shared memory, and the (M+1)-th largest is read from the sorted candidates;
-// a bit-wise binary search over the key space is the exact fallback (ties, degenerate rows).
+// Selection is exact.  x = fl(r - max r) is formed exactly as psis.py:134 does.  A threshold guessed
+// from a 1-per-thread sample (warp-shuffle sorts) isolates ~1.9 (M+1) candidates; each candidate is
+// packed as (31-bit linear quantisation of x - tau | draw index) into ONE 64-bit word, so a single
+// shared-memory bitonic sort orders them by (value, index); quantisation collisions between
+// distinct values are detected after the sort and sent to the full-key path, and a bit-wise binary
+// search over the 64-bit ordered key space is the exact fallback for degenerate rows (ties,
+// constant rows).  The (M+1)-th largest is then read from the sorted candidates.
 #pragma once
 
 #include "b2l_common.cuh"
@@ -19,6 +22,7 @@ enum : int { MODE_PSISLW = 0, MODE_LOO = 1 };
 
 constexpr int GPD_MAX_GRID = 128;  // m = 30 + floor(sqrt(n)) <= 128  <=>  n <= 9603
 constexpr int DIAG_STRIDE = 8;
+constexpr int POOL_PER_WARP = 8;   // per-warp top sample keys pooled for the threshold guess
 
 struct RowParams {
     const double* in;      // row i = in + i * in_stride, S contiguous doubles
@@ -36,35 +40,38 @@ struct RowParams {
     int S;
     int M;         // tail length, cutoff_ind = -M-1 (computed by the caller, pyloo/psis.py:89)
     int cap;       // candidate capacity (power of two)
-    int ns;        // threshold sample size (power of two)
-    int r0;        // initial sample rank
+    int r0;        // initial pooled sample rank for the threshold guess
     int nbuf;      // row buffers per CTA (1 or 2)
     int use_bulk;  // 1: 16 B aligned rows -> bulk TMA; 0: cooperative LDG/STG
     int waic_only; // LOO mode: skip PSIS, only lppd / variance outputs
+    int force_legacy;  // testing: always take the full-key (unpacked) candidate path
     double cutoffmin;
 };
 
 struct RowSmemLayout {
-    size_t row_bytes, off_row, off_ckey, off_cidx, off_tbuf, off_gb, off_gk, off_gw, off_gflag,
-        off_part, off_red, off_ctl, off_bar, total;
+    size_t row_bytes, off_row, off_ckey, off_cidx, off_tbuf, off_tx, off_ts, off_gb, off_gk, off_gw,
+        off_gflag, off_part, off_red, off_ctl, off_bar, total;
 };
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Same carve-up on host (launch size) and device.
-__host__ __device__ inline RowSmemLayout row_smem_layout(int S, int M, int cap, int ns, int nbuf,
-                                                         int nt) {
+__host__ __device__ inline RowSmemLayout row_smem_layout(int S, int M, int cap, int nbuf, int nt) {
     RowSmemLayout L;
     size_t o = 0;
     L.row_bytes = align_up((size_t)S * 8, 128);
     L.off_row = o;
     o += L.row_bytes * (size_t)nbuf;
-    L.off_ckey = o;
+    L.off_ckey = o;  // packed candidates (u64) alias the full keys of the legacy path
     o += (size_t)cap * 8;
     L.off_cidx = o;
     o += align_up((size_t)cap * 4, 16);
-    L.off_tbuf = o;
+    L.off_tbuf = o;  // tail t_i, then smoothed values
     o += align_up((size_t)(M + 1) * 8, 16);
+    L.off_tx = o;    // tail raw x_i (ascending)
+    o += align_up((size_t)(M + 1) * 8, 16);
+    L.off_ts = o;    // tail draw indices
+    o += align_up((size_t)(M + 1) * 4, 16);
     L.off_gb = o;
     o += GPD_MAX_GRID * 8;
     L.off_gk = o;
@@ -72,31 +79,78 @@ __host__ __device__ inline RowSmemLayout row_smem_layout(int S, int M, int cap, 
     L.off_gw = o;
     o += GPD_MAX_GRID * 8;
     L.off_gflag = o;
-    o += GPD_MAX_GRID * 4;
-    L.off_part = o;  // sample keys (ns * 8) alias the GPD partial products (nt * 12)
-    size_t a = (size_t)ns * 8, b = align_up((size_t)nt * 12, 16);
-    o += (a > b ? a : b);
+    o += GPD_MAX_GRID * 4 * 2;  // flags + compact list of flagged grid points
+    L.off_part = o;  // sample pool ((nt/32) * 8 keys) aliases the GPD partial products (nt * 12)
+    o += align_up((size_t)nt * 12, 16);
     L.off_red = o;
     o += 128 * 8;
     L.off_ctl = o;
-    o += 16 * 4;
+    o += 16 * 8;
     L.off_bar = o;
     o += 2 * 8;
     L.total = align_up(o, 128);
     return L;
 }
 
+// ------------------------------------------------------------------ fast exp for x <= 0
+// exp(x), x in [-708, 0]: Cody-Waite reduction, degree-13 Taylor/Horner, exponent insertion.
+// Max error ~1 ulp.  Anything below -708 (denormal results, -inf) goes to the library routine.
+__device__ __forceinline__ double exp_nonpos(double x) {
+    if (x < -708.0) return exp(x);
+    const double t = fma(x, 1.4426950408889634074, 6755399441055744.0);
+    const int ni = __double2loint(t);
+    const double n = t - 6755399441055744.0;
+    double r = fma(n, -6.93147180369123816490e-01, x);
+    r = fma(n, -1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;            // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);          // 1/12!
+    p = fma(p, r, 2.505210838544172e-08);         // 1/11!
+    p = fma(p, r, 2.755731922398589e-07);         // 1/10!
+    p = fma(p, r, 2.7557319223985893e-06);        // 1/9!
+    p = fma(p, r, 2.48015873015873e-05);          // 1/8!
+    p = fma(p, r, 1.984126984126984e-04);         // 1/7!
+    p = fma(p, r, 1.388888888888889e-03);         // 1/6!
+    p = fma(p, r, 8.333333333333333e-03);         // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);        // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);        // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (ni << 20), __double2loint(p));
+}
+
+// ------------------------------------------------------------------ warp-level helpers
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m) {
+    return (uint64_t)__shfl_xor_sync(FULL, (long long)v, m);
+}
+// ascending across lanes (lane 31 ends with the largest); 15 shuffle stages, no shared memory
+__device__ __forceinline__ uint64_t warp_sort32(uint64_t v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const uint64_t o = shfl_xor_u64(v, j);
+            const bool up = ((lane & k) == 0);
+            const bool lower = ((lane & j) == 0);
+            const uint64_t lo = (v < o) ? v : o, hi = (v < o) ? o : v;
+            v = (up == lower) ? lo : hi;
+        }
+    }
+    return v;
+}
+
 // ------------------------------------------------------------------ bitonic sorts (shared memory)
+// single 64-bit words, ascending
 template <int NT>
-__device__ void bitonic_sort_keys(uint64_t* key, int n) {
+__device__ void bitonic_sort_u64(uint64_t* key, int n) {
     for (int k = 2; k <= n; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int t = threadIdx.x; t < (n >> 1); t += NT) {
-                int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                int l = i | j;
-                bool up = ((i & k) == 0);
-                uint64_t a = key[i], b = key[l];
-                if ((a > b) == up) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                const uint64_t a = key[i], b = key[l];
+                if ((a > b) == ((i & k) == 0)) {
                     key[i] = b;
                     key[l] = a;
                 }
@@ -111,12 +165,12 @@ __device__ void bitonic_sort_pairs(uint64_t* key, int* idx, int n) {
     for (int k = 2; k <= n; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int t = threadIdx.x; t < (n >> 1); t += NT) {
-                int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                int l = i | j;
-                bool up = ((i & k) == 0);
-                uint64_t a = key[i], b = key[l];
-                int ia = idx[i], ib = idx[l];
-                bool gt = (a > b) || (a == b && ia > ib);
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                const bool up = ((i & k) == 0);
+                const uint64_t a = key[i], b = key[l];
+                const int ia = idx[i], ib = idx[l];
+                const bool gt = (a > b) || (a == b && ia > ib);
                 if (gt == up) {
                     key[i] = b;
                     key[l] = a;
@@ -135,9 +189,11 @@ struct GpdScratch {
     double* ks;    // [GPD_MAX_GRID] sum_i log1p(-b_j t_i), then L_j (psis.py:190-191)
     double* w;     // [GPD_MAX_GRID] posterior weights              (psis.py:192-198)
     int* flag;     // [GPD_MAX_GRID] grid points that need the literal log1p path
+    int* list;     // [GPD_MAX_GRID] compact list of flagged grid points
     double* part;  // [NT] partial products
     int* parte;    // [NT] partial exponents
     double* red;   // reduction scratch
+    int* ctl;      // small control words
 };
 
 __device__ __forceinline__ bool rescale_pos(double& P, int& E) {
@@ -179,70 +235,97 @@ __device__ void gpdfit_block(const double* t, int n, GpdScratch g, double& k_out
     }
     __syncthreads();
 
-    // ---- product-form profile: thread = (grid point j, chunk of t)
-    const int JW = (m + 31) >> 5;          // warps per chunk
-    const int NCH = (NT / 32) / JW;        // chunks
+    // ---- product-form profile: thread = (chunk of t, grid point j), flattened over the CTA
+    const int NCH = NT / m;                      // chunks (>= 2 since m <= 128 <= NT / 2)
+    const int len = (n + NCH - 1) / NCH;
     {
-        const int jw = wid % JW, ch = wid / JW;
-        const int j = (jw << 5) + lane;
+        const int ch = tid / m, j = tid - ch * m;
         double P = 1.0;
-        int E = 0;
+        int E = 0, sgn = 0;
         bool ok = true;
-        if (j < m && ch < NCH) {
+        if (ch < NCH) {
             const double bmag = fmax(fabs(g.b[0]), fabs(g.b[m - 1]));
             const double fmx = 1.0 + bmag * tn;
-            const int R = (fmx < 0x1p120) ? 8 : ((fmx < 0x1p250) ? 4 : 1);
-            const int len = (n + NCH - 1) / NCH;
             const int i0 = ch * len, i1 = min(n, i0 + len);
             const double nb = -g.b[j];
-            int cnt = 0;
-            for (int i = i0; i < i1; ++i) {
-                double f = fma(nb, t[i], 1.0);
-                ok = ok && (f > 0.0);
-                P *= f;
-                if (++cnt == R) {
-                    cnt = 0;
+            if (fmx < 0x1p120) {  // common case: rescale every 8 factors, sign check by OR of the high words
+                int i = i0;
+                for (; i + 8 <= i1; i += 8) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const double f = fma(nb, t[i + u], 1.0);
+                        sgn |= __double2hiint(f);
+                        P *= f;
+                    }
                     ok = rescale_pos(P, E) && ok;
                 }
+                for (; i < i1; ++i) {
+                    const double f = fma(nb, t[i], 1.0);
+                    sgn |= __double2hiint(f);
+                    P *= f;
+                }
+                ok = rescale_pos(P, E) && ok;
+            } else {
+                const int R = (fmx < 0x1p250) ? 4 : 1;
+                int cnt = 0;
+                for (int i = i0; i < i1; ++i) {
+                    const double f = fma(nb, t[i], 1.0);
+                    sgn |= __double2hiint(f);
+                    P *= f;
+                    if (++cnt == R) {
+                        cnt = 0;
+                        ok = rescale_pos(P, E) && ok;
+                    }
+                }
+                ok = rescale_pos(P, E) && ok;
             }
-            ok = rescale_pos(P, E) && ok;
+            ok = ok && (sgn >= 0);
+            if (!ok) g.flag[j] = 1;  // benign race: all writers store 1
         }
         g.part[tid] = P;
         g.parte[tid] = E;
-        if (!ok && j < m) g.flag[j] = 1;  // benign race: all writers store 1
     }
     __syncthreads();
     if (tid < m && !g.flag[tid]) {
-        const int jw = tid >> 5, l = tid & 31;
         double P = 1.0;
         int E = 0;
         for (int ch = 0; ch < NCH; ++ch) {
-            const int slot = ((ch * JW + jw) << 5) + l;
-            P *= g.part[slot];
-            E += g.parte[slot];
+            P *= g.part[ch * m + tid];
+            E += g.parte[ch * m + tid];
             rescale_pos(P, E);
         }
         g.ks[tid] = log(P) + (double)E * 0.6931471805599453094;
     }
-    __syncthreads();
-    // ---- literal path for flagged grid points (block-uniform loop)
-    for (int j = 0; j < m; ++j) {
-        if (g.flag[j]) {
-            const double nb = -g.b[j];
-            double acc = 0.0;
-            for (int i = tid; i < n; i += NT) acc += log1p(nb * t[i]);
-            acc = block_sum<NT>(acc, g.red);
-            if (tid == 0) g.ks[j] = acc;
+    // ---- compact list of flagged grid points (warp 0), then the literal log1p path for each
+    if (wid == 0) {
+        int nf = 0;
+        for (int base = 0; base < m; base += 32) {
+            const int j = base + lane;
+            const bool f = (j < m) && g.flag[j];
+            const unsigned mask = __ballot_sync(FULL, f);
+            if (f) g.list[nf + __popc(mask & ((1u << lane) - 1u))] = j;
+            nf += __popc(mask);
         }
+        if (lane == 0) g.ctl[1] = nf;
     }
     __syncthreads();
+    const int nflag = g.ctl[1];
+    for (int q = 0; q < nflag; ++q) {
+        const int j = g.list[q];
+        const double nb = -g.b[j];
+        double acc = 0.0;
+        for (int i = tid; i < n; i += NT) acc += log1p(nb * t[i]);
+        acc = block_sum<NT>(acc, g.red);
+        if (tid == 0) g.ks[j] = acc;
+    }
+    if (nflag) __syncthreads();
     // ---- profile log-likelihood L_j (psis.py:191)
     bool fin = true;
     if (tid < m) {
         const double kj = g.ks[tid] / (double)n;
-        const double L = (double)n * (log(-(g.b[tid] / kj)) - kj - 1.0);
-        g.ks[tid] = L;
-        fin = is_finite(L);
+        const double Lj = (double)n * (log(-(g.b[tid] / kj)) - kj - 1.0);
+        g.ks[tid] = Lj;
+        fin = is_finite(Lj);
     }
     const int allfin = __syncthreads_and(fin ? 1 : 0);
     // ---- weights (psis.py:192): 1 / sum_l exp(L_l - L_j)
@@ -304,25 +387,32 @@ __device__ void gpdfit_block(const double* t, int n, GpdScratch g, double& k_out
 template <int NT, int MODE>
 __global__ void __launch_bounds__(NT, (NT <= 256) ? 3 : 1) psis_row_kernel(const RowParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const RowSmemLayout L = row_smem_layout(p.S, p.M, p.cap, p.ns, p.nbuf, NT);
-    uint64_t* ckey = reinterpret_cast<uint64_t*>(smem_raw + L.off_ckey);
+    constexpr int NW = NT / 32;
+    const RowSmemLayout L = row_smem_layout(p.S, p.M, p.cap, p.nbuf, NT);
+    uint64_t* ckey = reinterpret_cast<uint64_t*>(smem_raw + L.off_ckey);  // packed or full keys
     int* cidx = reinterpret_cast<int*>(smem_raw + L.off_cidx);
     double* tbuf = reinterpret_cast<double*>(smem_raw + L.off_tbuf);
-    uint64_t* skey = reinterpret_cast<uint64_t*>(smem_raw + L.off_part);
+    double* tx = reinterpret_cast<double*>(smem_raw + L.off_tx);
+    int* ts = reinterpret_cast<int*>(smem_raw + L.off_ts);
+    uint64_t* pool = reinterpret_cast<uint64_t*>(smem_raw + L.off_part);
     double* red = reinterpret_cast<double*>(smem_raw + L.off_red);
     int* ctl = reinterpret_cast<int*>(smem_raw + L.off_ctl);
+    uint64_t* ctl64 = reinterpret_cast<uint64_t*>(smem_raw + L.off_ctl + 32);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L.off_bar);
     GpdScratch g;
     g.b = reinterpret_cast<double*>(smem_raw + L.off_gb);
     g.ks = reinterpret_cast<double*>(smem_raw + L.off_gk);
     g.w = reinterpret_cast<double*>(smem_raw + L.off_gw);
     g.flag = reinterpret_cast<int*>(smem_raw + L.off_gflag);
+    g.list = g.flag + GPD_MAX_GRID;
     g.part = reinterpret_cast<double*>(smem_raw + L.off_part);
     g.parte = reinterpret_cast<int*>(smem_raw + L.off_part + (size_t)NT * 8);
     g.red = red;
+    g.ctl = ctl;
 
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int S = p.S, M = p.M, cap = p.cap, ns = p.ns;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int S = p.S, M = p.M, cap = p.cap;
+    const int S2 = S >> 1;
     const uint32_t row_tx = (uint32_t)S * 8u;
     const double NEG_INF = -inf_f64();
 
@@ -342,6 +432,7 @@ __global__ void __launch_bounds__(NT, (NT <= 256) ? 3 : 1) psis_row_kernel(const
     for (int it = 0; row < p.n_rows; row += gridDim.x, ++it) {
         const int bsel = (p.nbuf == 2) ? (it & 1) : 0;
         double* rbuf = reinterpret_cast<double*>(smem_raw + L.off_row + (size_t)bsel * L.row_bytes);
+        const double2* rbuf2 = reinterpret_cast<const double2*>(rbuf);
         const long long nrow = row + gridDim.x;
 
         // ---------------- stage the row
@@ -362,62 +453,100 @@ __global__ void __launch_bounds__(NT, (NT <= 256) ? 3 : 1) psis_row_kernel(const
             __syncthreads();
         }
 
-        // ---------------- pass A: extrema, NaN/inf census (and sum for the WAIC variance)
+        // ---------------- pass A (fast): extrema and sum; any NaN/inf only raises a flag
         double a_max = NEG_INF, a_min = inf_f64(), a_sum = 0.0;
         int c_nan = 0, c_pinf = 0, c_ninf = 0;
-        for (int s = tid; s < S; s += NT) {
-            double v = rbuf[s];
-            if (v != v) {
-                ++c_nan;
-                if (MODE == MODE_LOO) {  // pyloo/loo.py:227: NaN -> -1e10
-                    v = -1e10;
-                    rbuf[s] = v;
-                }
-            }
-            if (MODE == MODE_LOO || v == v) {
-                a_max = fmax(a_max, v);
-                a_min = fmin(a_min, v);
-                a_sum += v;
-                if (!is_finite(v)) {
-                    if (v > 0) ++c_pinf; else ++c_ninf;
-                }
-            }
-        }
         {
-            a_max = warp_max(a_max);
-            a_min = warp_min(a_min);
-            a_sum = warp_sum(a_sum);
-            int packed_inf = warp_isum(c_pinf), packed_ninf = warp_isum(c_ninf);
-            c_nan = warp_isum(c_nan);
+            double m0 = NEG_INF, m1 = NEG_INF, n0 = inf_f64(), n1 = inf_f64(), s0 = 0.0, s1 = 0.0;
+            int spec = 0;  // max over |hi word|: >= 0x7ff00000 <=> some inf / NaN
+            for (int i = tid; i < S2; i += NT) {
+                const double2 v = rbuf2[i];
+                m0 = (v.x > m0) ? v.x : m0;
+                m1 = (v.y > m1) ? v.y : m1;
+                spec = max(spec, max(__double2hiint(v.x) & 0x7fffffff, __double2hiint(v.y) & 0x7fffffff));
+                if (MODE == MODE_LOO) {
+                    n0 = (v.x < n0) ? v.x : n0;
+                    n1 = (v.y < n1) ? v.y : n1;
+                    s0 += v.x;
+                    s1 += v.y;
+                }
+            }
+            if ((S & 1) && tid == 0) {
+                const double v = rbuf[S - 1];
+                m0 = (v > m0) ? v : m0;
+                spec = max(spec, __double2hiint(v) & 0x7fffffff);
+                if (MODE == MODE_LOO) {
+                    n0 = (v < n0) ? v : n0;
+                    s0 += v;
+                }
+            }
+            m0 = warp_max(fmax(m0, m1));
+            spec = __reduce_max_sync(FULL, spec);
+            if (MODE == MODE_LOO) {
+                n0 = warp_min(fmin(n0, n1));
+                s0 = warp_sum(s0 + s1);
+            }
             __syncthreads();
             if (lane == 0) {
-                double* r = red + (tid >> 5) * 6;
-                r[0] = a_max; r[1] = a_min; r[2] = a_sum;
-                r[3] = (double)c_nan; r[4] = (double)packed_inf; r[5] = (double)packed_ninf;
+                double* r = red + wid * 4;
+                r[0] = m0; r[1] = n0; r[2] = s0;
+                reinterpret_cast<int*>(r + 3)[0] = spec;
             }
             __syncthreads();
             a_max = red[0]; a_min = red[1]; a_sum = red[2];
-            double dn = red[3], dp = red[4], dm = red[5];
+            int sp = reinterpret_cast<int*>(red + 3)[0];
 #pragma unroll
-            for (int w = 1; w < NT / 32; ++w) {
-                a_max = fmax(a_max, red[w * 6 + 0]);
-                a_min = fmin(a_min, red[w * 6 + 1]);
-                a_sum += red[w * 6 + 2];
-                dn += red[w * 6 + 3]; dp += red[w * 6 + 4]; dm += red[w * 6 + 5];
+            for (int w = 1; w < NW; ++w) {
+                a_max = fmax(a_max, red[w * 4 + 0]);
+                a_min = fmin(a_min, red[w * 4 + 1]);
+                a_sum += red[w * 4 + 2];
+                sp = max(sp, reinterpret_cast<int*>(red + w * 4 + 3)[0]);
             }
-            c_nan = (int)dn; c_pinf = (int)dp; c_ninf = (int)dm;
             __syncthreads();
-        }
-        if (tid == 0 && p.counters && (c_nan | c_pinf | c_ninf)) {
-            if (c_nan) atomicAdd(&p.counters[0], (unsigned long long)c_nan);
-            if (c_pinf) atomicAdd(&p.counters[1], (unsigned long long)c_pinf);
-            if (c_ninf) atomicAdd(&p.counters[2], (unsigned long long)c_ninf);
+            if (sp >= 0x7ff00000) {
+                // ---------------- census (slow, rare): NaN / inf counts, NaN -> -1e10 in LOO mode
+                a_max = NEG_INF; a_min = inf_f64(); a_sum = 0.0;
+                for (int s = tid; s < S; s += NT) {
+                    double v = rbuf[s];
+                    if (v != v) {
+                        ++c_nan;
+                        if (MODE == MODE_LOO) {  // pyloo/loo.py:227
+                            v = -1e10;
+                            rbuf[s] = v;
+                        }
+                    }
+                    if (MODE == MODE_LOO || v == v) {
+                        a_max = fmax(a_max, v);
+                        a_min = fmin(a_min, v);
+                        a_sum += v;
+                        if (!is_finite(v)) {
+                            if (v > 0) ++c_pinf; else ++c_ninf;
+                        }
+                    }
+                }
+                a_max = block_max<NT>(a_max, red);
+                a_min = block_min<NT>(a_min, red);
+                a_sum = block_sum<NT>(a_sum, red);
+                c_nan = block_isum<NT>(c_nan, red);
+                c_pinf = block_isum<NT>(c_pinf, red);
+                c_ninf = block_isum<NT>(c_ninf, red);
+                __syncthreads();
+                if (tid == 0 && p.counters) {
+                    if (c_nan) atomicAdd(&p.counters[0], (unsigned long long)c_nan);
+                    if (c_pinf) atomicAdd(&p.counters[1], (unsigned long long)c_pinf);
+                    if (c_ninf) atomicAdd(&p.counters[2], (unsigned long long)c_ninf);
+                }
+            }
         }
 
         // r = raw log weight: PSISLW r = v ; LOO r = -ll (pyloo/loo.py:286-288)
         const double mx = (MODE == MODE_LOO) ? -a_min : a_max;  // max_s r_s
         const double ll_max = a_max;
         const double ll_mean = a_sum / (double)S;
+        auto xval = [&](int s) -> double {  // x_s = fl(r_s - max r), psis.py:134
+            const double v = rbuf[s];
+            return ((MODE == MODE_LOO) ? -v : v) - mx;
+        };
 
         // Rows on which the reference produces no tail at all (NaN / inf arithmetic, App. D)
         bool run_psis;
@@ -426,79 +555,146 @@ __global__ void __launch_bounds__(NT, (NT <= 256) ? 3 : 1) psis_row_kernel(const
 
         double kk = inf_f64(), sigma = nan_f64(), lse = nan_f64();
         double c = nan_f64(), body = 0.0, tails = 0.0, lsum = 0.0, vsum = 0.0;
-        int n = 0, C = 0, attempts = 0, tail0 = 0;
+        int n = 0, C = 0, attempts = 0;
         bool smooth = false;
 
         if (run_psis) {
-            // ---------------- threshold guess from a sorted sample
+            // ---------------- threshold guess: 1 sample per thread, warp sorts, pooled per-warp top 8
             const bool sampling = S > cap;
             int R = p.r0;
             if (sampling) {
-                for (int j = tid; j < ns; j += NT) {
-                    const int idx = (int)(((long long)j * S) / ns);
-                    const double v = rbuf[idx];
-                    skey[j] = key_of(((MODE == MODE_LOO) ? -v : v) - mx);
-                }
+                const int idx = (int)(((long long)tid * S) / NT);
+                const uint64_t sk = warp_sort32(key_of(xval(idx)));
+                if (lane >= 32 - POOL_PER_WARP) pool[wid * POOL_PER_WARP + (lane - (32 - POOL_PER_WARP))] = sk;
                 __syncthreads();
-                bitonic_sort_keys<NT>(skey, ns);
             }
-            bool exact = false;
-            double tau = NEG_INF, craw_exact = NEG_INF;
+            bool exact = false, packed = false;
+            double tau = NEG_INF, craw_exact = NEG_INF, qscale = 0.0;
             while (true) {
-                if (sampling && !exact) tau = val_of(skey[ns - R]);
+                if (sampling && !exact) {
+                    // R-th largest of the pooled keys: warp 0 ranks by counting (pool is tiny)
+                    if (wid == 0) {
+                        constexpr int PN = NW * POOL_PER_WARP;
+                        constexpr int PE = (PN + 31) / 32;
+                        uint64_t mine[PE];
+                        int gt[PE];
+#pragma unroll
+                        for (int e = 0; e < PE; ++e) {
+                            const int i = e * 32 + lane;
+                            mine[e] = (i < PN) ? pool[i] : 0ull;
+                            gt[e] = 0;
+                        }
+                        for (int q = 0; q < PN; ++q) {
+                            const uint64_t o = pool[q];
+#pragma unroll
+                            for (int e = 0; e < PE; ++e) {
+                                const int i = e * 32 + lane;
+                                gt[e] += (o > mine[e] || (o == mine[e] && q < i)) ? 1 : 0;
+                            }
+                        }
+                        const int want = min(R, PN) - 1;
+#pragma unroll
+                        for (int e = 0; e < PE; ++e)
+                            if (e * 32 + lane < PN && gt[e] == want) ctl64[0] = mine[e];
+                    }
+                    __syncthreads();
+                    tau = val_of(ctl64[0]);
+                }
+                // packed candidates: 31-bit linear quantisation of (x - tau) over (tau, 0] | draw index
+                qscale = 0x1p31 / (0.0 - tau);
+                packed = sampling && !p.force_legacy && (tau < 0.0) && (qscale < 0x1p900);
                 if (tid == 0) ctl[0] = 0;
                 __syncthreads();
-                // -------- pass B: x = fl(r - mx) (psis.py:134); candidates x > tau; body exp-sum
-                double bsum = 0.0;
-                lsum = 0.0;
-                vsum = 0.0;
-                for (int base = 0; base < S; base += NT) {
-                    const int s = base + tid;
-                    const bool valid = s < S;
-                    double x = NEG_INF;
-                    if (valid) {
-                        const double v = rbuf[s];
-                        x = ((MODE == MODE_LOO) ? -v : v) - mx;
+                // -------- pass B: x = fl(r - mx); candidates x > tau; body exp-sum (+ LOO lppd / variance sums)
+                double bsum0 = 0.0, bsum1 = 0.0, ls0 = 0.0, ls1 = 0.0, vs0 = 0.0, vs1 = 0.0;
+                const int iters = (S2 + NT - 1) / NT;
+                for (int itb = 0; itb <= iters; ++itb) {
+                    // last iteration handles the odd element (if any) in thread 0 of warp 0
+                    const bool last = (itb == iters);
+                    if (last && !(S & 1)) break;
+                    const int i2 = itb * NT + tid;
+                    bool v0 = false, v1 = false;
+                    double x0 = NEG_INF, x1 = NEG_INF;
+                    int s0 = 0;
+                    if (!last) {
+                        if (i2 < S2) {
+                            const double2 v = rbuf2[i2];
+                            s0 = 2 * i2;
+                            v0 = v1 = true;
+                            x0 = ((MODE == MODE_LOO) ? -v.x : v.x) - mx;
+                            x1 = ((MODE == MODE_LOO) ? -v.y : v.y) - mx;
+                            if (MODE == MODE_LOO) {
+                                ls0 += exp_nonpos(v.x - ll_max);  // loo.py:329-337 / utils.py:349-351
+                                ls1 += exp_nonpos(v.y - ll_max);
+                                const double d0 = v.x - ll_mean, d1 = v.y - ll_mean;  // waic.py:145
+                                vs0 = fma(d0, d0, vs0);
+                                vs1 = fma(d1, d1, vs1);
+                            }
+                        }
+                    } else if (tid == 0) {
+                        const double v = rbuf[S - 1];
+                        s0 = S - 1;
+                        v0 = true;
+                        x0 = ((MODE == MODE_LOO) ? -v : v) - mx;
                         if (MODE == MODE_LOO) {
-                            lsum += exp(v - ll_max);         // loo.py:329-337 / utils.py:349-351
-                            const double d = v - ll_mean;    // waic.py:145 (two-pass variance)
-                            vsum += d * d;
+                            ls0 += exp_nonpos(v - ll_max);
+                            const double d0 = v - ll_mean;
+                            vs0 = fma(d0, d0, vs0);
                         }
                     }
-                    const bool isc = valid && (x > tau);
-                    const unsigned mask = __ballot_sync(FULL, isc);
-                    if (mask) {
-                        const int leader = __ffs(mask) - 1;
+                    const bool c0 = v0 && (x0 > tau), c1 = v1 && (x1 > tau);
+                    const unsigned mk0 = __ballot_sync(FULL, c0), mk1 = __ballot_sync(FULL, c1);
+                    if (mk0 | mk1) {
+                        const int n0c = __popc(mk0);
                         int basepos = 0;
-                        if (lane == leader) basepos = atomicAdd(&ctl[0], __popc(mask));
-                        basepos = __shfl_sync(FULL, basepos, leader);
-                        if (isc) {
-                            const int pos = basepos + __popc(mask & ((1u << lane) - 1u));
+                        if (lane == 0) basepos = atomicAdd(&ctl[0], n0c + __popc(mk1));
+                        basepos = __shfl_sync(FULL, basepos, 0);
+                        const unsigned lt = (1u << lane) - 1u;
+                        if (c0) {
+                            const int pos = basepos + __popc(mk0 & lt);
                             if (pos < cap) {
-                                ckey[pos] = key_of(x);
-                                cidx[pos] = s;
+                                if (packed) {
+                                    const uint32_t q = __double2uint_rz((x0 - tau) * qscale) + 1u;
+                                    ckey[pos] = ((uint64_t)q << 32) | (uint32_t)s0;
+                                } else {
+                                    ckey[pos] = key_of(x0);
+                                    cidx[pos] = s0;
+                                }
+                            }
+                        }
+                        if (c1) {
+                            const int pos = basepos + n0c + __popc(mk1 & lt);
+                            if (pos < cap) {
+                                if (packed) {
+                                    const uint32_t q = __double2uint_rz((x1 - tau) * qscale) + 1u;
+                                    ckey[pos] = ((uint64_t)q << 32) | (uint32_t)(s0 + 1);
+                                } else {
+                                    ckey[pos] = key_of(x1);
+                                    cidx[pos] = s0 + 1;
+                                }
                             }
                         }
                     }
-                    if (valid && !isc) bsum += exp(x);
+                    const double e0 = exp_nonpos(x0), e1 = exp_nonpos(x1);
+                    bsum0 += (v0 && !c0) ? e0 : 0.0;
+                    bsum1 += (v1 && !c1) ? e1 : 0.0;
                 }
-                body = block_sum<NT>(bsum, red);
+                body = block_sum<NT>(bsum0 + bsum1, red);
+                lsum = ls0 + ls1;
+                vsum = vs0 + vs1;
                 C = ctl[0];
                 __syncthreads();
                 if (!sampling || exact) break;
                 if (C >= M + 1 && C <= cap) break;
                 ++attempts;
-                int Rn = (C < M + 1) ? min(ns, 2 * R + 8) : max(1, R >> 1);
+                const int Rn = (C < M + 1) ? min(NW * POOL_PER_WARP, 2 * R + 8) : max(1, R >> 1);
                 if (attempts >= 3 || Rn == R) {
                     // -------- exact fallback: (M+1)-th largest key by bit-wise binary search
                     uint64_t K = 0;
                     for (int bit = 63; bit >= 0; --bit) {
                         const uint64_t trial = K | (1ull << bit);
                         int cnt = 0;
-                        for (int s = tid; s < S; s += NT) {
-                            const double v = rbuf[s];
-                            cnt += (key_of(((MODE == MODE_LOO) ? -v : v) - mx) >= trial) ? 1 : 0;
-                        }
+                        for (int s = tid; s < S; s += NT) cnt += (key_of(xval(s)) >= trial) ? 1 : 0;
                         cnt = block_isum<NT>(cnt, red);
                         if (cnt >= M + 1) K = trial;
                     }
@@ -515,49 +711,83 @@ __global__ void __launch_bounds__(NT, (NT <= 256) ? 3 : 1) psis_row_kernel(const
                 vsum = block_sum<NT>(vsum, red);
             }
 
-            // ---------------- sort candidates ascending by (value, index); pads (key 0) first
+            // ---------------- sort candidates ascending by (value, index); pads (0) first
             int P2 = 1;
             while (P2 < C) P2 <<= 1;
             for (int i = C + tid; i < P2; i += NT) {
                 ckey[i] = 0ull;
-                cidx[i] = -1;
+                if (!packed) cidx[i] = -1;
             }
             __syncthreads();
-            if (P2 > 1) bitonic_sort_pairs<NT>(ckey, cidx, P2);
+            if (packed) {
+                if (P2 > 1) bitonic_sort_u64<NT>(ckey, P2);
+                // equal quantised values must be equal doubles, else order is not trustworthy
+                int bad = 0;
+                for (int i = P2 - C + 1 + tid; i < P2; i += NT) {
+                    const uint64_t a = ckey[i - 1], b = ckey[i];
+                    if ((a >> 32) == (b >> 32) && xval((int)(uint32_t)a) != xval((int)(uint32_t)b)) bad = 1;
+                }
+                bad = __syncthreads_or(bad);
+                if (bad) {  // rare: rebuild full keys in place and use the (key, index) sort
+                    for (int i = tid; i < P2; i += NT) {
+                        const uint64_t a = ckey[i];
+                        if (i >= P2 - C) {
+                            const int s = (int)(uint32_t)a;
+                            ckey[i] = key_of(xval(s));
+                            cidx[i] = s;
+                        } else {
+                            cidx[i] = -1;
+                        }
+                    }
+                    __syncthreads();
+                    packed = false;
+                }
+            }
+            if (!packed && P2 > 1) bitonic_sort_pairs<NT>(ckey, cidx, P2);
+            auto cand_idx = [&](int i) -> int { return packed ? (int)(uint32_t)ckey[i] : cidx[i]; };
+            auto cand_x = [&](int i) -> double { return packed ? xval((int)(uint32_t)ckey[i]) : val_of(ckey[i]); };
 
             // ---------------- cutoff (psis.py:135-136) and tail (psis.py:139-141)
             double c_raw;
             if (exact) c_raw = craw_exact;
-            else c_raw = (C >= M + 1) ? val_of(ckey[P2 - M - 1]) : NEG_INF;
+            else c_raw = (C >= M + 1) ? cand_x(P2 - M - 1) : NEG_INF;
             c = fmax(c_raw, p.cutoffmin);
+            int tail0;
             {
-                const uint64_t kc = key_of(c);
                 int lo = P2 - C, hi = P2;
                 while (lo < hi) {
                     const int mid = (lo + hi) >> 1;
-                    if (ckey[mid] > kc) hi = mid; else lo = mid + 1;
+                    if (cand_x(mid) > c) hi = mid; else lo = mid + 1;
                 }
                 tail0 = lo;
                 n = P2 - lo;
             }
             const double exp_c = exp(c);  // psis.py:138
+            // tail in ascending order: raw x_i, draw index, t_i = exp(x_i) - exp(c) (psis.py:146-147);
             // candidates at or below the cutoff belong to the body sum
             {
                 double b2 = 0.0;
-                for (int i = P2 - C + tid; i < tail0; i += NT) b2 += exp(val_of(ckey[i]));
-                body += block_sum<NT>(b2, red);
+                for (int i = P2 - C + tid; i < P2; i += NT) {
+                    const double xi = cand_x(i);
+                    if (i < tail0) {
+                        b2 += exp_nonpos(xi);
+                    } else {
+                        tx[i - tail0] = xi;
+                        ts[i - tail0] = cand_idx(i);
+                        tbuf[i - tail0] = exp(xi) - exp_c;
+                    }
+                }
+                body += block_sum<NT>(b2, red);  // (syncs: tx / ts / tbuf visible)
             }
 
             // ---------------- GPD fit on the tail (psis.py:146-148)
             if (n > 4) {
-                for (int i = tid; i < n; i += NT) tbuf[i] = exp(val_of(ckey[tail0 + i])) - exp_c;
-                __syncthreads();
                 gpdfit_block<NT>(tbuf, n, g, kk, sigma);
                 smooth = is_finite(kk);  // psis.py:150
                 __syncthreads();
             }
             // ---------------- smoothed tail (psis.py:153-157, _gpinv :211-222) and its exp-sum
-            double ts = 0.0;
+            double tsm = 0.0;
             if (smooth) {
                 for (int i = tid; i < n; i += NT) {
                     const double pr = ((double)i + 0.5) / (double)n;
@@ -576,32 +806,48 @@ __global__ void __launch_bounds__(NT, (NT <= 256) ? 3 : 1) psis_row_kernel(const
                         y = 1.0;
                     }
                     tbuf[i] = sm;
-                    ts += y;  // exp(log y) == y: the tail needs no exp
+                    tsm += y;  // exp(log y) == y: the tail needs no exp
                 }
             } else {
-                for (int i = tid; i < n; i += NT) ts += exp(val_of(ckey[tail0 + i]));
+                for (int i = tid; i < n; i += NT) tsm += exp(tx[i]);
             }
-            tails = block_sum<NT>(ts, red);
+            tails = block_sum<NT>(tsm, red);
             lse = log(body + tails);  // psis.py:158 / utils.py:349-357 (row max is 0 or the top smoothed value)
         } else if (MODE == MODE_LOO) {
-            // rows with ll = -inf: still need lppd / variance sums below
-            for (int s = tid; s < S; s += NT) {
-                const double v = rbuf[s];
-                lsum += exp(v - ll_max);
-                const double d = v - ll_mean;
-                vsum += d * d;
+            // rows without PSIS (ll = -inf, or WAIC-only): still need the lppd / variance sums
+            double ls0 = 0.0, ls1 = 0.0, vs0 = 0.0, vs1 = 0.0;
+            for (int i = tid; i < S2; i += NT) {
+                const double2 v = rbuf2[i];
+                ls0 += exp(v.x - ll_max);
+                ls1 += exp(v.y - ll_max);
+                const double d0 = v.x - ll_mean, d1 = v.y - ll_mean;
+                vs0 = fma(d0, d0, vs0);
+                vs1 = fma(d1, d1, vs1);
             }
-            lsum = block_sum<NT>(lsum, red);
-            vsum = block_sum<NT>(vsum, red);
+            if ((S & 1) && tid == 0) {
+                const double v = rbuf[S - 1];
+                ls0 += exp(v - ll_max);
+                const double d0 = v - ll_mean;
+                vs0 = fma(d0, d0, vs0);
+            }
+            lsum = block_sum<NT>(ls0 + ls1, red);
+            vsum = block_sum<NT>(vs0 + vs1, red);
         }
 
         // ---------------- outputs
         if (MODE == MODE_PSISLW) {
             if (run_psis) {
-                for (int s = tid; s < S; s += NT) rbuf[s] = (rbuf[s] - mx) - lse;
+                double2* w2 = reinterpret_cast<double2*>(rbuf);
+                for (int i = tid; i < S2; i += NT) {
+                    double2 v = w2[i];
+                    v.x = (v.x - mx) - lse;
+                    v.y = (v.y - mx) - lse;
+                    w2[i] = v;
+                }
+                if ((S & 1) && tid == 0) rbuf[S - 1] = (rbuf[S - 1] - mx) - lse;
                 __syncthreads();
                 if (smooth)
-                    for (int i = tid; i < n; i += NT) rbuf[cidx[tail0 + i]] = tbuf[i] - lse;
+                    for (int i = tid; i < n; i += NT) rbuf[ts[i]] = tbuf[i] - lse;
             } else {
                 const double qn = nan_f64();
                 for (int s = tid; s < S; s += NT) rbuf[s] = qn;
@@ -627,11 +873,9 @@ __global__ void __launch_bounds__(NT, (NT <= 256) ? 3 : 1) psis_row_kernel(const
                 double dmax = 0.0, es = 0.0;
                 if (smooth) {
                     double dm = 0.0;
-                    for (int i = tid; i < n; i += NT)
-                        dm = fmax(dm, tbuf[i] - val_of(ckey[tail0 + i]));
+                    for (int i = tid; i < n; i += NT) dm = fmax(dm, tbuf[i] - tx[i]);
                     dmax = block_max<NT>(dm, red);
-                    for (int i = tid; i < n; i += NT)
-                        es += exp((tbuf[i] - val_of(ckey[tail0 + i])) - dmax);
+                    for (int i = tid; i < n; i += NT) es += exp((tbuf[i] - tx[i]) - dmax);
                     es = block_sum<NT>(es, red);
                 } else {
                     es = (double)n;

@@ -35,7 +35,7 @@ static int fail(int code, const char* fmt, ...) {
 
 // ------------------------------------------------------------------------------------ planning
 struct RowPlan {
-    int nt, cap, ns, r0, nbuf, ctas_per_sm, grid, sms;
+    int nt, cap, r0, nbuf, ctas_per_sm, grid, sms;
     size_t smem;
 };
 
@@ -67,15 +67,12 @@ static int plan_row(long long S, int M, int mode, long long n_rows, RowPlan* pl)
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     pl->sms = sms;
     pl->cap = std::max(512, pow2ceil(3ll * (M + 1)));
-    pl->ns = std::min(1024, std::max(256, pow2ceil((S + 15) / 16)));
-    long long r0 = (long long)std::ceil(1.9 * (M + 1) * (double)pl->ns / (double)S);
-    pl->r0 = (int)std::min<long long>(pl->ns, std::max<long long>(1, r0));
     // rows in flight per SM: prefer more resident CTAs (more warps), double-buffer on a tie
     int best_ctas = 0, best_nbuf = 0, best_nt = 256;
     size_t best_smem = 0;
     for (int nbuf = 1; nbuf <= 2; ++nbuf) {
         for (int nt : {256, 512}) {
-            size_t smem = row_smem_layout((int)S, M, pl->cap, pl->ns, nbuf, nt).total;
+            size_t smem = row_smem_layout((int)S, M, pl->cap, nbuf, nt).total;
             if (smem > (size_t)smem_optin) continue;
             int ctas = (int)((size_t)smem_sm / (smem + 1024));
             if (ctas < 1) continue;
@@ -91,7 +88,7 @@ static int plan_row(long long S, int M, int mode, long long n_rows, RowPlan* pl)
     if (const char* ev = getenv("B2L_NBUF")) {
         int nb = atoi(ev), nt = getenv("B2L_NT") ? atoi(getenv("B2L_NT")) : best_nt;
         if ((nb == 1 || nb == 2) && (nt == 256 || nt == 512)) {
-            size_t smem = row_smem_layout((int)S, M, pl->cap, pl->ns, nb, nt).total;
+            size_t smem = row_smem_layout((int)S, M, pl->cap, nb, nt).total;
             if (smem <= (size_t)smem_optin) {
                 best_nbuf = nb; best_nt = nt; best_smem = smem;
                 best_ctas = std::max(1, (int)((size_t)smem_sm / (smem + 1024)));
@@ -102,6 +99,11 @@ static int plan_row(long long S, int M, int mode, long long n_rows, RowPlan* pl)
         return fail(B2L_E_UNSUPPORTED, "S=%lld draws (%lld bytes/observation) do not fit the %d-byte "
                     "shared memory of one SM", S, S * 8, smem_optin);
     pl->nt = best_nt; pl->nbuf = best_nbuf; pl->smem = best_smem;
+    {   // pooled sample rank aiming at ~1.9 (M+1) candidates (one sample per thread)
+        const int pool = (best_nt / 32) * POOL_PER_WARP;
+        long long r0 = std::llround(1.9 * (M + 1) * (double)best_nt / (double)S);
+        pl->r0 = (int)std::min<long long>(pool, std::max<long long>(1, r0));
+    }
     int occ = 0;
     cudaError_t e;
     if (mode == MODE_PSISLW)
@@ -119,7 +121,8 @@ static int plan_row(long long S, int M, int mode, long long n_rows, RowPlan* pl)
 }
 
 static int launch_rows(int mode, const RowPlan& pl, RowParams rp, cudaStream_t st) {
-    rp.cap = pl.cap; rp.ns = pl.ns; rp.r0 = pl.r0; rp.nbuf = pl.nbuf;
+    rp.cap = pl.cap; rp.r0 = pl.r0; rp.nbuf = pl.nbuf;
+    rp.force_legacy = getenv("B2L_FORCE_LEGACY") ? 1 : 0;
     int grid = (int)std::max<long long>(1, std::min<long long>(pl.grid, rp.n_rows));
     if (rp.n_rows == 0) return 0;
     if (mode == MODE_PSISLW) {

@@ -314,3 +314,32 @@ def test_full_size_properties_cfg2():
     out2, k2 = engine.psislw_cuda(x[:4096] + 3.0, 0.9)
     torch.cuda.synchronize()
     assert float((k2 - k[:4096]).abs().max()) < 1e-9
+
+
+def test_packed_and_full_key_candidate_paths_agree_bitwise(monkeypatch):
+    """The 31-bit packed candidate sort (fast path) and the full 64-bit (key, index) sort give the
+    same bits; forcing the latter exercises the collision-fallback code."""
+    rng = np.random.default_rng(21)
+    x = np.ascontiguousarray(rng.normal(size=(600, 4000)))
+    fast = gpu_psislw(x, 0.9)
+    monkeypatch.setenv("B2L_FORCE_LEGACY", "1")
+    slow = gpu_psislw(x, 0.9)
+    monkeypatch.delenv("B2L_FORCE_LEGACY")
+    assert np.array_equal(fast[0], slow[0]) and np.array_equal(fast[1], slow[1])
+
+
+def test_quantisation_collisions_fall_back_to_exact_order():
+    """Distinct doubles closer than the 31-bit quantisation step inside the tail: detected, exact order kept."""
+    rng = np.random.default_rng(22)
+    x = rng.normal(size=(64, 4000))
+    top = np.argsort(x, axis=1)[:, -50:]
+    for i in range(64):                      # squeeze the 50 largest draws into a 1e-13-wide cluster
+        x[i, top[i]] = 3.0 + 1e-15 * rng.permutation(50) * (i + 1)
+    lw, k, diag = gpu_psislw(x, 0.9, diag=True)
+    with np.errstate(all="ignore"):
+        ref_lw, ref_k = orc.psislw(x, 0.9)
+    close(k, ref_k)
+    same_special(k, ref_k)
+    close(lw, ref_lw, atol=1e-12)
+    cut, cnt = oracle_tail(x, 200)
+    assert np.array_equal(diag[:, 1], cut) and np.array_equal(diag[:, 2].astype(int), cnt)
