@@ -47,52 +47,28 @@ __device__ __forceinline__ int warp_isum(int v) {
     return v;
 }
 
-// `red` = shared scratch of >= NT/32 doubles.  Every thread returns the same value.
-template <int NT>
-__device__ __forceinline__ double block_sum(double v, double* red) {
-    v = warp_sum(v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double t = red[0];
-#pragma unroll
-    for (int i = 1; i < NT / 32; ++i) t += red[i];
-    return t;
-}
-template <int NT>
-__device__ __forceinline__ double block_max(double v, double* red) {
-    v = warp_max(v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double t = red[0];
-#pragma unroll
-    for (int i = 1; i < NT / 32; ++i) t = fmax(t, red[i]);
-    return t;
-}
-template <int NT>
-__device__ __forceinline__ double block_min(double v, double* red) {
-    v = warp_min(v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double t = red[0];
-#pragma unroll
-    for (int i = 1; i < NT / 32; ++i) t = fmin(t, red[i]);
-    return t;
-}
-template <int NT>
-__device__ __forceinline__ int block_isum(int v, double* red) {
-    int* ired = reinterpret_cast<int*>(red);
-    v = warp_isum(v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) ired[threadIdx.x >> 5] = v;
-    __syncthreads();
-    int t = ired[0];
-#pragma unroll
-    for (int i = 1; i < NT / 32; ++i) t += ired[i];
-    return t;
-}
+// `red` = shared scratch of 128 doubles.  Every thread returns the same value.
+// Two levels: warp butterfly -> one word per warp -> warp 0 butterfly -> broadcast word.
+#define B2L_BLOCK_REDUCE(NAME, TYPE, WARPOP, IDENT, OFFS)                             \
+    template <int NT>                                                                 \
+    __device__ __forceinline__ TYPE NAME(TYPE v, double* red_) {                      \
+        TYPE* red = reinterpret_cast<TYPE*>(red_ + (OFFS));                           \
+        constexpr int NW = NT / 32;                                                   \
+        v = WARPOP(v);                                                                \
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;                       \
+        __syncthreads();                                                              \
+        if (threadIdx.x < 32) {                                                       \
+            TYPE t = (threadIdx.x < NW) ? red[threadIdx.x] : (IDENT);                 \
+            t = WARPOP(t);                                                            \
+            if (threadIdx.x == 0) red[NW] = t;                                        \
+        }                                                                             \
+        __syncthreads();                                                              \
+        return red[NW];                                                               \
+    }
+B2L_BLOCK_REDUCE(block_sum, double, warp_sum, 0.0, 0)
+B2L_BLOCK_REDUCE(block_max, double, warp_max, -__longlong_as_double(0x7ff0000000000000ll), 0)
+B2L_BLOCK_REDUCE(block_min, double, warp_min, __longlong_as_double(0x7ff0000000000000ll), 0)
+B2L_BLOCK_REDUCE(block_isum, int, warp_isum, 0, 64)  // ints live in their own half of `red`
 
 // ---------------------------------------------------------------- mbarrier / bulk TMA
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -45,11 +45,14 @@ struct RowParams {
     int use_bulk;  // 1: 16 B aligned rows -> bulk TMA; 0: cooperative LDG/STG
     int waic_only; // LOO mode: skip PSIS, only lppd / variance outputs
     int force_legacy;  // testing: always take the full-key (unpacked) candidate path
+    double* row_ws; // non-null: rows too long for shared memory live here (gridDim.x rows of row_ld doubles)
+    long long row_ld;
+    int m_full;    // GPD grid size 30 + floor(sqrt(M)) for the common full tail n == M (host-computed)
     double cutoffmin;
 };
 
 struct RowSmemLayout {
-    size_t row_bytes, off_row, off_ckey, off_cidx, off_tbuf, off_tx, off_ts, off_gb, off_gk, off_gw,
+    size_t row_bytes, off_row, off_ckey, off_cidx, off_tbuf, off_tx, off_ts, off_l1p, off_gb, off_gk, off_gw,
         off_gflag, off_part, off_red, off_ctl, off_bar, total;
 };
 
@@ -72,6 +75,8 @@ __host__ __device__ inline RowSmemLayout row_smem_layout(int S, int M, int cap, 
     o += align_up((size_t)(M + 1) * 8, 16);
     L.off_ts = o;    // tail draw indices
     o += align_up((size_t)(M + 1) * 4, 16);
+    L.off_l1p = o;   // log1p(-(i + 0.5) / M), i < M: the _gpinv argument for a full tail
+    o += align_up((size_t)(M + 1) * 8, 16);
     L.off_gb = o;
     o += GPD_MAX_GRID * 8;
     L.off_gk = o;
@@ -95,25 +100,24 @@ __host__ __device__ inline RowSmemLayout row_smem_layout(int S, int M, int cap, 
 // ------------------------------------------------------------------ fast exp for x <= 0
 // exp(x), x in [-708, 0]: Cody-Waite reduction, degree-13 Taylor/Horner, exponent insertion.
 // Max error ~1 ulp.  Anything below -708 (denormal results, -inf) goes to the library routine.
+__constant__ double c_exp_poly[12] = {
+    1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07,
+    2.7557319223985893e-06, 2.48015873015873e-05, 1.984126984126984e-04, 1.388888888888889e-03,
+    8.333333333333333e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, 0.5};  // 1/13! .. 1/2!
+__constant__ double c_exp_red[4] = {1.4426950408889634074, 6755399441055744.0,
+                                    -6.93147180369123816490e-01, -1.90821492927058770002e-10};
+
 __device__ __forceinline__ double exp_nonpos(double x) {
     if (x < -708.0) return exp(x);
-    const double t = fma(x, 1.4426950408889634074, 6755399441055744.0);
+    // coefficients come from the constant bank (DFMA c[][] operand): no per-use 64-bit immediates
+    const double t = fma(x, c_exp_red[0], c_exp_red[1]);
     const int ni = __double2loint(t);
-    const double n = t - 6755399441055744.0;
-    double r = fma(n, -6.93147180369123816490e-01, x);
-    r = fma(n, -1.90821492927058770002e-10, r);
-    double p = 1.6059043836821613e-10;            // 1/13!
-    p = fma(p, r, 2.08767569878681e-09);          // 1/12!
-    p = fma(p, r, 2.505210838544172e-08);         // 1/11!
-    p = fma(p, r, 2.755731922398589e-07);         // 1/10!
-    p = fma(p, r, 2.7557319223985893e-06);        // 1/9!
-    p = fma(p, r, 2.48015873015873e-05);          // 1/8!
-    p = fma(p, r, 1.984126984126984e-04);         // 1/7!
-    p = fma(p, r, 1.388888888888889e-03);         // 1/6!
-    p = fma(p, r, 8.333333333333333e-03);         // 1/5!
-    p = fma(p, r, 4.1666666666666664e-02);        // 1/4!
-    p = fma(p, r, 1.6666666666666666e-01);        // 1/3!
-    p = fma(p, r, 0.5);
+    const double n = t - c_exp_red[1];
+    double r = fma(n, c_exp_red[2], x);
+    r = fma(n, c_exp_red[3], r);
+    double p = c_exp_poly[0];
+#pragma unroll
+    for (int i = 1; i < 12; ++i) p = fma(p, r, c_exp_poly[i]);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
     return __hiloint2double(__double2hiint(p) + (ni << 20), __double2loint(p));
@@ -141,18 +145,67 @@ __device__ __forceinline__ uint64_t warp_sort32(uint64_t v) {
 }
 
 // ------------------------------------------------------------------ bitonic sorts (shared memory)
-// single 64-bit words, ascending
+// single 64-bit words, ascending.  Sizes 256..2048 run a fully unrolled network: every stage's
+// (k, j) is a compile-time constant, so the index arithmetic folds and the loop control vanishes.
+template <int NT, int N, int K, int J>
+__device__ __forceinline__ void bitonic_stage_const(uint64_t* key) {
+#pragma unroll
+    for (int t0 = 0; t0 < N / 2; t0 += NT) {
+        const int t = t0 + (int)threadIdx.x;
+        if (N / 2 >= NT || t < N / 2) {
+            const int i = 2 * t - (t & (J - 1));
+            const uint64_t a = key[i], b = key[i + J];
+            if ((a > b) != ((i & K) != 0)) {
+                key[i] = b;
+                key[i + J] = a;
+            }
+        }
+    }
+    // a stage whose partners stay inside one warp's 64-element block only needs a warp barrier
+    if (J <= 32 && J > 1 && N / 2 >= NT) __syncwarp();
+    else __syncthreads();
+}
+template <int NT, int N, int K, int J>
+struct BitonicJ {
+    static __device__ __forceinline__ void run(uint64_t* key) {
+        bitonic_stage_const<NT, N, K, J>(key);
+        BitonicJ<NT, N, K, J / 2>::run(key);
+    }
+};
+template <int NT, int N, int K>
+struct BitonicJ<NT, N, K, 0> {
+    static __device__ __forceinline__ void run(uint64_t*) {}
+};
+template <int NT, int N, int K>
+struct BitonicK {
+    static __device__ __forceinline__ void run(uint64_t* key) {
+        BitonicK<NT, N, K / 2>::run(key);
+        BitonicJ<NT, N, K, K / 2>::run(key);
+    }
+};
+template <int NT, int N>
+struct BitonicK<NT, N, 1> {
+    static __device__ __forceinline__ void run(uint64_t*) {}
+};
 template <int NT>
 __device__ void bitonic_sort_u64(uint64_t* key, int n) {
+    switch (n) {
+        case 256: BitonicK<NT, 256, 256>::run(key); return;
+        case 512: BitonicK<NT, 512, 512>::run(key); return;
+        case 1024: BitonicK<NT, 1024, 1024>::run(key); return;
+        case 2048: BitonicK<NT, 2048, 2048>::run(key); return;
+        default: break;
+    }
+    const int half = n >> 1;
     for (int k = 2; k <= n; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < (n >> 1); t += NT) {
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const int l = i | j;
-                const uint64_t a = key[i], b = key[l];
-                if ((a > b) == ((i & k) == 0)) {
-                    key[i] = b;
-                    key[l] = a;
+            for (int t = threadIdx.x; t < half; t += NT) {
+                const int i = 2 * t - (t & (j - 1));
+                uint64_t* pa = key + i;
+                const uint64_t a = pa[0], b = pa[j];
+                if ((a > b) != ((i & k) != 0)) {
+                    pa[0] = b;
+                    pa[j] = a;
                 }
             }
             __syncthreads();
@@ -212,13 +265,16 @@ __device__ __forceinline__ bool rescale_pos(double& P, int& E) {
 // renormalisation (one log per grid point); grid points where that loses relative accuracy
 // (|b_j| sum t small, non-positive or non-finite factors) take the literal log1p path.
 template <int NT>
-__device__ void gpdfit_block(const double* t, int n, GpdScratch g, double& k_out,
+__device__ void gpdfit_block(const double* t, int n, int m_hint, GpdScratch g, double& k_out,
                              double& sigma_out) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    int m = (int)sqrt((double)n);
-    while (m * m > n) --m;
-    while ((m + 1) * (m + 1) <= n) ++m;
-    m += 30;                                               // psis.py:184
+    int m = m_hint;                                        // psis.py:184 (host-computed when n == M)
+    if (m <= 0) {
+        m = (int)sqrt((double)n);
+        while (m * m > n) --m;
+        while ((m + 1) * (m + 1) <= n) ++m;
+        m += 30;
+    }
     const double tq = t[(int)((double)n / 4.0 + 0.5) - 1];  // psis.py:187
     const double tn = t[n - 1];
 
@@ -394,6 +450,7 @@ __global__ void __launch_bounds__(NT, (NT <= 256) ? 3 : 1) psis_row_kernel(const
     double* tbuf = reinterpret_cast<double*>(smem_raw + L.off_tbuf);
     double* tx = reinterpret_cast<double*>(smem_raw + L.off_tx);
     int* ts = reinterpret_cast<int*>(smem_raw + L.off_ts);
+    double* l1p = reinterpret_cast<double*>(smem_raw + L.off_l1p);
     uint64_t* pool = reinterpret_cast<uint64_t*>(smem_raw + L.off_part);
     double* red = reinterpret_cast<double*>(smem_raw + L.off_red);
     int* ctl = reinterpret_cast<int*>(smem_raw + L.off_ctl);
@@ -421,6 +478,9 @@ __global__ void __launch_bounds__(NT, (NT <= 256) ? 3 : 1) psis_row_kernel(const
         mbar_init(&bars[1], 1);
         fence_mbar_init();
     }
+    // per-CTA table for the smoothing step: depends only on (i, M), psis.py:153 + :221
+    if (MODE == MODE_PSISLW || !p.waic_only)
+        for (int i = tid; i < M; i += NT) l1p[i] = log1p(-(((double)i + 0.5) / (double)M));
     __syncthreads();
 
     long long row = blockIdx.x;
@@ -431,7 +491,8 @@ __global__ void __launch_bounds__(NT, (NT <= 256) ? 3 : 1) psis_row_kernel(const
 
     for (int it = 0; row < p.n_rows; row += gridDim.x, ++it) {
         const int bsel = (p.nbuf == 2) ? (it & 1) : 0;
-        double* rbuf = reinterpret_cast<double*>(smem_raw + L.off_row + (size_t)bsel * L.row_bytes);
+        double* rbuf = p.row_ws ? p.row_ws + (size_t)blockIdx.x * p.row_ld
+                                : reinterpret_cast<double*>(smem_raw + L.off_row + (size_t)bsel * L.row_bytes);
         const double2* rbuf2 = reinterpret_cast<const double2*>(rbuf);
         const long long nrow = row + gridDim.x;
 
@@ -480,29 +541,12 @@ __global__ void __launch_bounds__(NT, (NT <= 256) ? 3 : 1) psis_row_kernel(const
                     s0 += v;
                 }
             }
-            m0 = warp_max(fmax(m0, m1));
-            spec = __reduce_max_sync(FULL, spec);
+            a_max = block_max<NT>(fmax(m0, m1), red);
             if (MODE == MODE_LOO) {
-                n0 = warp_min(fmin(n0, n1));
-                s0 = warp_sum(s0 + s1);
+                a_min = block_min<NT>(fmin(n0, n1), red);
+                a_sum = block_sum<NT>(s0 + s1, red);
             }
-            __syncthreads();
-            if (lane == 0) {
-                double* r = red + wid * 4;
-                r[0] = m0; r[1] = n0; r[2] = s0;
-                reinterpret_cast<int*>(r + 3)[0] = spec;
-            }
-            __syncthreads();
-            a_max = red[0]; a_min = red[1]; a_sum = red[2];
-            int sp = reinterpret_cast<int*>(red + 3)[0];
-#pragma unroll
-            for (int w = 1; w < NW; ++w) {
-                a_max = fmax(a_max, red[w * 4 + 0]);
-                a_min = fmin(a_min, red[w * 4 + 1]);
-                a_sum += red[w * 4 + 2];
-                sp = max(sp, reinterpret_cast<int*>(red + w * 4 + 3)[0]);
-            }
-            __syncthreads();
+            const int sp = __syncthreads_or(spec >= 0x7ff00000) ? 0x7ff00000 : 0;
             if (sp >= 0x7ff00000) {
                 // ---------------- census (slow, rare): NaN / inf counts, NaN -> -1e10 in LOO mode
                 a_max = NEG_INF; a_min = inf_f64(); a_sum = 0.0;
@@ -605,24 +649,25 @@ __global__ void __launch_bounds__(NT, (NT <= 256) ? 3 : 1) psis_row_kernel(const
                 packed = sampling && !p.force_legacy && (tau < 0.0) && (qscale < 0x1p900);
                 if (tid == 0) ctl[0] = 0;
                 __syncthreads();
-                // -------- pass B: x = fl(r - mx); candidates x > tau; body exp-sum (+ LOO lppd / variance sums)
+                // -------- pass B: x = fl(r - mx); body exp-sum (+ LOO lppd / variance sums).  Candidates
+                // (x > tau, ~9 % of the draws) are only marked in a per-thread bit mask here and
+                // replayed afterwards, so the streaming loop carries no compaction code.
                 double bsum0 = 0.0, bsum1 = 0.0, ls0 = 0.0, ls1 = 0.0, vs0 = 0.0, vs1 = 0.0;
-                const int iters = (S2 + NT - 1) / NT;
-                for (int itb = 0; itb <= iters; ++itb) {
-                    // last iteration handles the odd element (if any) in thread 0 of warp 0
-                    const bool last = (itb == iters);
-                    if (last && !(S & 1)) break;
-                    const int i2 = itb * NT + tid;
-                    bool v0 = false, v1 = false;
-                    double x0 = NEG_INF, x1 = NEG_INF;
-                    int s0 = 0;
-                    if (!last) {
-                        if (i2 < S2) {
+                // segments of <= 32 iterations (64 NT draws) so the mask fits 64 bits for any S
+                for (int seg = 0; seg < S2; seg += 32 * NT) {
+                    unsigned long long cmask = 0ull;  // bit 2*it + e  <=>  element e of iteration it
+                    const int seg_end = min(S2, seg + 32 * NT);
+                    {
+                        int itb = 0;
+                        for (int i2 = seg + tid; i2 < seg_end; i2 += NT, ++itb) {
                             const double2 v = rbuf2[i2];
-                            s0 = 2 * i2;
-                            v0 = v1 = true;
-                            x0 = ((MODE == MODE_LOO) ? -v.x : v.x) - mx;
-                            x1 = ((MODE == MODE_LOO) ? -v.y : v.y) - mx;
+                            const double x0 = ((MODE == MODE_LOO) ? -v.x : v.x) - mx;
+                            const double x1 = ((MODE == MODE_LOO) ? -v.y : v.y) - mx;
+                            const bool c0 = x0 > tau, c1 = x1 > tau;
+                            cmask |= (unsigned long long)((c0 ? 1u : 0u) | (c1 ? 2u : 0u)) << (2 * itb);
+                            const double e0 = exp_nonpos(x0), e1 = exp_nonpos(x1);
+                            bsum0 += c0 ? 0.0 : e0;
+                            bsum1 += c1 ? 0.0 : e1;
                             if (MODE == MODE_LOO) {
                                 ls0 += exp_nonpos(v.x - ll_max);  // loo.py:329-337 / utils.py:349-351
                                 ls1 += exp_nonpos(v.y - ll_max);
@@ -631,53 +676,59 @@ __global__ void __launch_bounds__(NT, (NT <= 256) ? 3 : 1) psis_row_kernel(const
                                 vs1 = fma(d1, d1, vs1);
                             }
                         }
-                    } else if (tid == 0) {
-                        const double v = rbuf[S - 1];
-                        s0 = S - 1;
-                        v0 = true;
-                        x0 = ((MODE == MODE_LOO) ? -v : v) - mx;
-                        if (MODE == MODE_LOO) {
-                            ls0 += exp_nonpos(v - ll_max);
-                            const double d0 = v - ll_mean;
-                            vs0 = fma(d0, d0, vs0);
-                        }
                     }
-                    const bool c0 = v0 && (x0 > tau), c1 = v1 && (x1 > tau);
-                    const unsigned mk0 = __ballot_sync(FULL, c0), mk1 = __ballot_sync(FULL, c1);
-                    if (mk0 | mk1) {
-                        const int n0c = __popc(mk0);
-                        int basepos = 0;
-                        if (lane == 0) basepos = atomicAdd(&ctl[0], n0c + __popc(mk1));
-                        basepos = __shfl_sync(FULL, basepos, 0);
-                        const unsigned lt = (1u << lane) - 1u;
-                        if (c0) {
-                            const int pos = basepos + __popc(mk0 & lt);
-                            if (pos < cap) {
-                                if (packed) {
-                                    const uint32_t q = __double2uint_rz((x0 - tau) * qscale) + 1u;
-                                    ckey[pos] = ((uint64_t)q << 32) | (uint32_t)s0;
-                                } else {
-                                    ckey[pos] = key_of(x0);
-                                    cidx[pos] = s0;
-                                }
+                    // replay: one smem atomic per warp reserves a slot range, then each thread emits its own
+                    const int mine = __popcll(cmask);
+                    int incl = mine;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int u = __shfl_up_sync(FULL, incl, o);
+                        if (lane >= o) incl += u;
+                    }
+                    int base = 0;
+                    if (lane == 31) base = atomicAdd(&ctl[0], incl);
+                    base = __shfl_sync(FULL, base, 31);
+                    int pos = base + incl - mine;
+                    while (cmask) {
+                        const int bpos = __ffsll((long long)cmask) - 1;
+                        cmask &= cmask - 1;
+                        const int s = 2 * (seg + (bpos >> 1) * NT + tid) + (bpos & 1);
+                        if (pos < cap) {
+                            const double x = xval(s);
+                            if (packed) {
+                                const uint32_t q = __double2uint_rz((x - tau) * qscale) + 1u;
+                                ckey[pos] = ((uint64_t)q << 32) | (uint32_t)s;
+                            } else {
+                                ckey[pos] = key_of(x);
+                                cidx[pos] = s;
                             }
                         }
-                        if (c1) {
-                            const int pos = basepos + n0c + __popc(mk1 & lt);
-                            if (pos < cap) {
-                                if (packed) {
-                                    const uint32_t q = __double2uint_rz((x1 - tau) * qscale) + 1u;
-                                    ckey[pos] = ((uint64_t)q << 32) | (uint32_t)(s0 + 1);
-                                } else {
-                                    ckey[pos] = key_of(x1);
-                                    cidx[pos] = s0 + 1;
-                                }
+                        ++pos;
+                    }
+                }
+                if ((S & 1) && tid == 0) {  // odd S: last draw
+                    const int s = S - 1;
+                    const double v = rbuf[s];
+                    const double x = ((MODE == MODE_LOO) ? -v : v) - mx;
+                    if (x > tau) {
+                        const int pos = atomicAdd(&ctl[0], 1);
+                        if (pos < cap) {
+                            if (packed) {
+                                const uint32_t q = __double2uint_rz((x - tau) * qscale) + 1u;
+                                ckey[pos] = ((uint64_t)q << 32) | (uint32_t)s;
+                            } else {
+                                ckey[pos] = key_of(x);
+                                cidx[pos] = s;
                             }
                         }
+                    } else {
+                        bsum0 += exp_nonpos(x);
                     }
-                    const double e0 = exp_nonpos(x0), e1 = exp_nonpos(x1);
-                    bsum0 += (v0 && !c0) ? e0 : 0.0;
-                    bsum1 += (v1 && !c1) ? e1 : 0.0;
+                    if (MODE == MODE_LOO) {
+                        ls0 += exp_nonpos(v - ll_max);
+                        const double d0 = v - ll_mean;
+                        vs0 = fma(d0, d0, vs0);
+                    }
                 }
                 body = block_sum<NT>(bsum0 + bsum1, red);
                 lsum = ls0 + ls1;
@@ -782,7 +833,7 @@ __global__ void __launch_bounds__(NT, (NT <= 256) ? 3 : 1) psis_row_kernel(const
 
             // ---------------- GPD fit on the tail (psis.py:146-148)
             if (n > 4) {
-                gpdfit_block<NT>(tbuf, n, g, kk, sigma);
+                gpdfit_block<NT>(tbuf, n, (n == M) ? p.m_full : 0, g, kk, sigma);
                 smooth = is_finite(kk);  // psis.py:150
                 __syncthreads();
             }
@@ -795,7 +846,7 @@ __global__ void __launch_bounds__(NT, (NT <= 256) ? 3 : 1) psis_row_kernel(const
                     if (sigma <= 0.0) {
                         q = nan_f64();
                     } else {
-                        const double l1 = log1p(-pr);
+                        const double l1 = (n == M) ? l1p[i] : log1p(-pr);
                         q = (fabs(kk) < 2.220446049250313e-16) ? -l1 : expm1(-kk * l1) / kk;
                         q *= sigma;
                     }

@@ -34,8 +34,9 @@ static int fail(int code, const char* fmt, ...) {
     } while (0)
 
 // ------------------------------------------------------------------------------------ planning
+constexpr int GROWS_MAX_CTAS = 192;  // global-memory row mode: at most this many resident rows
 struct RowPlan {
-    int nt, cap, r0, nbuf, ctas_per_sm, grid, sms;
+    int nt, cap, r0, nbuf, ctas_per_sm, grid, sms, global_rows;
     size_t smem;
 };
 
@@ -95,9 +96,16 @@ static int plan_row(long long S, int M, int mode, long long n_rows, RowPlan* pl)
             }
         }
     }
-    if (best_ctas == 0)
-        return fail(B2L_E_UNSUPPORTED, "S=%lld draws (%lld bytes/observation) do not fit the %d-byte "
-                    "shared memory of one SM", S, S * 8, smem_optin);
+    pl->global_rows = 0;
+    if (best_ctas == 0) {
+        // rows longer than shared memory: same kernel, the row lives in a global-memory workspace
+        // (L2-resident: gridDim.x rows) instead of shared memory.  Slow path, any S.
+        size_t smem = row_smem_layout((int)S, M, pl->cap, 0, 512).total;
+        if (smem > (size_t)smem_optin)
+            return fail(B2L_E_UNSUPPORTED, "tail length M=%d needs %zu bytes of shared memory", M, smem);
+        best_ctas = 1; best_nbuf = 0; best_nt = 512; best_smem = smem;
+        pl->global_rows = 1;
+    }
     pl->nt = best_nt; pl->nbuf = best_nbuf; pl->smem = best_smem;
     {   // pooled sample rank aiming at ~1.9 (M+1) candidates (one sample per thread)
         const int pool = (best_nt / 32) * POOL_PER_WARP;
@@ -116,6 +124,7 @@ static int plan_row(long long S, int M, int mode, long long n_rows, RowPlan* pl)
     if (occ < 1) return fail(B2L_E_UNSUPPORTED, "row kernel does not fit on an SM (smem %zu)", best_smem);
     pl->ctas_per_sm = occ;
     long long g = (long long)sms * occ;
+    if (pl->global_rows) g = std::min<long long>(g, GROWS_MAX_CTAS);
     pl->grid = (int)std::max<long long>(1, std::min<long long>(g, n_rows));
     return 0;
 }
@@ -123,6 +132,18 @@ static int plan_row(long long S, int M, int mode, long long n_rows, RowPlan* pl)
 static int launch_rows(int mode, const RowPlan& pl, RowParams rp, cudaStream_t st) {
     rp.cap = pl.cap; rp.r0 = pl.r0; rp.nbuf = pl.nbuf;
     rp.force_legacy = getenv("B2L_FORCE_LEGACY") ? 1 : 0;
+    if (pl.global_rows) {
+        if (!rp.row_ws) return fail(B2L_E_WORKSPACE, "rows of S=%d draws need the global-row workspace", rp.S);
+        rp.use_bulk = 0;
+    } else {
+        rp.row_ws = nullptr;
+    }
+    {
+        int r = (int)std::sqrt((double)rp.M);
+        while (r * r > rp.M) --r;
+        while ((r + 1) * (r + 1) <= rp.M) ++r;
+        rp.m_full = 30 + r;
+    }
     int grid = (int)std::max<long long>(1, std::min<long long>(pl.grid, rp.n_rows));
     if (rp.n_rows == 0) return 0;
     if (mode == MODE_PSISLW) {
@@ -286,6 +307,11 @@ static long long panel_obs(long long S, long long N) {
     return std::min(p, (N + 31) / 32 * 32);
 }
 static size_t stats_ws_bytes() { return align_up(sizeof(StatAcc) * STATS_BLOCKS, 256); }
+// rows that do not fit shared memory are staged in global memory: one row per resident CTA
+static size_t grows_ws_bytes(long long S) {
+    if (S * 8 <= 160 * 1024) return 0;  // certainly fits shared memory
+    return align_up((size_t)((S + 1) & ~1ll) * 8 * GROWS_MAX_CTAS, 256);
+}
 
 extern "C" int b2l_version(void) { return B2L_VERSION; }
 extern "C" const char* b2l_last_error(void) { return g_err; }
@@ -304,7 +330,7 @@ extern "C" int b2l_workspace_bytes(int64_t S, int64_t N, int32_t M, int32_t layo
                                    size_t* out_bytes) {
     (void)M;
     if (!out_bytes || S < 1 || N < 0) return fail(B2L_E_INVALID, "bad arguments");
-    size_t b = stats_ws_bytes();
+    size_t b = stats_ws_bytes() + grows_ws_bytes(S);
     if (layout_obs_fastest) b += 2 * align_up((size_t)panel_obs(S, N) * (size_t)S * 8, 256);
     *out_bytes = b;
     return 0;
@@ -325,6 +351,12 @@ extern "C" int b2l_psislw_dev_f64(const double* lw, int64_t S, int64_t N, int64_
     RowParams rp;
     memset(&rp, 0, sizeof(rp));
     rp.S = (int)S; rp.M = M; rp.cutoffmin = cutoffmin; rp.k_out = k_out; rp.diag = diag;
+    const size_t gro = grows_ws_bytes(S);
+    if (gro) {
+        if (!ws || ws_bytes < stats_ws_bytes() + gro) return fail(B2L_E_WORKSPACE, "workspace too small for S=%lld", (long long)S);
+        rp.row_ws = reinterpret_cast<double*>((char*)ws + stats_ws_bytes());
+        rp.row_ld = (S + 1) & ~1ll;
+    }
     const bool rows_in = (stride_s == 1 || S == 1), rows_out = (ostride_s == 1 || S == 1);
     if (rows_in && rows_out) {
         rp.in = lw; rp.in_stride = stride_n; rp.out = lw_out; rp.out_stride = ostride_n; rp.n_rows = N;
@@ -337,10 +369,10 @@ extern "C" int b2l_psislw_dev_f64(const double* lw, int64_t S, int64_t N, int64_
     // obs-fastest on either side: go through row panels
     const long long P = panel_obs(S, N);
     const size_t panel_bytes = align_up((size_t)P * (size_t)S * 8, 256);
-    if (!ws || ws_bytes < stats_ws_bytes() + 2 * panel_bytes)
-        return fail(B2L_E_WORKSPACE, "workspace too small: need %zu bytes", stats_ws_bytes() + 2 * panel_bytes);
-    double* pa = reinterpret_cast<double*>((char*)ws + stats_ws_bytes());
-    double* pb = reinterpret_cast<double*>((char*)ws + stats_ws_bytes() + panel_bytes);
+    if (!ws || ws_bytes < stats_ws_bytes() + gro + 2 * panel_bytes)
+        return fail(B2L_E_WORKSPACE, "workspace too small: need %zu bytes", stats_ws_bytes() + gro + 2 * panel_bytes);
+    double* pa = reinterpret_cast<double*>((char*)ws + stats_ws_bytes() + gro);
+    double* pb = reinterpret_cast<double*>((char*)ws + stats_ws_bytes() + gro + panel_bytes);
     for (long long i0 = 0; i0 < N; i0 += P) {
         const long long np = std::min<long long>(P, N - i0);
         RowParams r = rp;
@@ -381,6 +413,12 @@ extern "C" int b2l_loo_dev_f64(const double* ll, int64_t S, int64_t N, int64_t s
     memset(&rp, 0, sizeof(rp));
     rp.S = (int)S; rp.M = M; rp.cutoffmin = cutoffmin; rp.counters = counters;
     rp.waic_only = (flags & B2L_FLAG_WAIC_ONLY) ? 1 : 0;
+    const size_t gro = grows_ws_bytes(S);
+    if (gro) {
+        if (!ws || ws_bytes < stats_ws_bytes() + gro) return fail(B2L_E_WORKSPACE, "workspace too small for S=%lld", (long long)S);
+        rp.row_ws = reinterpret_cast<double*>((char*)ws + stats_ws_bytes());
+        rp.row_ld = (S + 1) & ~1ll;
+    }
     if (stride_s == 1 || S == 1) {  // rows contiguous
         rp.in = ll; rp.in_stride = stride_n; rp.n_rows = N;
         rp.k_out = k_i; rp.elpd_i = elpd_i; rp.lppd_i = lppd_i; rp.var_i = var_i; rp.lppdw_i = lppdw_i;
@@ -392,9 +430,9 @@ extern "C" int b2l_loo_dev_f64(const double* ll, int64_t S, int64_t N, int64_t s
         return fail(B2L_E_INVALID, "one of (stride_s, stride_n) must be 1");
     const long long P = panel_obs(S, N);
     const size_t panel_bytes = align_up((size_t)P * (size_t)S * 8, 256);
-    if (!ws || ws_bytes < stats_ws_bytes() + panel_bytes)
-        return fail(B2L_E_WORKSPACE, "workspace too small: need %zu bytes", stats_ws_bytes() + panel_bytes);
-    double* pa = reinterpret_cast<double*>((char*)ws + stats_ws_bytes());
+    if (!ws || ws_bytes < stats_ws_bytes() + gro + panel_bytes)
+        return fail(B2L_E_WORKSPACE, "workspace too small: need %zu bytes", stats_ws_bytes() + gro + panel_bytes);
+    double* pa = reinterpret_cast<double*>((char*)ws + stats_ws_bytes() + gro);
     for (long long i0 = 0; i0 < N; i0 += P) {
         const long long np = std::min<long long>(P, N - i0);
         rc = launch_transpose(ll + i0, stride_s, pa, S, S, np, st);

@@ -132,7 +132,7 @@ def test_psislw_vs_oracle(S, N, reff, scale):
     x = scale * rng.normal(size=(N, S))
     lw, k, diag = gpu_psislw(x, reff, diag=True)
     ref_lw, ref_k = orc.psislw(x, reff)
-    close(k, ref_k)
+    close(k, ref_k, atol=1e-13)
     close(lw, ref_lw, atol=1e-12)
     M = orc.tail_length(S, reff)
     cut, cnt = oracle_tail(x, M)
@@ -181,7 +181,7 @@ def test_loo_vs_oracle_obs_fastest(S, N, reff):
     pw = orc.loo_pointwise(ll, reff)
     ww = orc.waic_pointwise(ll)
     close(r["elpd_i"], pw["elpd_i"])
-    close(r["pareto_k"], pw["pareto_k"])
+    close(r["pareto_k"], pw["pareto_k"], atol=1e-13)   # k can sit arbitrarily close to 0
     close(r["lppd_i"], pw["lppd_i"])
     close(r["var_i"], ww["var_i"])
     close(r["lppdw_i"], ww["lppd_i"])
@@ -203,7 +203,10 @@ def test_loo_special_values():
     for key_g, ref in (("elpd_i", pw["elpd_i"]), ("pareto_k", pw["pareto_k"]), ("lppd_i", pw["lppd_i"]),
                        ("var_i", ww["var_i"]), ("lppdw_i", ww["lppd_i"])):
         same_special(r[key_g], ref)
-        close(r[key_g], ref)
+        # obs 9 holds a +1e10 draw: the reference forms lw + ll = fl(fl(-1e10 - max - lse) + 1e10), which
+        # cancels to ~1e-6 absolute, i.e. its own elpd_i carries ~1e-9 of rounding noise there
+        # (pyloo/loo.py:289).  The kernel's closed form has no such cancellation; compare at 1e-8.
+        close(r[key_g], ref, rtol=1e-8 if key_g == "elpd_i" else RTOL)
     assert r["counters"][0] == 1 and r["counters"][1] == 1 and r["counters"][2] == 1
 
 
