@@ -441,7 +441,7 @@ __device__ void gpdfit_block(const double* t, int n, int m_hint, GpdScratch g, d
 
 // ------------------------------------------------------------------ the kernel
 template <int NT, int MODE>
-__global__ void __launch_bounds__(NT, (NT <= 256) ? 3 : 1) psis_row_kernel(const RowParams p) {
+__global__ void __launch_bounds__(NT, (NT == 128) ? 4 : ((NT == 256) ? 3 : 1)) psis_row_kernel(const RowParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NW = NT / 32;
     const RowSmemLayout L = row_smem_layout(p.S, p.M, p.cap, p.nbuf, NT);

@@ -68,6 +68,10 @@ static int plan_row(long long S, int M, int mode, long long n_rows, RowPlan* pl)
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     pl->sms = sms;
     pl->cap = std::max(512, pow2ceil(3ll * (M + 1)));
+    if (const char* ev = getenv("B2L_CAP")) {
+        int c = atoi(ev);
+        if (c >= 2 * (M + 1) && (c & (c - 1)) == 0) pl->cap = c;
+    }
     // rows in flight per SM: prefer more resident CTAs (more warps), double-buffer on a tie
     int best_ctas = 0, best_nbuf = 0, best_nt = 256;
     size_t best_smem = 0;
@@ -88,7 +92,7 @@ static int plan_row(long long S, int M, int mode, long long n_rows, RowPlan* pl)
     // tuning overrides (numerics are unaffected): B2L_NBUF = 1|2, B2L_NT = 256|512
     if (const char* ev = getenv("B2L_NBUF")) {
         int nb = atoi(ev), nt = getenv("B2L_NT") ? atoi(getenv("B2L_NT")) : best_nt;
-        if ((nb == 1 || nb == 2) && (nt == 256 || nt == 512)) {
+        if ((nb == 1 || nb == 2) && ((nt == 128 && 30 + (int)std::sqrt((double)M) <= 64) || nt == 256 || nt == 512)) {
             size_t smem = row_smem_layout((int)S, M, pl->cap, nb, nt).total;
             if (smem <= (size_t)smem_optin) {
                 best_nbuf = nb; best_nt = nt; best_smem = smem;
@@ -115,11 +119,13 @@ static int plan_row(long long S, int M, int mode, long long n_rows, RowPlan* pl)
     int occ = 0;
     cudaError_t e;
     if (mode == MODE_PSISLW)
-        e = (best_nt == 256) ? occupancy_of<256, MODE_PSISLW>(best_smem, &occ)
-                             : occupancy_of<512, MODE_PSISLW>(best_smem, &occ);
+        e = (best_nt == 128) ? occupancy_of<128, MODE_PSISLW>(best_smem, &occ)
+            : (best_nt == 256) ? occupancy_of<256, MODE_PSISLW>(best_smem, &occ)
+                               : occupancy_of<512, MODE_PSISLW>(best_smem, &occ);
     else
-        e = (best_nt == 256) ? occupancy_of<256, MODE_LOO>(best_smem, &occ)
-                             : occupancy_of<512, MODE_LOO>(best_smem, &occ);
+        e = (best_nt == 128) ? occupancy_of<128, MODE_LOO>(best_smem, &occ)
+            : (best_nt == 256) ? occupancy_of<256, MODE_LOO>(best_smem, &occ)
+                               : occupancy_of<512, MODE_LOO>(best_smem, &occ);
     CK(e);
     if (occ < 1) return fail(B2L_E_UNSUPPORTED, "row kernel does not fit on an SM (smem %zu)", best_smem);
     pl->ctas_per_sm = occ;
@@ -147,10 +153,12 @@ static int launch_rows(int mode, const RowPlan& pl, RowParams rp, cudaStream_t s
     int grid = (int)std::max<long long>(1, std::min<long long>(pl.grid, rp.n_rows));
     if (rp.n_rows == 0) return 0;
     if (mode == MODE_PSISLW) {
-        if (pl.nt == 256) psis_row_kernel<256, MODE_PSISLW><<<grid, 256, pl.smem, st>>>(rp);
+        if (pl.nt == 128) psis_row_kernel<128, MODE_PSISLW><<<grid, 128, pl.smem, st>>>(rp);
+        else if (pl.nt == 256) psis_row_kernel<256, MODE_PSISLW><<<grid, 256, pl.smem, st>>>(rp);
         else psis_row_kernel<512, MODE_PSISLW><<<grid, 512, pl.smem, st>>>(rp);
     } else {
-        if (pl.nt == 256) psis_row_kernel<256, MODE_LOO><<<grid, 256, pl.smem, st>>>(rp);
+        if (pl.nt == 128) psis_row_kernel<128, MODE_LOO><<<grid, 128, pl.smem, st>>>(rp);
+        else if (pl.nt == 256) psis_row_kernel<256, MODE_LOO><<<grid, 256, pl.smem, st>>>(rp);
         else psis_row_kernel<512, MODE_LOO><<<grid, 512, pl.smem, st>>>(rp);
     }
     CK(cudaGetLastError());
