@@ -19,6 +19,7 @@ SRC = os.path.join(_PKG, "csrc", "psisloo_b200.cu")
 HEADERS = [
     os.path.join(_PKG, "csrc", "b2l_common.cuh"),
     os.path.join(_PKG, "csrc", "b2l_row_kernel.cuh"),
+    os.path.join(_PKG, "csrc", "b2l_split.cuh"),
     os.path.join(_ROOT, "include", "psisloo_b200.h"),
 ]
 

@@ -49,6 +49,9 @@ struct RowParams {
     long long row_ld;
     int m_full;    // GPD grid size 30 + floor(sqrt(M)) for the common full tail n == M (host-computed)
     double cutoffmin;
+    // non-null: process rows row_list[0 .. *n_list) instead of 0 .. n_rows (rows the split path handed over)
+    const int* row_list;
+    const int* n_list;
 };
 
 struct RowSmemLayout {
@@ -483,22 +486,26 @@ __global__ void __launch_bounds__(NT, (NT == 128) ? 4 : ((NT == 256) ? 3 : 1)) p
         for (int i = tid; i < M; i += NT) l1p[i] = log1p(-(((double)i + 0.5) / (double)M));
     __syncthreads();
 
-    long long row = blockIdx.x;
-    if (p.use_bulk && tid == 0 && row < p.n_rows) {
+    const long long n_items = p.row_list ? (long long)*p.n_list : p.n_rows;
+    auto row_of = [&](long long item) -> long long { return p.row_list ? (long long)p.row_list[item] : item; };
+    long long item = blockIdx.x;
+    if (p.use_bulk && tid == 0 && item < n_items) {
         mbar_expect_tx(&bars[0], row_tx);
-        bulk_g2s(smem_raw + L.off_row, p.in + row * p.in_stride, row_tx, &bars[0]);
+        bulk_g2s(smem_raw + L.off_row, p.in + row_of(item) * p.in_stride, row_tx, &bars[0]);
     }
 
-    for (int it = 0; row < p.n_rows; row += gridDim.x, ++it) {
+    for (int it = 0; item < n_items; item += gridDim.x, ++it) {
+        const long long row = row_of(item);
         const int bsel = (p.nbuf == 2) ? (it & 1) : 0;
         double* rbuf = p.row_ws ? p.row_ws + (size_t)blockIdx.x * p.row_ld
                                 : reinterpret_cast<double*>(smem_raw + L.off_row + (size_t)bsel * L.row_bytes);
         const double2* rbuf2 = reinterpret_cast<const double2*>(rbuf);
-        const long long nrow = row + gridDim.x;
+        const long long nitem = item + gridDim.x;
+        const long long nrow = (nitem < n_items) ? row_of(nitem) : 0;
 
         // ---------------- stage the row
         if (p.use_bulk) {
-            if (p.nbuf == 2 && nrow < p.n_rows && tid == 0) {
+            if (p.nbuf == 2 && nitem < n_items && tid == 0) {
                 // the other buffer was stored from in the previous iteration: drain, then refill
                 bulk_wait_read0();
                 fence_proxy_async();
@@ -978,7 +985,7 @@ __global__ void __launch_bounds__(NT, (NT == 128) ? 4 : ((NT == 256) ? 3 : 1)) p
         }
 
         // ---------------- single-buffer mode: refill this buffer for the next row
-        if (p.use_bulk && p.nbuf == 1 && nrow < p.n_rows && tid == 0) {
+        if (p.use_bulk && p.nbuf == 1 && nitem < n_items && tid == 0) {
             if (MODE == MODE_PSISLW) bulk_wait_read0();
             fence_proxy_async();
             mbar_expect_tx(&bars[0], row_tx);

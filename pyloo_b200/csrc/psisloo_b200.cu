@@ -13,6 +13,7 @@
 
 #include "../../include/psisloo_b200.h"
 #include "b2l_row_kernel.cuh"
+#include "b2l_split.cuh"
 
 using namespace b2l;
 
@@ -163,6 +164,169 @@ static int launch_rows(int mode, const RowPlan& pl, RowParams rp, cudaStream_t s
     }
     CK(cudaGetLastError());
     return 0;
+}
+
+
+// ------------------------------------------------------------------------------------ split path
+// stream kernel (one CTA per observation, row in registers) + tail kernel (one warp per observation)
+// + the general row kernel on the rows those two hand over.  See b2l_split.cuh.
+struct SplitPlan {
+    int ok, nt, ept, tl, cap, q0, grid1, grid2, occ1, occ2;
+    size_t smem1, smem2;
+    long long batch;  // observations per stream -> tail -> fallback round
+};
+
+template <int NT, int EPT, int MODE>
+static cudaError_t stream_setup(size_t smem, int* occ) {
+    cudaError_t e = cudaFuncSetAttribute(psis_stream_kernel<NT, EPT, MODE>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, psis_stream_kernel<NT, EPT, MODE>, NT, smem);
+}
+template <int TL, int MODE>
+static cudaError_t tail_setup(size_t smem, int* occ) {
+    cudaError_t e = cudaFuncSetAttribute(psis_tail_kernel<TL, MODE>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, psis_tail_kernel<TL, MODE>, TAIL_WARPS * 32, smem);
+}
+
+#define B2L_STREAM_CASES(X)                                                                        \
+    X(128, 8) X(128, 16) X(256, 8) X(256, 16) X(512, 8) X(512, 16) X(1024, 8) X(1024, 16)
+
+// shape part of the plan: pure arithmetic (also sizes the workspace without touching the device)
+static bool split_shape(long long S, int M, long long n_rows, SplitPlan* sp) {
+    memset(sp, 0, sizeof(*sp));
+    if (const char* ev = getenv("B2L_SPLIT")) if (atoi(ev) == 0) return false;
+    if (getenv("B2L_FORCE_LEGACY")) return false;
+    if (S % 2 != 0 || S < 64 || S > SPLIT_MAX_S || M < 5 || M + 2 > 512 || (long long)M + 1 > S / 2) return false;
+    static const int shapes[8][2] = {{128, 8}, {128, 16}, {256, 8}, {256, 16}, {512, 8}, {512, 16}, {1024, 8}, {1024, 16}};
+    int nt = 0, ept = 0;
+    for (auto& sh : shapes) {
+        if ((long long)sh[0] * sh[1] >= S && (double)sh[0] >= 1.25 * (M + 1) &&
+            (nt == 0 || sh[0] * sh[1] < nt * ept)) {
+            nt = sh[0]; ept = sh[1];
+        }
+    }
+    if (!nt) return false;
+    sp->nt = nt; sp->ept = ept;
+    sp->tl = (M + 2 <= 128) ? 4 : ((M + 2 <= 256) ? 8 : 16);
+    sp->cap = 64 * sp->tl;
+    {
+        const double ratio = (double)(M + 1) / nt;
+        int q = (int)std::lround(32.0 * (1.0 - std::exp(-1.25 * ratio))) + (ratio > 0.45 ? 1 : 0);
+        if (const char* ev = getenv("B2L_Q0")) q = atoi(ev);
+        sp->q0 = std::min(30, std::max(1, q));
+    }
+    // observations per stream -> tail -> fallback round: ~128 MB of draws
+    long long b = (128ll << 20) / (S * 8);
+    b = std::min<long long>(16384, std::max<long long>(256, b / 64 * 64));
+    if (const char* ev = getenv("B2L_BATCH")) b = std::max<long long>(1, atoll(ev));
+    sp->batch = std::max<long long>(1, std::min<long long>(b, std::max<long long>(n_rows, 1)));
+    sp->smem1 = stream_smem((int)S).total;
+    sp->smem2 = tail_smem(M, sp->tl, TAIL_WARPS).total;
+    return true;
+}
+
+static int plan_split(long long S, int M, int mode, long long n_rows, SplitPlan* sp) {
+    if (!split_shape(S, M, n_rows, sp)) return 0;
+    const int nt = sp->nt, ept = sp->ept;
+    int dev = 0, sms = 0, smem_optin = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CK(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (sp->smem1 > (size_t)smem_optin || sp->smem2 > (size_t)smem_optin) return 0;
+    cudaError_t e = cudaErrorInvalidValue;
+#define X(NT_, EPT_)                                                                               \
+    if (nt == NT_ && ept == EPT_)                                                                  \
+        e = (mode == MODE_PSISLW) ? stream_setup<NT_, EPT_, MODE_PSISLW>(sp->smem1, &sp->occ1)     \
+                                  : stream_setup<NT_, EPT_, MODE_LOO>(sp->smem1, &sp->occ1);
+    B2L_STREAM_CASES(X)
+#undef X
+    CK(e);
+    if (sp->tl == 4) e = (mode == MODE_PSISLW) ? tail_setup<4, MODE_PSISLW>(sp->smem2, &sp->occ2) : tail_setup<4, MODE_LOO>(sp->smem2, &sp->occ2);
+    else if (sp->tl == 8) e = (mode == MODE_PSISLW) ? tail_setup<8, MODE_PSISLW>(sp->smem2, &sp->occ2) : tail_setup<8, MODE_LOO>(sp->smem2, &sp->occ2);
+    else e = (mode == MODE_PSISLW) ? tail_setup<16, MODE_PSISLW>(sp->smem2, &sp->occ2) : tail_setup<16, MODE_LOO>(sp->smem2, &sp->occ2);
+    CK(e);
+    if (sp->occ1 < 1 || sp->occ2 < 1) return 0;
+    sp->grid1 = sms * sp->occ1;
+    sp->grid2 = sms * sp->occ2;
+    sp->ok = 1;
+    return 0;
+}
+
+static size_t split_ws_bytes(const SplitPlan& sp) {
+    if (!sp.nt) return 0;
+    return align_up((size_t)sp.batch * sizeof(SplitHeader), 256) + align_up((size_t)sp.batch * sp.cap * 8, 256) +
+           align_up((size_t)sp.batch * 4, 256) + 256;
+}
+
+static int launch_split(int mode, const RowPlan& pl, const SplitPlan& sp, const RowParams& rp, void* sws,
+                        cudaStream_t st) {
+    char* w = (char*)sws;
+    SplitHeader* hdr = reinterpret_cast<SplitHeader*>(w);
+    w += align_up((size_t)sp.batch * sizeof(SplitHeader), 256);
+    unsigned long long* ckey = reinterpret_cast<unsigned long long*>(w);
+    w += align_up((size_t)sp.batch * sp.cap * 8, 256);
+    int* fb_list = reinterpret_cast<int*>(w);
+    w += align_up((size_t)sp.batch * 4, 256);
+    int* fb_count = reinterpret_cast<int*>(w);
+    int msq = (int)std::sqrt((double)rp.M);
+    while (msq * msq > rp.M) --msq;
+    while ((msq + 1) * (msq + 1) <= rp.M) ++msq;
+    for (long long i0 = 0; i0 < rp.n_rows; i0 += sp.batch) {
+        const long long nb = std::min<long long>(sp.batch, rp.n_rows - i0);
+        SplitParams q;
+        memset(&q, 0, sizeof(q));
+        q.in = rp.in + i0 * rp.in_stride; q.in_stride = rp.in_stride;
+        q.out = rp.out ? rp.out + i0 * rp.out_stride : nullptr; q.out_stride = rp.out_stride;
+        q.k_out = rp.k_out + i0;
+        q.elpd_i = rp.elpd_i ? rp.elpd_i + i0 : nullptr; q.lppd_i = rp.lppd_i ? rp.lppd_i + i0 : nullptr;
+        q.var_i = rp.var_i ? rp.var_i + i0 : nullptr; q.lppdw_i = rp.lppdw_i ? rp.lppdw_i + i0 : nullptr;
+        q.diag = rp.diag ? rp.diag + i0 * DIAG_STRIDE : nullptr;
+        q.n_rows = nb; q.S = rp.S; q.M = rp.M; q.cap = sp.cap; q.q0 = sp.q0; q.m_full = 30 + msq;
+        q.cutoffmin = rp.cutoffmin; q.counters = rp.counters; q.hdr = hdr; q.ckey = ckey; q.fb_list = fb_list; q.fb_count = fb_count;
+        CK(cudaMemsetAsync(fb_count, 0, sizeof(int), st));
+        const int g1 = (int)std::min<long long>(sp.grid1, nb);
+        const int g2 = (int)std::min<long long>(sp.grid2, (nb + TAIL_WARPS - 1) / TAIL_WARPS);
+#define X(NT_, EPT_)                                                                               \
+    if (sp.nt == NT_ && sp.ept == EPT_) {                                                          \
+        if (mode == MODE_PSISLW) psis_stream_kernel<NT_, EPT_, MODE_PSISLW><<<g1, NT_, sp.smem1, st>>>(q); \
+        else psis_stream_kernel<NT_, EPT_, MODE_LOO><<<g1, NT_, sp.smem1, st>>>(q);                \
+    }
+        B2L_STREAM_CASES(X)
+#undef X
+        CK(cudaGetLastError());
+        if (sp.tl == 4) {
+            if (mode == MODE_PSISLW) psis_tail_kernel<4, MODE_PSISLW><<<g2, TAIL_WARPS * 32, sp.smem2, st>>>(q);
+            else psis_tail_kernel<4, MODE_LOO><<<g2, TAIL_WARPS * 32, sp.smem2, st>>>(q);
+        } else if (sp.tl == 8) {
+            if (mode == MODE_PSISLW) psis_tail_kernel<8, MODE_PSISLW><<<g2, TAIL_WARPS * 32, sp.smem2, st>>>(q);
+            else psis_tail_kernel<8, MODE_LOO><<<g2, TAIL_WARPS * 32, sp.smem2, st>>>(q);
+        } else {
+            if (mode == MODE_PSISLW) psis_tail_kernel<16, MODE_PSISLW><<<g2, TAIL_WARPS * 32, sp.smem2, st>>>(q);
+            else psis_tail_kernel<16, MODE_LOO><<<g2, TAIL_WARPS * 32, sp.smem2, st>>>(q);
+        }
+        CK(cudaGetLastError());
+        // rows handed over: general kernel driven by the device-side list (empty list = no work)
+        RowParams r = rp;
+        r.in = q.in; r.out = q.out; r.k_out = q.k_out; r.elpd_i = q.elpd_i; r.lppd_i = q.lppd_i;
+        r.var_i = q.var_i; r.lppdw_i = q.lppdw_i; r.diag = q.diag; r.n_rows = nb;
+        r.row_list = fb_list; r.n_list = fb_count;
+        RowPlan pf = pl;
+        pf.grid = std::min(pl.grid, pl.sms);
+        int rc = launch_rows(mode, pf, r, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// rows contiguous: split path when the shape and alignment allow it, else the general kernel alone
+static int process_rows(int mode, const RowPlan& pl, const SplitPlan& sp, const RowParams& rp, void* sws,
+                        cudaStream_t st) {
+    if (sp.ok && sws && rp.use_bulk && !rp.waic_only && !rp.row_ws && !getenv("B2L_FORCE_LEGACY"))
+        return launch_split(mode, pl, sp, rp, sws, st);
+    return launch_rows(mode, pl, rp, st);
 }
 
 // ------------------------------------------------------------------------------------ transpose
@@ -336,9 +500,13 @@ extern "C" int b2l_device_count(void) {
 
 extern "C" int b2l_workspace_bytes(int64_t S, int64_t N, int32_t M, int32_t layout_obs_fastest,
                                    size_t* out_bytes) {
-    (void)M;
     if (!out_bytes || S < 1 || N < 0) return fail(B2L_E_INVALID, "bad arguments");
     size_t b = stats_ws_bytes() + grows_ws_bytes(S);
+    {
+        SplitPlan sp;
+        split_shape(S, M, layout_obs_fastest ? panel_obs(S, N) : N, &sp);
+        b += split_ws_bytes(sp);
+    }
     if (layout_obs_fastest) b += 2 * align_up((size_t)panel_obs(S, N) * (size_t)S * 8, 256);
     *out_bytes = b;
     return 0;
@@ -366,21 +534,30 @@ extern "C" int b2l_psislw_dev_f64(const double* lw, int64_t S, int64_t N, int64_
         rp.row_ld = (S + 1) & ~1ll;
     }
     const bool rows_in = (stride_s == 1 || S == 1), rows_out = (ostride_s == 1 || S == 1);
+    SplitPlan sp;
+    const size_t sws_off = stats_ws_bytes() + gro;
     if (rows_in && rows_out) {
         rp.in = lw; rp.in_stride = stride_n; rp.out = lw_out; rp.out_stride = ostride_n; rp.n_rows = N;
         rp.use_bulk = (S % 2 == 0) && aligned16(lw) && aligned16(lw_out) && (stride_n % 2 == 0) &&
                       (ostride_n % 2 == 0);
-        return launch_rows(MODE_PSISLW, pl, rp, st);
+        rc = plan_split(S, M, MODE_PSISLW, N, &sp);
+        if (rc) return rc;
+        void* sws = (ws && ws_bytes >= sws_off + split_ws_bytes(sp)) ? (char*)ws + sws_off : nullptr;
+        return process_rows(MODE_PSISLW, pl, sp, rp, sws, st);
     }
     if (!((stride_n == 1 || N == 1) || rows_in) || !((ostride_n == 1 || N == 1) || rows_out))
         return fail(B2L_E_INVALID, "one of (stride_s, stride_n) must be 1 for input and output");
     // obs-fastest on either side: go through row panels
     const long long P = panel_obs(S, N);
     const size_t panel_bytes = align_up((size_t)P * (size_t)S * 8, 256);
-    if (!ws || ws_bytes < stats_ws_bytes() + gro + 2 * panel_bytes)
-        return fail(B2L_E_WORKSPACE, "workspace too small: need %zu bytes", stats_ws_bytes() + gro + 2 * panel_bytes);
-    double* pa = reinterpret_cast<double*>((char*)ws + stats_ws_bytes() + gro);
-    double* pb = reinterpret_cast<double*>((char*)ws + stats_ws_bytes() + gro + panel_bytes);
+    rc = plan_split(S, M, MODE_PSISLW, P, &sp);
+    if (rc) return rc;
+    const size_t pan_off = sws_off + split_ws_bytes(sp);
+    if (!ws || ws_bytes < pan_off + 2 * panel_bytes)
+        return fail(B2L_E_WORKSPACE, "workspace too small: need %zu bytes", pan_off + 2 * panel_bytes);
+    void* sws = (char*)ws + sws_off;
+    double* pa = reinterpret_cast<double*>((char*)ws + pan_off);
+    double* pb = reinterpret_cast<double*>((char*)ws + pan_off + panel_bytes);
     for (long long i0 = 0; i0 < N; i0 += P) {
         const long long np = std::min<long long>(P, N - i0);
         RowParams r = rp;
@@ -395,7 +572,7 @@ extern "C" int b2l_psislw_dev_f64(const double* lw, int64_t S, int64_t N, int64_
         else { r.out = pb; r.out_stride = S; }
         r.use_bulk = (S % 2 == 0) && aligned16(r.in) && aligned16(r.out) && (r.in_stride % 2 == 0) &&
                      (r.out_stride % 2 == 0);
-        rc = launch_rows(MODE_PSISLW, pl, r, st);
+        rc = process_rows(MODE_PSISLW, pl, sp, r, sws, st);
         if (rc) return rc;
         if (!rows_out) {
             rc = launch_transpose(pb, S, lw_out + i0, ostride_s, np, S, st);  // (np x S) -> (S x np)
@@ -427,20 +604,29 @@ extern "C" int b2l_loo_dev_f64(const double* ll, int64_t S, int64_t N, int64_t s
         rp.row_ws = reinterpret_cast<double*>((char*)ws + stats_ws_bytes());
         rp.row_ld = (S + 1) & ~1ll;
     }
+    SplitPlan sp;
+    const size_t sws_off = stats_ws_bytes() + gro;
     if (stride_s == 1 || S == 1) {  // rows contiguous
         rp.in = ll; rp.in_stride = stride_n; rp.n_rows = N;
         rp.k_out = k_i; rp.elpd_i = elpd_i; rp.lppd_i = lppd_i; rp.var_i = var_i; rp.lppdw_i = lppdw_i;
         rp.diag = diag;
         rp.use_bulk = (S % 2 == 0) && aligned16(ll) && (stride_n % 2 == 0);
-        return launch_rows(MODE_LOO, pl, rp, st);
+        rc = plan_split(S, M, MODE_LOO, N, &sp);
+        if (rc) return rc;
+        void* sws = (ws && ws_bytes >= sws_off + split_ws_bytes(sp)) ? (char*)ws + sws_off : nullptr;
+        return process_rows(MODE_LOO, pl, sp, rp, sws, st);
     }
     if (!(stride_n == 1 || N == 1))
         return fail(B2L_E_INVALID, "one of (stride_s, stride_n) must be 1");
     const long long P = panel_obs(S, N);
     const size_t panel_bytes = align_up((size_t)P * (size_t)S * 8, 256);
-    if (!ws || ws_bytes < stats_ws_bytes() + gro + panel_bytes)
-        return fail(B2L_E_WORKSPACE, "workspace too small: need %zu bytes", stats_ws_bytes() + gro + panel_bytes);
-    double* pa = reinterpret_cast<double*>((char*)ws + stats_ws_bytes() + gro);
+    rc = plan_split(S, M, MODE_LOO, P, &sp);
+    if (rc) return rc;
+    const size_t pan_off = sws_off + split_ws_bytes(sp);
+    if (!ws || ws_bytes < pan_off + panel_bytes)
+        return fail(B2L_E_WORKSPACE, "workspace too small: need %zu bytes", pan_off + panel_bytes);
+    void* sws = (char*)ws + sws_off;
+    double* pa = reinterpret_cast<double*>((char*)ws + pan_off);
     for (long long i0 = 0; i0 < N; i0 += P) {
         const long long np = std::min<long long>(P, N - i0);
         rc = launch_transpose(ll + i0, stride_s, pa, S, S, np, st);
@@ -450,7 +636,7 @@ extern "C" int b2l_loo_dev_f64(const double* ll, int64_t S, int64_t N, int64_t s
         r.k_out = k_i + i0; r.elpd_i = elpd_i + i0; r.lppd_i = lppd_i + i0; r.var_i = var_i + i0;
         r.lppdw_i = lppdw_i + i0; r.diag = diag ? diag + i0 * DIAG_STRIDE : nullptr;
         r.use_bulk = (S % 2 == 0) && aligned16(pa);
-        rc = launch_rows(MODE_LOO, pl, r, st);
+        rc = process_rows(MODE_LOO, pl, sp, r, sws, st);
         if (rc) return rc;
     }
     return 0;
