@@ -15,11 +15,13 @@ import threading
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "lib", "libpsisloo_b200.so")
-SRC = os.path.join(_PKG, "csrc", "psisloo_b200.cu")
+SRCS = [os.path.join(_PKG, "csrc", n) for n in ("psisloo_b200.cu", "b2l_split_stream.cu", "b2l_split_tail.cu")]
+SRC = SRCS[0]
 HEADERS = [
     os.path.join(_PKG, "csrc", "b2l_common.cuh"),
     os.path.join(_PKG, "csrc", "b2l_row_kernel.cuh"),
     os.path.join(_PKG, "csrc", "b2l_split.cuh"),
+    os.path.join(_PKG, "csrc", "b2l_split_host.h"),
     os.path.join(_ROOT, "include", "psisloo_b200.h"),
 ]
 
@@ -49,7 +51,7 @@ def needs_build() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
     built = os.path.getmtime(LIB_PATH)
-    return any(os.path.getmtime(p) > built for p in [SRC, *HEADERS])
+    return any(os.path.getmtime(p) > built for p in [*SRCS, *HEADERS])
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -57,18 +59,31 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
     os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
-    cmd = [
-        _nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-        "-Xcompiler", "-fPIC", "-shared", "-o", LIB_PATH, SRC,
-    ]
+    objdir = os.path.join(_PKG, "lib", "obj")
+    os.makedirs(objdir, exist_ok=True)
+    flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+             "-Xcompiler", "-fPIC"]
     if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
+        flags += ["-Xptxas", "-v"]
+    # one nvcc per translation unit, in parallel (the kernel templates dominate the build time)
+    procs, objs = [], []
+    for src in SRCS:
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        procs.append((src, subprocess.Popen([_nvcc(), *flags, "-c", "-o", obj, src],
+                                            stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    logs = []
+    for src, pr in procs:
+        out, err = pr.communicate()
+        logs.append(err)
+        if pr.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{out}\n{err}")
+    res = subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH, *objs],
+                         capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
+        raise RuntimeError(f"nvcc link failed:\n{res.stdout}\n{res.stderr}")
     if verbose:
-        print(res.stderr)
+        print("\n".join(logs))
     return LIB_PATH
 
 

@@ -103,11 +103,11 @@ __host__ __device__ inline RowSmemLayout row_smem_layout(int S, int M, int cap, 
 // ------------------------------------------------------------------ fast exp for x <= 0
 // exp(x), x in [-708, 0]: Cody-Waite reduction, degree-13 Taylor/Horner, exponent insertion.
 // Max error ~1 ulp.  Anything below -708 (denormal results, -inf) goes to the library routine.
-__constant__ double c_exp_poly[12] = {
+static __constant__ double c_exp_poly[12] = {
     1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07,
     2.7557319223985893e-06, 2.48015873015873e-05, 1.984126984126984e-04, 1.388888888888889e-03,
     8.333333333333333e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, 0.5};  // 1/13! .. 1/2!
-__constant__ double c_exp_red[4] = {1.4426950408889634074, 6755399441055744.0,
+static __constant__ double c_exp_red[4] = {1.4426950408889634074, 6755399441055744.0,
                                     -6.93147180369123816490e-01, -1.90821492927058770002e-10};
 
 __device__ __forceinline__ double exp_nonpos(double x) {

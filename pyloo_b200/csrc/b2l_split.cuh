@@ -138,15 +138,24 @@ __host__ __device__ inline StreamSmem stream_smem(int S) {
     return L;
 }
 
+// compare-select max / min: fmax / fmin on doubles expand to ~8 instructions each (IEEE NaN rules);
+// rows that hold a NaN are detected separately and leave the fast path, so plain selects are enough
+__device__ __forceinline__ double max_sel(double a, double b) { return (b > a) ? b : a; }
+__device__ __forceinline__ double min_sel(double a, double b) { return (b < a) ? b : a; }
+__device__ __forceinline__ double warp_max_sel(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max_sel(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
 template <int NW>
 __device__ __forceinline__ double slots_max(const double* s, int lane) {
     if (NW <= 8) {
         double r = s[0];
 #pragma unroll
-        for (int i = 1; i < NW; ++i) r = fmax(r, s[i]);
+        for (int i = 1; i < NW; ++i) r = max_sel(r, s[i]);
         return r;
     }
-    return warp_max(lane < NW ? s[lane] : -inf_f64());
+    return warp_max_sel(lane < NW ? s[lane] : -inf_f64());
 }
 template <int NW>
 __device__ __forceinline__ double slots_sum(const double* s, int lane) {
@@ -227,19 +236,19 @@ __global__ void __launch_bounds__(NT, stream_min_blocks<NT>()) psis_stream_kerne
         int spec = 0;
 #pragma unroll
         for (int j = 0; j < EP2; ++j) {
-            m0 = fmax(m0, fmax(v[j].x, v[j].y));  // NaN-free rows only matter; flagged rows leave
+            m0 = max_sel(m0, max_sel(v[j].x, v[j].y));  // NaN-free rows only matter; flagged rows leave
             if (j < nv) {
                 spec = max(spec, max(__double2hiint(v[j].x) & 0x7fffffff, __double2hiint(v[j].y) & 0x7fffffff));
                 if (MODE == MODE_LOO) {
-                    n0 = fmin(n0, fmin(v[j].x, v[j].y));
+                    n0 = min_sel(n0, min_sel(v[j].x, v[j].y));
                     s0 += v[j].x + v[j].y;
                 }
             }
         }
         const double tmax = m0;  // this thread's maximum: one "bin" of the threshold estimate
-        m0 = warp_max(m0);
+        m0 = warp_max_sel(m0);
         if (MODE == MODE_LOO) {
-            n0 = warp_min(n0);
+            n0 = -warp_max_sel(-n0);
             s0 = warp_sum(s0);
         }
         if (lane == 0) {
@@ -285,7 +294,7 @@ __global__ void __launch_bounds__(NT, stream_min_blocks<NT>()) psis_stream_kerne
                     rank += (o < mine || (o == mine && j < lane)) ? 1 : 0;
                 }
                 const unsigned b = __ballot_sync(FULL, lane < NW && rank == NW / 2 - 1 + (NW == 1));
-                taux = fmax(-(double)__shfl_sync(FULL, mine, __ffs(b) - 1), -1e300);  // padding (-inf) never qualifies
+                taux = max_sel(-(double)__shfl_sync(FULL, mine, __ffs(b) - 1), -1e300);  // padding (-inf) never qualifies
             }
             // -------- pass B: body exp-sum, candidate marks.  `mxl` is laundered through an empty asm so
             // the compiler cannot hoist the (threshold-independent) exps out of the retry loop and
@@ -304,10 +313,10 @@ __global__ void __launch_bounds__(NT, stream_min_blocks<NT>()) psis_stream_kerne
                     const double x = r - mxl;  // psis.py:134
                     const bool cand = x >= taux;
                     cmask |= cand ? (1u << (2 * j + h)) : 0u;
-                    const double xc = fmax(x, -700.0);
+                    // x < -700 (and the -inf padding) runs through the exp as garbage that is never added
                     if (MODE == MODE_LOO && !wide) {
                         double ep, em;
-                        exp_tab_pm(xc, tb, ep, em);
+                        exp_tab_pm(x, tb, ep, em);
                         if (!cand && x >= -700.0) bs += ep;
                         if (j < nv) {
                             ls += em;  // exp(ll - ll_min)
@@ -315,7 +324,7 @@ __global__ void __launch_bounds__(NT, stream_min_blocks<NT>()) psis_stream_kerne
                             vs = fma(d, d, vs);
                         }
                     } else {
-                        const double e = exp_tab(xc, tb);
+                        const double e = exp_tab(x, tb);
                         if (!cand && x >= -700.0) bs += e;
                         if (MODE == MODE_LOO && j < nv) {
                             ls += exp(-r - ll_max_l);  // wide rows: literal (utils.py:349-351)
@@ -405,32 +414,42 @@ __global__ void __launch_bounds__(NT, stream_min_blocks<NT>()) psis_stream_kerne
 // ------------------------------------------------------------------ tail kernel helpers
 __device__ __forceinline__ double shfl_f64(double v, int src) { return __shfl_sync(FULL, v, src); }
 
-// Bitonic sort of 32 * CAPL doubles (all >= 0, no NaN) held as k[i] <-> element e = 32 i + lane,
-// ascending in e.  Partner distances below 32 are lane shuffles, the rest are register pairs.
+// Bitonic sort of 32 * CAPL unsigned 64-bit keys held as k[i] <-> element e = 32 i + lane, ascending
+// in e.  The (kk, j) stage loop is a RUN-TIME loop (the kernel must stay small enough for the
+// instruction cache: a fully unrolled 512-key network alone is ~60 KB of SASS); only the per-register
+// loop is unrolled.  Partner distances below 32 are lane shuffles, the rest are register pairs.
+template <int CAPL, int DJ>
+__device__ __forceinline__ void bitonic_inlane(unsigned long long (&k)[CAPL], int kk) {
+#pragma unroll
+    for (int i = 0; i < CAPL; ++i) {
+        if ((i & DJ) == 0 && (i | DJ) < CAPL) {
+            const bool up = (((i << 5) & kk) == 0);
+            const unsigned long long a = k[i], b = k[i | DJ];
+            const bool sw = (a > b) == up;
+            k[i] = sw ? b : a;
+            k[i | DJ] = sw ? a : b;
+        }
+    }
+}
 template <int CAPL>
-__device__ __forceinline__ void warp_bitonic_sort(double (&k)[CAPL], int lane) {
-#pragma unroll
+__device__ __forceinline__ void warp_bitonic_sort(unsigned long long (&k)[CAPL], int lane) {
+#pragma unroll 1
     for (int kk = 2; kk <= 32 * CAPL; kk <<= 1) {
-#pragma unroll
+#pragma unroll 1
         for (int j = kk >> 1; j > 0; j >>= 1) {
             if (j >= 32) {
                 const int dj = j >> 5;
-#pragma unroll
-                for (int i = 0; i < CAPL; ++i) {
-                    if ((i & dj) == 0) {
-                        const bool up = (((i << 5) & kk) == 0);
-                        const double a = k[i], b = k[i | dj];
-                        const bool sw = (a > b) == up;
-                        k[i] = sw ? b : a;
-                        k[i | dj] = sw ? a : b;
-                    }
-                }
+                if (dj == 1) bitonic_inlane<CAPL, 1>(k, kk);
+                else if (dj == 2) bitonic_inlane<CAPL, 2>(k, kk);
+                else if (dj == 4) bitonic_inlane<CAPL, 4>(k, kk);
+                else if (dj == 8) bitonic_inlane<CAPL, 8>(k, kk);
+                else bitonic_inlane<CAPL, 16>(k, kk);
             } else {
                 const bool lower = ((lane & j) == 0);
 #pragma unroll
                 for (int i = 0; i < CAPL; ++i) {
-                    const bool up = (kk >= 32) ? (((i << 5) & kk) == 0) : ((lane & kk) == 0);
-                    const double o = __shfl_xor_sync(FULL, k[i], j);
+                    const bool up = ((((i << 5) | lane) & kk) == 0);
+                    const unsigned long long o = __shfl_xor_sync(FULL, k[i], j);
                     const bool take_o = ((k[i] < o) != (up == lower));
                     k[i] = take_o ? o : k[i];
                 }
@@ -449,116 +468,106 @@ __device__ __forceinline__ bool rescale_pos_w(double& P, int& E) {
     return true;
 }
 
-// sum_i log1p(nb * t_i) over the warp's tail (t in shared memory, n values), literal form
-__device__ __forceinline__ double warp_log1p_sum(const double* t, int n, double nb, int lane) {
+// sum_i log1p(nb * t_i) over the warp's tail (t in shared memory, n values), literal form (rare)
+static __device__ __noinline__ double warp_log1p_sum(const double* t, int n, double nb, int lane) {
     double acc = 0.0;
     for (int i = lane; i < n; i += 32) acc += log1p(nb * t[i]);
     return warp_sum(acc);
 }
 
-// log prod_i (1 + nb t_i) for NJ grid points per lane (t broadcast from shared memory).
-template <int NJ>
-__device__ __forceinline__ bool gpd_products(const double* t, int n, const double (&nb)[4], int every,
-                                             double (&out)[4]) {
-    double P[NJ];
-    int E[NJ];
+// log prod_i (1 + nb t_i) for two grid points per lane (t broadcast from shared memory)
+__device__ __forceinline__ bool gpd_products2(const double* t, int n, double nb0, double nb1, int every,
+                                              double& out0, double& out1) {
+    double P0 = 1.0, P1 = 1.0;
+    int E0 = 0, E1 = 0;
     bool ok = true;
-#pragma unroll
-    for (int r = 0; r < NJ; ++r) {
-        P[r] = 1.0;
-        E[r] = 0;
-    }
     int i = 0;
+#pragma unroll 1
     while (i < n) {
         const int stop = min(n, i + every);
+#pragma unroll 4
         for (; i + 2 <= stop; i += 2) {  // t is 16 B aligned and `every` is even
             const double2 tt = *reinterpret_cast<const double2*>(t + i);
-#pragma unroll
-            for (int r = 0; r < NJ; ++r) {
-                P[r] *= fma(nb[r], tt.x, 1.0);
-                P[r] *= fma(nb[r], tt.y, 1.0);
-            }
+            P0 *= fma(nb0, tt.x, 1.0);
+            P1 *= fma(nb1, tt.x, 1.0);
+            P0 *= fma(nb0, tt.y, 1.0);
+            P1 *= fma(nb1, tt.y, 1.0);
         }
         if (i < stop) {
             const double t0 = t[i];
-#pragma unroll
-            for (int r = 0; r < NJ; ++r) P[r] *= fma(nb[r], t0, 1.0);
+            P0 *= fma(nb0, t0, 1.0);
+            P1 *= fma(nb1, t0, 1.0);
             ++i;
         }
-#pragma unroll
-        for (int r = 0; r < NJ; ++r) ok = rescale_pos_w(P[r], E[r]) && ok;
+        ok = rescale_pos_w(P0, E0) && ok;
+        ok = rescale_pos_w(P1, E1) && ok;
     }
-#pragma unroll
-    for (int r = 0; r < NJ; ++r) out[r] = log(P[r]) + (double)E[r] * 0.6931471805599453094;
+    out0 = log(P0) + (double)E0 * 0.6931471805599453094;
+    out1 = log(P1) + (double)E1 * 0.6931471805599453094;
     return ok;
 }
 
 // Zhang-Stephens fit for one warp (pyloo/psis.py:181-208).  t: shared memory, DESCENDING (t[0] is
-// the largest), n >= 5.  Returns false when the row must go to the general kernel.
-__device__ bool gpdfit_warp(const double* t, int n, int m, double tsum, int lane, double& k_out,
-                            double& sigma_out) {
+// the largest), n >= 5, grid size m <= 64 (two grid points per lane).  Returns false when the row
+// must go to the general kernel.
+__device__ __forceinline__ bool gpdfit_warp(const double* t, int n, int m, double tsum, int lane, double& k_out,
+                                            double& sigma_out) {
     const double tq = t[n - ((int)((double)n / 4.0 + 0.5))];  // ascending index int(n/4+.5)-1 (psis.py:187)
     const double tn = t[0];
-    if (!(tq > 0.0) || !is_finite(tn) || m > 128) return false;
-    const int NJ = (m + 31) >> 5;
-    double b[4], nb[4], ks[4];
-    bool flag[4];
+    if (!(tq > 0.0) || !is_finite(tn) || m > 64) return false;
+    double b[2], ks[2];
+    bool flag[2];
     double bmag = 0.0;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < 2; ++r) {
         const int j = lane + 32 * r;
         double bj = 1.0 - sqrt((double)m / ((double)(j + 1) - 0.5));  // psis.py:186
         bj /= 3.0 * tq;                                                // psis.py:187
         bj += 1.0 / tn;                                                // psis.py:188
         const bool live = j < m;
         b[r] = live ? bj : 0.0;
-        nb[r] = -b[r];
         ks[r] = 0.0;
         flag[r] = live && (fabs(bj) * tsum < 0.015625);
-        if (live) bmag = fmax(bmag, fabs(bj));
+        if (live) bmag = (fabs(bj) > bmag) ? fabs(bj) : bmag;
         if (live && !is_finite(bj)) bmag = inf_f64();
     }
     bmag = warp_max(bmag);
     const double fmx = 1.0 + bmag * tn;
     if (!(fmx < 0x1p31)) return false;
-    bool ok;
-    const int every = 32;  // (2^31)^32 < 2^1023 and (1 - b_max t_n)^32 > 2^-290: no over/underflow
-    if (NJ == 1) ok = gpd_products<1>(t, n, nb, every, ks);
-    else if (NJ == 2) ok = gpd_products<2>(t, n, nb, every, ks);
-    else if (NJ == 3) ok = gpd_products<3>(t, n, nb, every, ks);
-    else ok = gpd_products<4>(t, n, nb, every, ks);
+    // (2^31)^32 < 2^1023 and (1 - b_max t_n)^32 > 2^-340: rescaling every 32 factors cannot over/underflow
+    const bool ok = gpd_products2(t, n, -b[0], -b[1], 32, ks[0], ks[1]);
     if (!__all_sync(FULL, ok)) return false;
     // grid points where the product form loses relative accuracy: literal log1p sum
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < 2; ++r) {
         unsigned fm = __ballot_sync(FULL, flag[r]);
         while (fm) {
             const int src = __ffs(fm) - 1;
             fm &= fm - 1;
-            const double nbj = shfl_f64(nb[r], src);
+            const double nbj = shfl_f64(-b[r], src);
             const double acc = warp_log1p_sum(t, n, nbj, lane);
             if (lane == src) ks[r] = acc;
         }
     }
     // profile log-likelihood (psis.py:190-191) and weights (psis.py:192)
-    double Lj[4];
+    double Lj[2];
     double lm = -inf_f64();
     bool fin = true;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < 2; ++r) {
         const bool live = (lane + 32 * r) < m;
         const double kj = ks[r] / (double)n;
         Lj[r] = live ? (double)n * (log(-(b[r] / kj)) - kj - 1.0) : -inf_f64();
         if (live) {
             fin = fin && is_finite(Lj[r]);
-            lm = fmax(lm, Lj[r]);
+            lm = (Lj[r] > lm) ? Lj[r] : lm;
         }
     }
     if (!__all_sync(FULL, fin)) return false;
     lm = warp_max(lm);
-    double w[4], es = 0.0;
+    double w[2], es = 0.0;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < 2; ++r) {
         w[r] = ((lane + 32 * r) < m) ? exp(Lj[r] - lm) : 0.0;
         es += w[r];
     }
@@ -566,7 +575,7 @@ __device__ bool gpdfit_warp(const double* t, int n, int m, double tsum, int lane
     const double thr = 10.0 * 2.220446049250313e-16;
     double ws = 0.0;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < 2; ++r) {
         w[r] = w[r] / es;
         if (w[r] < thr) w[r] = 0.0;  // psis.py:194-197 (dead grid points already carry 0)
         ws += w[r];
@@ -574,35 +583,27 @@ __device__ bool gpdfit_warp(const double* t, int n, int m, double tsum, int lane
     ws = warp_sum(ws);
     double bp = 0.0;
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < 2; ++r)
         if (w[r] != 0.0) bp += b[r] * (w[r] / ws);  // psis.py:198-201
     bp = warp_sum(bp);
     // k_post = mean log1p(-b_post t) (psis.py:203): product form unless it loses accuracy
     double lsum;
-    if (fabs(bp) * tsum < 0.015625 || !is_finite(bp)) {
-        lsum = warp_log1p_sum(t, n, -bp, lane);
-    } else {
+    bool literal = (fabs(bp) * tsum < 0.015625) || !is_finite(bp);
+    if (!literal) {
         double P = 1.0;
         int E = 0;
-        bool okp = true;
-        int cnt = 0;
-        for (int i = lane; i < n; i += 32) {
-            P *= fma(-bp, t[i], 1.0);
-            if (++cnt == 32) {
-                cnt = 0;
-                okp = rescale_pos_w(P, E) && okp;
-            }
-        }
-        okp = rescale_pos_w(P, E) && okp;
+        for (int i = lane; i < n; i += 32) P *= fma(-bp, t[i], 1.0);  // <= 16 factors < 2^31 each
+        bool okp = rescale_pos_w(P, E);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             P *= __shfl_xor_sync(FULL, P, o);
             E += __shfl_xor_sync(FULL, E, o);
         }
         okp = rescale_pos_w(P, E) && okp;
-        if (!__all_sync(FULL, okp)) lsum = warp_log1p_sum(t, n, -bp, lane);
+        if (!__all_sync(FULL, okp)) literal = true;
         else lsum = log(P) + (double)E * 0.6931471805599453094;
     }
+    if (literal) lsum = warp_log1p_sum(t, n, -bp, lane);
     const double k_post = lsum / (double)n;
     sigma_out = -k_post / bp;                                  // psis.py:205
     k_out = ((double)n * k_post + 5.0) / ((double)n + 10.0);   // psis.py:206
@@ -610,135 +611,133 @@ __device__ bool gpdfit_warp(const double* t, int n, int m, double tsum, int lane
 }
 
 struct TailSmem {
-    size_t off_l1p, off_t, t_stride, total;
+    size_t off_l1p, off_w, w_stride, off_x, off_t, off_s, total;
 };
+// per-warp staging: xs[32 TL] exact x of the head of the order, tb[32 TL] t_i / smoothed values,
+// ss[32 TL] draw indices
 __host__ __device__ inline TailSmem tail_smem(int M, int TL, int warps) {
     TailSmem L;
     L.off_l1p = 0;
     size_t o = align_up((size_t)(M + 1) * 8, 16);
-    L.off_t = o;
-    L.t_stride = (size_t)32 * TL * 8;
-    o += L.t_stride * warps;
+    L.off_w = o;
+    L.off_x = 0;
+    L.off_t = (size_t)32 * TL * 8;
+    L.off_s = (size_t)32 * TL * 16;
+    L.w_stride = (size_t)32 * TL * 20;
+    o += L.w_stride * warps;
     L.total = align_up(o, 128);
     return L;
 }
 
 constexpr int TAIL_WARPS = 4;
 
-// One row for one warp.  Returns false -> general kernel.
-template <int CAPL, int TL, int MODE>
-__device__ __forceinline__ bool tail_row(const SplitParams& p, long long row, const SplitHeader& h,
-                                         const double* l1p, double* tsh, int lane) {
-    const int S = p.S, M = p.M, C = h.C;
-    const double mx = h.mx;
-    const double PAD = inf_f64();
-    const double* src = p.in + row * p.in_stride;
+struct SortOut {
+    int n_lt, n_eq;
+    bool run_escapes;  // ties with the cutoff key beyond the staged range
+};
 
-    // ---- candidate keys -> registers, sort ascending (= descending x, ties by descending draw index)
-    double k[CAPL];
+// keys -> registers, sort ascending (= descending x, ties by descending draw index), stage the exact
+// values of the first 32 TL elements (tail + cutoff) and the rest's x (never in the tail) to smem.
+template <int CAPL, int TL, int MODE>
+__device__ __forceinline__ SortOut sort_and_stage(const double* src, const unsigned long long* ck, int M, int C,
+                                                  double mx, double* xs, double* tb, int* ss, int lane) {
+    unsigned long long k[CAPL];
     {
-        const unsigned long long* ck = p.ckey + (size_t)row * (size_t)p.cap;
 #pragma unroll
         for (int i = 0; i < CAPL; ++i) {
             const int e = 32 * i + lane;
-            k[i] = (e < C) ? __longlong_as_double((long long)ck[e]) : PAD;
+            k[i] = (e < C) ? ck[e] : 0x7ff0000000000000ull;  // pad: above every finite |x|
         }
     }
     warp_bitonic_sort<CAPL>(k, lane);
-
-    // ---- exact values of the head of the order (tail + cutoff), gathered from the row
-    double xt[TL];
-    int st[TL];
-#pragma unroll
-    for (int i = 0; i < TL; ++i) {
-        const int e = 32 * i + lane;
-        st[i] = (int)(KEY_IDX_MASK - ((unsigned)__double2loint(k[i]) & KEY_IDX_MASK));
-        const double v = (e < C) ? src[st[i]] : 0.0;
-        xt[i] = (e < C) ? ((MODE == MODE_LOO) ? -v : v) - mx : -inf_f64();
-    }
-    // candidates that can never be in the tail (e >= 32 TL > M): their exp goes to the normaliser
-    double nont = 0.0;
-#pragma unroll
-    for (int i = TL; i < CAPL; ++i) {
-        const int e = 32 * i + lane;
-        if (32 * i < C) {
-            const int s = (int)(KEY_IDX_MASK - ((unsigned)__double2loint(k[i]) & KEY_IDX_MASK));
-            if (e < C) {
-                const double v = src[s];
-                nont += exp(((MODE == MODE_LOO) ? -v : v) - mx);
-            }
-        }
-    }
-
-    // ---- cutoff = (M+1)-th largest = element M of the order (psis.py:135-136)
-    double kc = 0.0, xc = 0.0;
-#pragma unroll
-    for (int i = 0; i < TL; ++i)
-        if (i == (M >> 5)) {
-            kc = k[i];
-            xc = xt[i];
-        }
-    kc = shfl_f64(kc, M & 31);
-    xc = shfl_f64(xc, M & 31);
-    const unsigned long long tc = (unsigned long long)__double_as_longlong(kc) >> KEY_IDX_BITS;
-    int n_lt = 0, n_eq = 0;
-    bool bad = false;
 #pragma unroll
     for (int i = 0; i < CAPL; ++i) {
-        const unsigned long long ti = (unsigned long long)__double_as_longlong(k[i]) >> KEY_IDX_BITS;
-        const bool eq = (ti == tc);
-        n_lt += __popc(__ballot_sync(FULL, ti < tc));
-        n_eq += __popc(__ballot_sync(FULL, eq));
-        if (i < TL) {
-            if (eq && xt[i] != xc) bad = true;  // distinct values share the truncated key at the cutoff
-        } else if (eq) {
-            bad = true;  // the run of cutoff ties leaves the gathered range
+        const int e = 32 * i + lane;
+        if (32 * i < C) {
+            const int s = (int)(KEY_IDX_MASK - ((unsigned)k[i] & KEY_IDX_MASK));
+            double x = -inf_f64();
+            if (e < C) {
+                const double v = src[s];
+                x = ((MODE == MODE_LOO) ? -v : v) - mx;
+            }
+            if (i < TL) {
+                xs[e] = x;
+                ss[e] = s;
+            } else {
+                tb[e - 32 * TL] = x;
+            }
+        } else if (i < TL) {
+            xs[e] = -inf_f64();
+            ss[e] = 0;
         }
     }
-    (void)n_eq;
-    const int n = n_lt;  // draws with x > cutoff value (ties with the cutoff are not in the tail)
-    if (xc < p.cutoffmin) bad = true;  // cutoff clamped at log(DBL_MIN): general kernel
-    // order inside the tail must be exact (descending x, descending index on ties)
+    // cutoff = (M+1)-th largest = element M of the order (psis.py:135-136): its truncated key
+    unsigned long long kc = 0;
 #pragma unroll
-    for (int i = 0; i < TL; ++i) {
-        const int e = 32 * i + lane;
-        double xn = __shfl_down_sync(FULL, xt[i], 1);
-        int sn = __shfl_down_sync(FULL, st[i], 1);
-        if (i + 1 < TL) {
-            const double x0 = shfl_f64(xt[i + 1], 0);
-            const int s0 = __shfl_sync(FULL, st[i + 1], 0);
-            if (lane == 31) {
-                xn = x0;
-                sn = s0;
-            }
-        }
-        if (e + 1 < n && (lane < 31 || i + 1 < TL)) {
-            if (!(xt[i] > xn || (xt[i] == xn && st[i] > sn))) bad = true;
-        }
+    for (int i = 0; i < TL; ++i)
+        if (i == (M >> 5)) kc = k[i];
+    kc = __shfl_sync(FULL, kc, M & 31);
+    const unsigned long long tc = kc >> KEY_IDX_BITS;
+    SortOut o;
+    o.n_lt = 0;
+    o.n_eq = 0;
+    o.run_escapes = false;
+#pragma unroll
+    for (int i = 0; i < CAPL; ++i) {
+        const unsigned long long ti = k[i] >> KEY_IDX_BITS;
+        o.n_lt += __popc(__ballot_sync(FULL, ti < tc));
+        const unsigned eqm = __ballot_sync(FULL, ti == tc);
+        o.n_eq += __popc(eqm);
+        if (i >= TL && eqm) o.run_escapes = true;
+    }
+    __syncwarp();
+    return o;
+}
+
+// One row for one warp.  Returns false -> general kernel.
+template <int TL, int MODE>
+__device__ __forceinline__ bool tail_row(const SplitParams& p, long long row, const SplitHeader& h,
+                                         const double* l1p, double* xs, double* tb, int* ss, int lane) {
+    const int S = p.S, M = p.M, C = h.C;
+    const double mx = h.mx;
+    const double* src = p.in + row * p.in_stride;
+
+    SortOut so;
+    const unsigned long long* ck = p.ckey + (size_t)row * (size_t)p.cap;
+    if (C <= 32 * TL) so = sort_and_stage<TL, TL, MODE>(src, ck, M, C, mx, xs, tb, ss, lane);
+    else so = sort_and_stage<2 * TL, TL, MODE>(src, ck, M, C, mx, xs, tb, ss, lane);
+    if (so.run_escapes) return false;
+    const int n = so.n_lt;  // draws with x > cutoff value (ties with the cutoff are not in the tail)
+    const double xc = xs[M];
+    bool bad = xc < p.cutoffmin;  // cutoff clamped at log(DBL_MIN): general kernel
+    // distinct values sharing the truncated key at the cutoff: general kernel
+    for (int e = n + lane; e < n + so.n_eq; e += 32)
+        if (xs[e] != xc) bad = true;
+    // order inside the tail must be exact (descending x, descending index on ties)
+    for (int e = lane; e + 1 < n; e += 32) {
+        const double a = xs[e], b = xs[e + 1];
+        if (!(a > b || (a == b && ss[e] > ss[e + 1]))) bad = true;
     }
     if (__any_sync(FULL, bad)) return false;
 
-    const double c = xc;  // >= cutoffmin here
+    const double c = xc;          // >= cutoffmin here
     const double exp_c = exp(c);  // psis.py:138
-    // ---- t_i = exp(x_i) - exp(c) (psis.py:146-147), descending, to shared memory; candidates at or
-    //      below the cutoff join the normaliser
+    // candidates at or below the cutoff belong to the normaliser's body
+    double nont = 0.0;
+#pragma unroll 1
+    for (int e = n + lane; e < min(C, 32 * TL); e += 32) nont += exp(xs[e]);
+#pragma unroll 1
+    for (int e = lane; e < C - 32 * TL; e += 32) nont += exp(tb[e]);
+    __syncwarp();
+    // t_i = exp(x_i) - exp(c) (psis.py:146-147), descending
     double tsum = 0.0, traw = 0.0;
-#pragma unroll
-    for (int i = 0; i < TL; ++i) {
-        const int e = 32 * i + lane;
-        if (32 * i < C) {
-            if (e < C) {
-                const double ex = exp(xt[i]);
-                if (e < n) {
-                    const double ti = ex - exp_c;
-                    tsh[e] = ti;
-                    tsum += ti;
-                    traw += ex;
-                } else {
-                    nont += ex;
-                }
-            }
-        }
+#pragma unroll 1
+    for (int e = lane; e < n; e += 32) {
+        const double ex = exp(xs[e]);
+        const double ti = ex - exp_c;
+        tb[e] = ti;
+        tsum += ti;
+        traw += ex;
     }
     tsum = warp_sum(tsum);
     traw = warp_sum(traw);
@@ -755,53 +754,49 @@ __device__ __forceinline__ bool tail_row(const SplitParams& p, long long row, co
             while ((m + 1) * (m + 1) <= n) ++m;
             m += 30;
         }
-        if (!gpdfit_warp(tsh, n, m, tsum, lane, kk, sigma)) return false;
+        if (!gpdfit_warp(tb, n, m, tsum, lane, kk, sigma)) return false;
         smooth = is_finite(kk);  // psis.py:150
     }
-    // ---- smoothed tail (psis.py:153-157, _gpinv :211-222); element e has ascending rank n-1-e
+    // smoothed tail (psis.py:153-157, _gpinv :211-222); element e has ascending rank n-1-e.
+    // The smoothed values replace t in shared memory.
     double tails = traw;
-    double sm[TL];
-#pragma unroll
-    for (int i = 0; i < TL; ++i) sm[i] = 0.0;
     if (smooth) {
         double tsm = 0.0;
-#pragma unroll
-        for (int i = 0; i < TL; ++i) {
-            const int e = 32 * i + lane;
-            if (32 * i < n) {
-                if (e < n) {
-                    const int rk = n - 1 - e;
-                    double q;
-                    if (sigma <= 0.0) {
-                        q = nan_f64();
-                    } else {
-                        const double l1 = (n == M) ? l1p[rk] : log1p(-(((double)rk + 0.5) / (double)n));
-                        q = (fabs(kk) < 2.220446049250313e-16) ? -l1 : expm1(-kk * l1) / kk;
-                        q *= sigma;
-                    }
-                    double y = q + exp_c;
-                    double s_ = log(y);
-                    if (s_ > 0.0) {  // psis.py:157
-                        s_ = 0.0;
-                        y = 1.0;
-                    }
-                    sm[i] = s_;
-                    tsm += y;
-                }
+        __syncwarp();
+#pragma unroll 1
+        for (int e = lane; e < n; e += 32) {
+            const int rk = n - 1 - e;
+            double q;
+            if (sigma <= 0.0) {
+                q = nan_f64();
+            } else {
+                const double l1 = (n == M) ? l1p[rk] : log1p(-(((double)rk + 0.5) / (double)n));
+                q = (fabs(kk) < 2.220446049250313e-16) ? -l1 : expm1(-kk * l1) / kk;
+                q *= sigma;
             }
+            double y = q + exp_c;
+            double s_ = log(y);
+            if (s_ > 0.0) {  // psis.py:157
+                s_ = 0.0;
+                y = 1.0;
+            }
+            tb[e] = s_;
+            tsm += y;
         }
         tails = warp_sum(tsm);
+        __syncwarp();
     }
     const double body = h.body + nont;
     const double lse = log(body + tails);  // psis.py:158
 
     if (MODE == MODE_PSISLW) {
-        // ---- normalised row, then the smoothed tail on top of it
+        // normalised row, then the smoothed tail on top of it
         double* dst = p.out + row * p.out_stride;
         const double2* s2 = reinterpret_cast<const double2*>(src);
         double2* d2 = reinterpret_cast<double2*>(dst);
         const int S2 = S >> 1;
         int i2 = lane;
+#pragma unroll 1
         for (; i2 + 96 < S2; i2 += 128) {
             double2 a0 = s2[i2], a1 = s2[i2 + 32], a2 = s2[i2 + 64], a3 = s2[i2 + 96];
             a0.x = (a0.x - mx) - lse; a0.y = (a0.y - mx) - lse;
@@ -810,19 +805,15 @@ __device__ __forceinline__ bool tail_row(const SplitParams& p, long long row, co
             a3.x = (a3.x - mx) - lse; a3.y = (a3.y - mx) - lse;
             d2[i2] = a0; d2[i2 + 32] = a1; d2[i2 + 64] = a2; d2[i2 + 96] = a3;
         }
+#pragma unroll 1
         for (; i2 < S2; i2 += 32) {
             double2 a0 = s2[i2];
             a0.x = (a0.x - mx) - lse; a0.y = (a0.y - mx) - lse;
             d2[i2] = a0;
         }
         __syncwarp();
-        if (smooth) {
-#pragma unroll
-            for (int i = 0; i < TL; ++i) {
-                const int e = 32 * i + lane;
-                if (e < n) dst[st[i]] = sm[i] - lse;
-            }
-        }
+        if (smooth)
+            for (int e = lane; e < n; e += 32) dst[ss[e]] = tb[e] - lse;
         if (lane == 0) p.k_out[row] = kk;
     } else {
         // elpd_i = LSE_s(lw_s + ll_s): body terms are the constant -(mx + lse), tail terms differ
@@ -830,14 +821,14 @@ __device__ __forceinline__ bool tail_row(const SplitParams& p, long long row, co
         double dmax = 0.0, es = (double)n;
         if (smooth) {
             double dm = 0.0;
-#pragma unroll
-            for (int i = 0; i < TL; ++i)
-                if (32 * i + lane < n) dm = fmax(dm, sm[i] - xt[i]);
+            for (int e = lane; e < n; e += 32) {
+                const double d = tb[e] - xs[e];
+                dm = (d > dm) ? d : dm;
+            }
             dmax = warp_max(dm);
             double e2 = 0.0;
-#pragma unroll
-            for (int i = 0; i < TL; ++i)
-                if (32 * i < n && 32 * i + lane < n) e2 += exp((sm[i] - xt[i]) - dmax);
+#pragma unroll 1
+            for (int e = lane; e < n; e += 32) e2 += exp((tb[e] - xs[e]) - dmax);
             es = warp_sum(e2);
         }
         const double tot = (double)(S - n) * exp(-dmax) + es;
@@ -861,7 +852,7 @@ __device__ __forceinline__ bool tail_row(const SplitParams& p, long long row, co
 }
 
 template <int TL>
-constexpr int tail_min_blocks() { return TL <= 8 ? 4 : 2; }
+constexpr int tail_min_blocks() { return TL <= 8 ? 6 : 3; }
 
 template <int TL, int MODE>
 __global__ void __launch_bounds__(TAIL_WARPS * 32, tail_min_blocks<TL>()) psis_tail_kernel(const SplitParams p) {
@@ -869,17 +860,19 @@ __global__ void __launch_bounds__(TAIL_WARPS * 32, tail_min_blocks<TL>()) psis_t
     const TailSmem L = tail_smem(p.M, TL, TAIL_WARPS);
     double* l1p = reinterpret_cast<double*>(smem_raw + L.off_l1p);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    double* tsh = reinterpret_cast<double*>(smem_raw + L.off_t + L.t_stride * wid);
+    unsigned char* wbase = smem_raw + L.off_w + L.w_stride * wid;
+    double* xs = reinterpret_cast<double*>(wbase + L.off_x);
+    double* tb = reinterpret_cast<double*>(wbase + L.off_t);
+    int* ss = reinterpret_cast<int*>(wbase + L.off_s);
     // per-CTA table for the smoothing step: depends only on (rank, M), psis.py:153 + :221
     for (int i = threadIdx.x; i < p.M; i += TAIL_WARPS * 32) l1p[i] = log1p(-(((double)i + 0.5) / (double)p.M));
     __syncthreads();
     const long long nwarps = (long long)gridDim.x * TAIL_WARPS;
+#pragma unroll 1
     for (long long row = (long long)blockIdx.x * TAIL_WARPS + wid; row < p.n_rows; row += nwarps) {
         const SplitHeader h = p.hdr[row];
         if (h.flags) continue;
-        bool ok;
-        if (h.C <= 32 * TL) ok = tail_row<TL, TL, MODE>(p, row, h, l1p, tsh, lane);
-        else ok = tail_row<2 * TL, TL, MODE>(p, row, h, l1p, tsh, lane);
+        const bool ok = tail_row<TL, MODE>(p, row, h, l1p, xs, tb, ss, lane);
         if (!ok && lane == 0) {
             p.fb_list[atomicAdd(p.fb_count, 1)] = (int)row;
             if (p.counters) atomicAdd(&p.counters[3], 1ull);

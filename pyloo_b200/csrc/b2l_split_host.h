@@ -1,0 +1,14 @@
+// Host-side interface between the C-ABI translation unit and the split-path kernel translation
+// units (compiled in parallel: the stream kernel alone has 16 instantiations).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "b2l_split.cuh"
+
+namespace b2l {
+cudaError_t split_stream_setup(int nt, int ept, int mode, size_t smem, int* occ);
+cudaError_t split_stream_launch(int nt, int ept, int mode, int grid, size_t smem, cudaStream_t st,
+                                const SplitParams& q);
+cudaError_t split_tail_setup(int tl, int mode, size_t smem, int* occ);
+cudaError_t split_tail_launch(int tl, int mode, int grid, size_t smem, cudaStream_t st, const SplitParams& q);
+}  // namespace b2l

@@ -13,7 +13,7 @@
 
 #include "../../include/psisloo_b200.h"
 #include "b2l_row_kernel.cuh"
-#include "b2l_split.cuh"
+#include "b2l_split_host.h"
 
 using namespace b2l;
 
@@ -176,24 +176,6 @@ struct SplitPlan {
     long long batch;  // observations per stream -> tail -> fallback round
 };
 
-template <int NT, int EPT, int MODE>
-static cudaError_t stream_setup(size_t smem, int* occ) {
-    cudaError_t e = cudaFuncSetAttribute(psis_stream_kernel<NT, EPT, MODE>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, psis_stream_kernel<NT, EPT, MODE>, NT, smem);
-}
-template <int TL, int MODE>
-static cudaError_t tail_setup(size_t smem, int* occ) {
-    cudaError_t e = cudaFuncSetAttribute(psis_tail_kernel<TL, MODE>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, psis_tail_kernel<TL, MODE>, TAIL_WARPS * 32, smem);
-}
-
-#define B2L_STREAM_CASES(X)                                                                        \
-    X(128, 8) X(128, 16) X(256, 8) X(256, 16) X(512, 8) X(512, 16) X(1024, 8) X(1024, 16)
-
 // shape part of the plan: pure arithmetic (also sizes the workspace without touching the device)
 static bool split_shape(long long S, int M, long long n_rows, SplitPlan* sp) {
     memset(sp, 0, sizeof(*sp));
@@ -236,18 +218,8 @@ static int plan_split(long long S, int M, int mode, long long n_rows, SplitPlan*
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     CK(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     if (sp->smem1 > (size_t)smem_optin || sp->smem2 > (size_t)smem_optin) return 0;
-    cudaError_t e = cudaErrorInvalidValue;
-#define X(NT_, EPT_)                                                                               \
-    if (nt == NT_ && ept == EPT_)                                                                  \
-        e = (mode == MODE_PSISLW) ? stream_setup<NT_, EPT_, MODE_PSISLW>(sp->smem1, &sp->occ1)     \
-                                  : stream_setup<NT_, EPT_, MODE_LOO>(sp->smem1, &sp->occ1);
-    B2L_STREAM_CASES(X)
-#undef X
-    CK(e);
-    if (sp->tl == 4) e = (mode == MODE_PSISLW) ? tail_setup<4, MODE_PSISLW>(sp->smem2, &sp->occ2) : tail_setup<4, MODE_LOO>(sp->smem2, &sp->occ2);
-    else if (sp->tl == 8) e = (mode == MODE_PSISLW) ? tail_setup<8, MODE_PSISLW>(sp->smem2, &sp->occ2) : tail_setup<8, MODE_LOO>(sp->smem2, &sp->occ2);
-    else e = (mode == MODE_PSISLW) ? tail_setup<16, MODE_PSISLW>(sp->smem2, &sp->occ2) : tail_setup<16, MODE_LOO>(sp->smem2, &sp->occ2);
-    CK(e);
+    CK(split_stream_setup(nt, ept, mode, sp->smem1, &sp->occ1));
+    CK(split_tail_setup(sp->tl, mode, sp->smem2, &sp->occ2));
     if (sp->occ1 < 1 || sp->occ2 < 1) return 0;
     sp->grid1 = sms * sp->occ1;
     sp->grid2 = sms * sp->occ2;
@@ -289,25 +261,8 @@ static int launch_split(int mode, const RowPlan& pl, const SplitPlan& sp, const 
         CK(cudaMemsetAsync(fb_count, 0, sizeof(int), st));
         const int g1 = (int)std::min<long long>(sp.grid1, nb);
         const int g2 = (int)std::min<long long>(sp.grid2, (nb + TAIL_WARPS - 1) / TAIL_WARPS);
-#define X(NT_, EPT_)                                                                               \
-    if (sp.nt == NT_ && sp.ept == EPT_) {                                                          \
-        if (mode == MODE_PSISLW) psis_stream_kernel<NT_, EPT_, MODE_PSISLW><<<g1, NT_, sp.smem1, st>>>(q); \
-        else psis_stream_kernel<NT_, EPT_, MODE_LOO><<<g1, NT_, sp.smem1, st>>>(q);                \
-    }
-        B2L_STREAM_CASES(X)
-#undef X
-        CK(cudaGetLastError());
-        if (sp.tl == 4) {
-            if (mode == MODE_PSISLW) psis_tail_kernel<4, MODE_PSISLW><<<g2, TAIL_WARPS * 32, sp.smem2, st>>>(q);
-            else psis_tail_kernel<4, MODE_LOO><<<g2, TAIL_WARPS * 32, sp.smem2, st>>>(q);
-        } else if (sp.tl == 8) {
-            if (mode == MODE_PSISLW) psis_tail_kernel<8, MODE_PSISLW><<<g2, TAIL_WARPS * 32, sp.smem2, st>>>(q);
-            else psis_tail_kernel<8, MODE_LOO><<<g2, TAIL_WARPS * 32, sp.smem2, st>>>(q);
-        } else {
-            if (mode == MODE_PSISLW) psis_tail_kernel<16, MODE_PSISLW><<<g2, TAIL_WARPS * 32, sp.smem2, st>>>(q);
-            else psis_tail_kernel<16, MODE_LOO><<<g2, TAIL_WARPS * 32, sp.smem2, st>>>(q);
-        }
-        CK(cudaGetLastError());
+        CK(split_stream_launch(sp.nt, sp.ept, mode, g1, sp.smem1, st, q));
+        CK(split_tail_launch(sp.tl, mode, g2, sp.smem2, st, q));
         // rows handed over: general kernel driven by the device-side list (empty list = no work)
         RowParams r = rp;
         r.in = q.in; r.out = q.out; r.k_out = q.k_out; r.elpd_i = q.elpd_i; r.lppd_i = q.lppd_i;

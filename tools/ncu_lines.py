@@ -9,8 +9,12 @@ top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 lib = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pyloo_b200", "lib", "libpsisloo_b200.so")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=tmp, capture_output=True)
-cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
+dis = []
+for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):
+    d = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
+    if any(l.startswith(".text.") and kern in l for l in d):
+        dis = d
+        break
 # locate kernel section
 start = next(i for i, l in enumerate(dis) if l.startswith(".text.") and kern in l)
 lines = []  # per instruction: source line
@@ -59,7 +63,7 @@ print("\nby file:")
 for f, n in sorted(byfile.items(), key=lambda kv: -kv[1]): print(f"  {n:>11} {100*n/tot:5.1f}%  {f}")
 if os.environ.get("RANGES"):
     ranges = [tuple(map(int, r.split("-"))) for r in os.environ["RANGES"].split(",")]
-    print("\nby line range of b2l_row_kernel.cuh:")
+    print("\nby line range:")
     for a, b in ranges:
         n = sum(v[0] for ln, v in agg.items() if ln and ln[0] == "b2l_row_kernel.cuh" and a <= ln[1] <= b)
         s = sum(v[1] for ln, v in agg.items() if ln and ln[0] == "b2l_row_kernel.cuh" and a <= ln[1] <= b)
