@@ -27,17 +27,18 @@ constexpr int KEY_IDX_BITS = 14;               // draw index lives in the low bi
 constexpr int SPLIT_MAX_S = 1 << KEY_IDX_BITS;
 constexpr unsigned KEY_IDX_MASK = (1u << KEY_IDX_BITS) - 1u;
 
-struct __align__(16) SplitHeader {  // 64 B per observation: stream kernel -> tail kernel
+struct __align__(16) SplitHeader {  // 80 B per observation: stream kernel -> tail kernel -> apply kernel
     double mx;      // max_s r_s
     double body;    // sum of exp(x_s) over the draws that are NOT candidates
     double lsum;    // LOO: sum_s exp(ll_s - lshift)
     double vsum;    // LOO: sum_s (ll_s - mean ll)^2
     double lshift;  // LOO: shift used for lsum (min ll, or max ll for very wide rows)
-    double ll_max;
+    double taux;    // candidate threshold: every candidate has x >= taux
+    double lse;     // tail kernel -> apply kernel: the normaliser (psis.py:158)
     int C;          // candidates emitted (M + 1 <= C <= cap)
     int flags;      // != 0: the row was handed to the general kernel
     int attempts;
-    int pad;
+    int n_patch;    // tail kernel -> apply kernel: smoothed draws to patch in (0: none)
 };
 
 struct SplitParams {
@@ -53,11 +54,13 @@ struct SplitParams {
     double* diag;
     long long n_rows;
     int S, M, cap;
+    int nbuf;              // stream kernel row buffers in shared memory (2: prefetch during the whole row)
     int q0;                // per-warp rank (1..32) of the thread maxima used for the threshold guess
     int m_full;            // 30 + floor(sqrt(M))
     double cutoffmin;
     SplitHeader* hdr;          // [n_rows]
-    unsigned long long* ckey;  // [n_rows][cap]
+    double* cx;                // [n_rows][cap] candidate x (exact); then the smoothed values to patch in
+    unsigned short* cs;        // [n_rows][cap] candidate draw index; then the patch positions
     int* fb_list;              // [n_rows] rows for the general kernel
     int* fb_count;
     unsigned long long* counters;  // optional [4]; [3] += rows handed to the general kernel
@@ -122,10 +125,10 @@ __device__ __forceinline__ float warp_sort32_f(float v, int lane) {  // ascendin
 struct StreamSmem {
     size_t row_bytes, off_tab, off_red, off_ctl, off_bar, total;
 };
-__host__ __device__ inline StreamSmem stream_smem(int S) {
+__host__ __device__ inline StreamSmem stream_smem(int S, int nbuf) {
     StreamSmem L;
     L.row_bytes = align_up((size_t)S * 8, 128);
-    size_t o = L.row_bytes;
+    size_t o = L.row_bytes * (size_t)nbuf;
     L.off_tab = o;   // 64 doubles
     o += 64 * 8;
     L.off_red = o;   // 2 x (5 x 32 doubles + 32 floats): sets alternate between consecutive rows
@@ -179,8 +182,8 @@ __global__ void __launch_bounds__(NT, stream_min_blocks<NT>()) psis_stream_kerne
     constexpr int EP2 = EPT / 2;
     const int S = p.S, M = p.M, cap = p.cap;
     const int S2 = S >> 1;
-    const StreamSmem L = stream_smem(S);
-    const double2* rowbuf = reinterpret_cast<const double2*>(smem_raw);
+    const int nbuf = p.nbuf;
+    const StreamSmem L = stream_smem(S, nbuf);
     double* tab = reinterpret_cast<double*>(smem_raw + L.off_tab);
     int* ctl_all = reinterpret_cast<int*>(smem_raw + L.off_ctl);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.off_bar);
@@ -192,7 +195,8 @@ __global__ void __launch_bounds__(NT, stream_min_blocks<NT>()) psis_stream_kerne
     tb.tinv = tab + 32;
 
     if (tid == 0) {
-        mbar_init(bar, 1);
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
         fence_mbar_init();
     }
     if (tid < 32) {
@@ -202,8 +206,8 @@ __global__ void __launch_bounds__(NT, stream_min_blocks<NT>()) psis_stream_kerne
     __syncthreads();
     long long row = blockIdx.x;
     if (tid == 0 && row < p.n_rows) {
-        mbar_expect_tx(bar, row_tx);
-        bulk_g2s(smem_raw, p.in + row * p.in_stride, row_tx, bar);
+        mbar_expect_tx(&bar[0], row_tx);
+        bulk_g2s(smem_raw, p.in + row * p.in_stride, row_tx, &bar[0]);
     }
     int nv = 0;  // valid double2 slots of this thread
 #pragma unroll
@@ -215,8 +219,10 @@ __global__ void __launch_bounds__(NT, stream_min_blocks<NT>()) psis_stream_kerne
         double* red = reinterpret_cast<double*>(smem_raw + L.off_red + (size_t)(it & 1) * (5 * 32 * 8 + 32 * 4));
         float* redf = reinterpret_cast<float*>(red + 5 * 32);
         int* ctl = ctl_all + (it & 1);
-        // ---------------- row -> registers
-        mbar_wait(bar, (uint32_t)(it & 1));
+        // ---------------- row -> registers (the shared-memory copy stays valid until the candidates are out)
+        const int bsel = (nbuf == 2) ? (it & 1) : 0;
+        const double2* rowbuf = reinterpret_cast<const double2*>(smem_raw + (size_t)bsel * L.row_bytes);
+        mbar_wait(&bar[bsel], (uint32_t)((nbuf == 2) ? ((it >> 1) & 1) : (it & 1)));
         double2 v[EP2];
 #pragma unroll
         for (int j = 0; j < EP2; ++j) {
@@ -259,12 +265,13 @@ __global__ void __launch_bounds__(NT, stream_min_blocks<NT>()) psis_stream_kerne
             }
         }
         if (tid == 0) ctl[0] = 0;
-        // (1) the row is in registers everywhere: the buffer can be refilled
+        // (1) every warp is past the previous row: the other buffer can take the next row now
         const bool special = __syncthreads_or(spec >= 0x7ff00000) != 0;
-        if (tid == 0 && row + gridDim.x < p.n_rows) {
+        if (nbuf == 2 && tid == 0 && row + gridDim.x < p.n_rows) {
             fence_proxy_async();
-            mbar_expect_tx(bar, row_tx);
-            bulk_g2s(smem_raw, p.in + (row + gridDim.x) * p.in_stride, row_tx, bar);
+            mbar_expect_tx(&bar[bsel ^ 1], row_tx);
+            bulk_g2s(smem_raw + (size_t)(bsel ^ 1) * L.row_bytes, p.in + (row + gridDim.x) * p.in_stride, row_tx,
+                     &bar[bsel ^ 1]);
         }
         const double mx = slots_max<NW>(red, lane);
         double r_min = 0.0, r_sum = 0.0;
@@ -279,7 +286,7 @@ __global__ void __launch_bounds__(NT, stream_min_blocks<NT>()) psis_stream_kerne
         // ---------------- threshold guess: per-warp sorted thread maxima (as float distances to the max)
         const float dsorted = warp_sort32_f((float)(mx - tmax), lane);
         int q = p.q0, attempts = 0, C = 0;
-        double body = 0.0, lsum = 0.0, vsum = 0.0;
+        double body = 0.0, lsum = 0.0, vsum = 0.0, taux_used = 0.0;
         bool ok = !special;
         while (ok) {
             if (lane == q - 1) redf[wid] = dsorted;
@@ -296,6 +303,7 @@ __global__ void __launch_bounds__(NT, stream_min_blocks<NT>()) psis_stream_kerne
                 const unsigned b = __ballot_sync(FULL, lane < NW && rank == NW / 2 - 1 + (NW == 1));
                 taux = max_sel(-(double)__shfl_sync(FULL, mine, __ffs(b) - 1), -1e300);  // padding (-inf) never qualifies
             }
+            taux_used = taux;
             // -------- pass B: body exp-sum, candidate marks.  `mxl` is laundered through an empty asm so
             // the compiler cannot hoist the (threshold-independent) exps out of the retry loop and
             // then spill all EPT results
@@ -349,22 +357,21 @@ __global__ void __launch_bounds__(NT, stream_min_blocks<NT>()) psis_stream_kerne
                 if (lane == 31 && incl > 0) base = atomicAdd(&ctl[0], incl);
                 base = __shfl_sync(FULL, base, 31);
                 int pos = base + incl - mine;
-                unsigned long long* dst = p.ckey + (size_t)row * (size_t)cap;
-#pragma unroll
-                for (int j = 0; j < EP2; ++j) {
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        if (cmask & (1u << (2 * j + h))) {
-                            if (pos < cap) {
-                                const double x = (h ? v[j].y : v[j].x) - mxl;
-                                const int s = 2 * (j * NT + tid) + h;
-                                const unsigned hi = (unsigned)__double2hiint(x) & 0x7fffffffu;
-                                const unsigned lo = ((unsigned)__double2loint(x) & ~KEY_IDX_MASK) | (KEY_IDX_MASK - (unsigned)s);
-                                dst[pos] = ((unsigned long long)hi << 32) | lo;
-                            }
-                            ++pos;
-                        }
+                double* dst_x = p.cx + (size_t)row * (size_t)cap;
+                unsigned short* dst_s = p.cs + (size_t)row * (size_t)cap;
+                // per-thread walk over its marked draws, values re-read from the shared-memory row
+                // (a register array cannot be indexed by a run-time bit position)
+                const double* rb = reinterpret_cast<const double*>(rowbuf);
+                while (cmask) {
+                    const int bpos = __ffs((int)cmask) - 1;
+                    cmask &= cmask - 1;
+                    const int s = 2 * ((bpos >> 1) * NT + tid) + (bpos & 1);
+                    if (pos < cap) {
+                        const double rv = rb[s];
+                        dst_x[pos] = ((MODE == MODE_LOO) ? -rv : rv) - mxl;  // exact x = fl(r - max r)
+                        dst_s[pos] = (unsigned short)s;
                     }
+                    ++pos;
                 }
             }
             bs = warp_sum(bs);
@@ -397,11 +404,17 @@ __global__ void __launch_bounds__(NT, stream_min_blocks<NT>()) psis_stream_kerne
             __syncthreads();  // everyone has read ctl[0] / red before they are reused
             if (tid == 0) ctl[0] = 0;
         }
+        if (nbuf == 1 && tid == 0 && row + gridDim.x < p.n_rows) {
+            // single buffer (rows too long for two): refill once the candidates are out
+            fence_proxy_async();
+            mbar_expect_tx(&bar[0], row_tx);
+            bulk_g2s(smem_raw, p.in + (row + gridDim.x) * p.in_stride, row_tx, &bar[0]);
+        }
         if (tid == 0) {
             SplitHeader h;
             h.mx = mx; h.body = body; h.lsum = lsum; h.vsum = vsum;
-            h.lshift = wide ? ll_max : ll_min; h.ll_max = ll_max;
-            h.C = C; h.flags = ok ? 0 : 1; h.attempts = attempts; h.pad = 0;
+            h.lshift = wide ? ll_max : ll_min; h.taux = taux_used;
+            h.lse = 0.0; h.C = C; h.flags = ok ? 0 : 1; h.attempts = attempts; h.n_patch = 0;
             p.hdr[row] = h;
             if (!ok) {
                 p.fb_list[atomicAdd(p.fb_count, 1)] = (int)row;
@@ -414,45 +427,37 @@ __global__ void __launch_bounds__(NT, stream_min_blocks<NT>()) psis_stream_kerne
 // ------------------------------------------------------------------ tail kernel helpers
 __device__ __forceinline__ double shfl_f64(double v, int src) { return __shfl_sync(FULL, v, src); }
 
-// Bitonic sort of 32 * CAPL unsigned 64-bit keys held as k[i] <-> element e = 32 i + lane, ascending
-// in e.  The (kk, j) stage loop is a RUN-TIME loop (the kernel must stay small enough for the
-// instruction cache: a fully unrolled 512-key network alone is ~60 KB of SASS); only the per-register
-// loop is unrolled.  Partner distances below 32 are lane shuffles, the rest are register pairs.
-template <int CAPL, int DJ>
-__device__ __forceinline__ void bitonic_inlane(unsigned long long (&k)[CAPL], int kk) {
-#pragma unroll
-    for (int i = 0; i < CAPL; ++i) {
-        if ((i & DJ) == 0 && (i | DJ) < CAPL) {
-            const bool up = (((i << 5) & kk) == 0);
-            const unsigned long long a = k[i], b = k[i | DJ];
-            const bool sw = (a > b) == up;
-            k[i] = sw ? b : a;
-            k[i | DJ] = sw ? a : b;
-        }
-    }
-}
+// Bitonic sort of 32 * CAPL unsigned 32-bit keys held as k[i] <-> element e = 32 i + lane, ascending
+// in e.  The kk loop is unrolled, so the direction of every register-pair / register-lane exchange
+// is a compile-time constant and one exchange is SHFL + predicated min/max; the partner-distance
+// loop below 32 stays a run-time loop to keep the code small (instruction cache).
 template <int CAPL>
-__device__ __forceinline__ void warp_bitonic_sort(unsigned long long (&k)[CAPL], int lane) {
-#pragma unroll 1
-    for (int kk = 2; kk <= 32 * CAPL; kk <<= 1) {
-#pragma unroll 1
-        for (int j = kk >> 1; j > 0; j >>= 1) {
-            if (j >= 32) {
-                const int dj = j >> 5;
-                if (dj == 1) bitonic_inlane<CAPL, 1>(k, kk);
-                else if (dj == 2) bitonic_inlane<CAPL, 2>(k, kk);
-                else if (dj == 4) bitonic_inlane<CAPL, 4>(k, kk);
-                else if (dj == 8) bitonic_inlane<CAPL, 8>(k, kk);
-                else bitonic_inlane<CAPL, 16>(k, kk);
-            } else {
-                const bool lower = ((lane & j) == 0);
+__device__ __forceinline__ void warp_bitonic_sort32(unsigned (&k)[CAPL], int lane) {
 #pragma unroll
-                for (int i = 0; i < CAPL; ++i) {
-                    const bool up = ((((i << 5) | lane) & kk) == 0);
-                    const unsigned long long o = __shfl_xor_sync(FULL, k[i], j);
-                    const bool take_o = ((k[i] < o) != (up == lower));
-                    k[i] = take_o ? o : k[i];
+    for (int kk = 2; kk <= 32 * CAPL; kk <<= 1) {
+#pragma unroll
+        for (int j = kk >> 1; j >= 32; j >>= 1) {  // partners in the same lane
+            const int dj = j >> 5;
+#pragma unroll
+            for (int i = 0; i < CAPL; ++i) {
+                if ((i & dj) == 0) {
+                    const bool up = (((i << 5) & kk) == 0);
+                    const unsigned a = k[i], b = k[i | dj];
+                    const unsigned lo = min(a, b), hi = max(a, b);
+                    k[i] = up ? lo : hi;
+                    k[i | dj] = up ? hi : lo;
                 }
+            }
+        }
+        const bool upl = ((lane & kk) == 0);  // kk < 32: direction depends on the lane
+#pragma unroll 1
+        for (int j = (kk >> 1) < 16 ? (kk >> 1) : 16; j > 0; j >>= 1) {
+            const bool lower = ((lane & j) == 0);
+#pragma unroll
+            for (int i = 0; i < CAPL; ++i) {
+                const bool up = (kk >= 32) ? (((i << 5) & kk) == 0) : upl;
+                const unsigned o = __shfl_xor_sync(FULL, k[i], j);
+                k[i] = (up == lower) ? min(k[i], o) : max(k[i], o);
             }
         }
     }
@@ -611,19 +616,23 @@ __device__ __forceinline__ bool gpdfit_warp(const double* t, int n, int m, doubl
 }
 
 struct TailSmem {
-    size_t off_l1p, off_w, w_stride, off_x, off_t, off_s, total;
+    size_t off_l1p, off_tab, off_w, w_stride, off_a, off_x, off_s, off_p, total;
 };
-// per-warp staging: xs[32 TL] exact x of the head of the order, tb[32 TL] t_i / smoothed values,
-// ss[32 TL] draw indices
+// per CTA: l1p table, exp table.  Per warp: region A = xp[64 TL] candidate x by slot, later tb[32 TL]
+// (t_i, then smoothed values); xs[32 TL] exact x of the head of the order; ss[32 TL] their draw
+// indices; sp[64 TL] draw index by candidate slot.
 __host__ __device__ inline TailSmem tail_smem(int M, int TL, int warps) {
     TailSmem L;
     L.off_l1p = 0;
     size_t o = align_up((size_t)(M + 1) * 8, 16);
+    L.off_tab = o;
+    o += 64 * 8;
     L.off_w = o;
-    L.off_x = 0;
-    L.off_t = (size_t)32 * TL * 8;
-    L.off_s = (size_t)32 * TL * 16;
-    L.w_stride = (size_t)32 * TL * 20;
+    L.off_a = 0;
+    L.off_x = (size_t)64 * TL * 8;
+    L.off_s = L.off_x + (size_t)32 * TL * 8;
+    L.off_p = L.off_s + (size_t)32 * TL * 2;
+    L.w_stride = L.off_p + (size_t)64 * TL * 2;
     o += L.w_stride * warps;
     L.total = align_up(o, 128);
     return L;
@@ -631,89 +640,142 @@ __host__ __device__ inline TailSmem tail_smem(int M, int TL, int warps) {
 
 constexpr int TAIL_WARPS = 4;
 
-struct SortOut {
-    int n_lt, n_eq;
-    bool run_escapes;  // ties with the cutoff key beyond the staged range
+struct TailStage {
+    double* xp;           // candidate x by slot (aliases tb)
+    double* tb;
+    double* xs;
+    unsigned short* ss;
+    unsigned short* sp;
 };
 
-// keys -> registers, sort ascending (= descending x, ties by descending draw index), stage the exact
-// values of the first 32 TL elements (tail + cutoff) and the rest's x (never in the tail) to smem.
-template <int CAPL, int TL, int MODE>
-__device__ __forceinline__ SortOut sort_and_stage(const double* src, const unsigned long long* ck, int M, int C,
-                                                  double mx, double* xs, double* tb, int* ss, int lane) {
-    unsigned long long k[CAPL];
-    {
-#pragma unroll
-        for (int i = 0; i < CAPL; ++i) {
-            const int e = 32 * i + lane;
-            k[i] = (e < C) ? ck[e] : 0x7ff0000000000000ull;  // pad: above every finite |x|
-        }
-    }
-    warp_bitonic_sort<CAPL>(k, lane);
+// quantised image of x for the sort: the float image of (x - taux) >= 0, top QB bits, inverted so that
+// ascending keys mean descending x.  Monotone in x; fine near the threshold where the candidates
+// crowd, coarse towards the row maximum where they are sparse.
+template <int QB>
+__device__ __forceinline__ unsigned quant_key(double x, double taux) {
+    const unsigned fb = __float_as_uint((float)(x - taux));
+    return ((1u << QB) - 1u) - (fb >> (31 - QB));
+}
+
+// Candidates -> 32-bit sort keys (quantised x | candidate slot), register sort, then the exact values
+// of the first 32 TL elements of the order (tail + cutoff) staged to shared memory.  Candidates
+// further down can never be in the tail: their exp goes straight to the normaliser (returned).
+// Equal quantised values leave a short run in unspecified order; fix_runs() orders it exactly.
+template <int CAPL, int TL>
+__device__ __forceinline__ double sort_and_stage(const double* cx, const unsigned short* cs, int C, double taux,
+                                                 const TailStage& st, const ExpTab& tab, int lane) {
+    constexpr int PB = (TL == 4) ? 8 : ((TL == 8) ? 9 : 10);  // bits of a candidate slot (cap = 64 TL)
+    constexpr int QB = 32 - PB;
+    unsigned k[CAPL];
 #pragma unroll
     for (int i = 0; i < CAPL; ++i) {
         const int e = 32 * i + lane;
-        if (32 * i < C) {
-            const int s = (int)(KEY_IDX_MASK - ((unsigned)k[i] & KEY_IDX_MASK));
-            double x = -inf_f64();
-            if (e < C) {
-                const double v = src[s];
-                x = ((MODE == MODE_LOO) ? -v : v) - mx;
-            }
-            if (i < TL) {
-                xs[e] = x;
-                ss[e] = s;
-            } else {
-                tb[e - 32 * TL] = x;
-            }
-        } else if (i < TL) {
-            xs[e] = -inf_f64();
-            ss[e] = 0;
+        k[i] = 0xffffffffu;
+        if (e < C) {
+            const double x = cx[e];
+            st.xp[e] = x;
+            st.sp[e] = cs[e];
+            k[i] = (quant_key<QB>(x, taux) << PB) | (unsigned)e;
         }
     }
-    // cutoff = (M+1)-th largest = element M of the order (psis.py:135-136): its truncated key
-    unsigned long long kc = 0;
-#pragma unroll
-    for (int i = 0; i < TL; ++i)
-        if (i == (M >> 5)) kc = k[i];
-    kc = __shfl_sync(FULL, kc, M & 31);
-    const unsigned long long tc = kc >> KEY_IDX_BITS;
-    SortOut o;
-    o.n_lt = 0;
-    o.n_eq = 0;
-    o.run_escapes = false;
+    __syncwarp();
+    warp_bitonic_sort32<CAPL>(k, lane);
+    double rest = 0.0;
 #pragma unroll
     for (int i = 0; i < CAPL; ++i) {
-        const unsigned long long ti = k[i] >> KEY_IDX_BITS;
-        o.n_lt += __popc(__ballot_sync(FULL, ti < tc));
-        const unsigned eqm = __ballot_sync(FULL, ti == tc);
-        o.n_eq += __popc(eqm);
-        if (i >= TL && eqm) o.run_escapes = true;
+        const int e = 32 * i + lane;
+        const unsigned pidx = k[i] & ((1u << PB) - 1u);
+        if (i < TL) {
+            st.xs[e] = (e < C) ? st.xp[pidx] : -inf_f64();
+            st.ss[e] = (e < C) ? st.sp[pidx] : (unsigned short)0;
+        } else if (32 * i < C) {
+            if (e < C) {
+                const double x = st.xp[pidx];
+                if (x >= -700.0) rest += exp_tab(x, tab);
+            }
+        }
     }
     __syncwarp();
-    return o;
+    return rest;
+}
+
+// Exact order inside runs of equal quantised keys among the staged elements: every element of a run
+// counts the run members that precede it in (x descending, draw index descending) order and moves
+// there.  Returns false if a run is too long or may continue past the staged range.
+template <int TL>
+__device__ __forceinline__ bool fix_runs(const TailStage& st, int C, double taux, int lane) {
+    constexpr int NS = 32 * TL;
+    constexpr int PB = (TL == 4) ? 8 : ((TL == 8) ? 9 : 10);
+    constexpr int QB = 32 - PB;
+    bool bad = false;
+    double myx[TL];
+    int mys[TL], npos[TL];
+    unsigned moved = 0;
+    const int lim = (C < NS) ? C : NS;
+#pragma unroll
+    for (int i = 0; i < TL; ++i) {
+        const int e = 32 * i + lane;
+        npos[i] = e;
+        if (32 * i < lim) {  // warp-uniform
+            myx[i] = st.xs[e];
+            const unsigned q = quant_key<QB>(myx[i], taux);
+            const bool in_run = (e < lim) && ((e > 0 && quant_key<QB>(st.xs[e - 1], taux) == q) ||
+                                              (e + 1 < lim && quant_key<QB>(st.xs[e + 1], taux) == q));
+            if (__any_sync(FULL, in_run)) {
+                if (in_run) {
+                    int lo = e, hi = e;
+                    while (lo > 0 && e - lo < 33 && quant_key<QB>(st.xs[lo - 1], taux) == q) --lo;
+                    while (hi + 1 < lim && hi - e < 33 && quant_key<QB>(st.xs[hi + 1], taux) == q) ++hi;
+                    if (hi - lo > 32 || (hi == NS - 1 && C > NS)) bad = true;
+                    mys[i] = st.ss[e];
+                    int cnt = 0;
+                    for (int f = lo; f <= hi; ++f) {
+                        const double xf = st.xs[f];
+                        cnt += (xf > myx[i] || (xf == myx[i] && (int)st.ss[f] > mys[i])) ? 1 : 0;
+                    }
+                    npos[i] = lo + cnt;
+                    moved |= 1u << i;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (__any_sync(FULL, moved != 0)) {
+#pragma unroll
+        for (int i = 0; i < TL; ++i) {
+            if (moved & (1u << i)) {
+                st.xs[npos[i]] = myx[i];
+                st.ss[npos[i]] = (unsigned short)mys[i];
+            }
+        }
+        __syncwarp();
+    }
+    return !__any_sync(FULL, bad);
 }
 
 // One row for one warp.  Returns false -> general kernel.
 template <int TL, int MODE>
 __device__ __forceinline__ bool tail_row(const SplitParams& p, long long row, const SplitHeader& h,
-                                         const double* l1p, double* xs, double* tb, int* ss, int lane) {
+                                         const double* l1p, const TailStage& st, const ExpTab& tab, int lane) {
     const int S = p.S, M = p.M, C = h.C;
     const double mx = h.mx;
-    const double* src = p.in + row * p.in_stride;
+    double* xs = st.xs;
+    double* tb = st.tb;
+    unsigned short* ss = st.ss;
 
-    SortOut so;
-    const unsigned long long* ck = p.ckey + (size_t)row * (size_t)p.cap;
-    if (C <= 32 * TL) so = sort_and_stage<TL, TL, MODE>(src, ck, M, C, mx, xs, tb, ss, lane);
-    else so = sort_and_stage<2 * TL, TL, MODE>(src, ck, M, C, mx, xs, tb, ss, lane);
-    if (so.run_escapes) return false;
-    const int n = so.n_lt;  // draws with x > cutoff value (ties with the cutoff are not in the tail)
+    double* cx = p.cx + (size_t)row * (size_t)p.cap;
+    unsigned short* cs = p.cs + (size_t)row * (size_t)p.cap;
+    double nont;
+    if (C <= 32 * TL) nont = sort_and_stage<TL, TL>(cx, cs, C, h.taux, st, tab, lane);
+    else nont = sort_and_stage<2 * TL, TL>(cx, cs, C, h.taux, st, tab, lane);
+    if (!fix_runs<TL>(st, C, h.taux, lane)) return false;
+    // cutoff = (M+1)-th largest = element M of the order (psis.py:135-136); draws equal to it are
+    // not in the tail (psis.py:139)
     const double xc = xs[M];
+    int n = M;
+    while (n > 0 && xs[n - 1] == xc) --n;
     bool bad = xc < p.cutoffmin;  // cutoff clamped at log(DBL_MIN): general kernel
-    // distinct values sharing the truncated key at the cutoff: general kernel
-    for (int e = n + lane; e < n + so.n_eq; e += 32)
-        if (xs[e] != xc) bad = true;
-    // order inside the tail must be exact (descending x, descending index on ties)
+    // safety net: the order inside the tail must be exact (descending x, descending index on ties)
     for (int e = lane; e + 1 < n; e += 32) {
         const double a = xs[e], b = xs[e + 1];
         if (!(a > b || (a == b && ss[e] > ss[e + 1]))) bad = true;
@@ -722,13 +784,9 @@ __device__ __forceinline__ bool tail_row(const SplitParams& p, long long row, co
 
     const double c = xc;          // >= cutoffmin here
     const double exp_c = exp(c);  // psis.py:138
-    // candidates at or below the cutoff belong to the normaliser's body
-    double nont = 0.0;
+    // staged candidates at or below the cutoff belong to the normaliser's body too
 #pragma unroll 1
     for (int e = n + lane; e < min(C, 32 * TL); e += 32) nont += exp(xs[e]);
-#pragma unroll 1
-    for (int e = lane; e < C - 32 * TL; e += 32) nont += exp(tb[e]);
-    __syncwarp();
     // t_i = exp(x_i) - exp(c) (psis.py:146-147), descending
     double tsum = 0.0, traw = 0.0;
 #pragma unroll 1
@@ -790,31 +848,19 @@ __device__ __forceinline__ bool tail_row(const SplitParams& p, long long row, co
     const double lse = log(body + tails);  // psis.py:158
 
     if (MODE == MODE_PSISLW) {
-        // normalised row, then the smoothed tail on top of it
-        double* dst = p.out + row * p.out_stride;
-        const double2* s2 = reinterpret_cast<const double2*>(src);
-        double2* d2 = reinterpret_cast<double2*>(dst);
-        const int S2 = S >> 1;
-        int i2 = lane;
-#pragma unroll 1
-        for (; i2 + 96 < S2; i2 += 128) {
-            double2 a0 = s2[i2], a1 = s2[i2 + 32], a2 = s2[i2 + 64], a3 = s2[i2 + 96];
-            a0.x = (a0.x - mx) - lse; a0.y = (a0.y - mx) - lse;
-            a1.x = (a1.x - mx) - lse; a1.y = (a1.y - mx) - lse;
-            a2.x = (a2.x - mx) - lse; a2.y = (a2.y - mx) - lse;
-            a3.x = (a3.x - mx) - lse; a3.y = (a3.y - mx) - lse;
-            d2[i2] = a0; d2[i2 + 32] = a1; d2[i2 + 64] = a2; d2[i2 + 96] = a3;
+        // hand the normaliser and the smoothed tail to the apply kernel (the candidate scratch of this
+        // row is free again: values to patch in, and where)
+        if (smooth) {
+            for (int e = lane; e < n; e += 32) {
+                cx[e] = tb[e] - lse;
+                cs[e] = ss[e];
+            }
         }
-#pragma unroll 1
-        for (; i2 < S2; i2 += 32) {
-            double2 a0 = s2[i2];
-            a0.x = (a0.x - mx) - lse; a0.y = (a0.y - mx) - lse;
-            d2[i2] = a0;
+        if (lane == 0) {
+            p.hdr[row].lse = lse;
+            p.hdr[row].n_patch = smooth ? n : 0;
+            p.k_out[row] = kk;
         }
-        __syncwarp();
-        if (smooth)
-            for (int e = lane; e < n; e += 32) dst[ss[e]] = tb[e] - lse;
-        if (lane == 0) p.k_out[row] = kk;
     } else {
         // elpd_i = LSE_s(lw_s + ll_s): body terms are the constant -(mx + lse), tail terms differ
         // from it by (smoothed - raw) (loo.py:289,319-324)
@@ -861,9 +907,20 @@ __global__ void __launch_bounds__(TAIL_WARPS * 32, tail_min_blocks<TL>()) psis_t
     double* l1p = reinterpret_cast<double*>(smem_raw + L.off_l1p);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     unsigned char* wbase = smem_raw + L.off_w + L.w_stride * wid;
-    double* xs = reinterpret_cast<double*>(wbase + L.off_x);
-    double* tb = reinterpret_cast<double*>(wbase + L.off_t);
-    int* ss = reinterpret_cast<int*>(wbase + L.off_s);
+    TailStage st;
+    st.xp = reinterpret_cast<double*>(wbase + L.off_a);
+    st.tb = st.xp;
+    st.xs = reinterpret_cast<double*>(wbase + L.off_x);
+    st.ss = reinterpret_cast<unsigned short*>(wbase + L.off_s);
+    st.sp = reinterpret_cast<unsigned short*>(wbase + L.off_p);
+    double* tabm = reinterpret_cast<double*>(smem_raw + L.off_tab);
+    ExpTab tab;
+    tab.t = tabm;
+    tab.tinv = tabm + 32;
+    if (threadIdx.x < 32) {
+        tabm[threadIdx.x] = exp2((double)threadIdx.x / 32.0);
+        tabm[32 + threadIdx.x] = exp2(-(double)threadIdx.x / 32.0);
+    }
     // per-CTA table for the smoothing step: depends only on (rank, M), psis.py:153 + :221
     for (int i = threadIdx.x; i < p.M; i += TAIL_WARPS * 32) l1p[i] = log1p(-(((double)i + 0.5) / (double)p.M));
     __syncthreads();
@@ -872,12 +929,50 @@ __global__ void __launch_bounds__(TAIL_WARPS * 32, tail_min_blocks<TL>()) psis_t
     for (long long row = (long long)blockIdx.x * TAIL_WARPS + wid; row < p.n_rows; row += nwarps) {
         const SplitHeader h = p.hdr[row];
         if (h.flags) continue;
-        const bool ok = tail_row<TL, MODE>(p, row, h, l1p, xs, tb, ss, lane);
+        const bool ok = tail_row<TL, MODE>(p, row, h, l1p, st, tab, lane);
         if (!ok && lane == 0) {
+            p.hdr[row].flags = 1;  // the apply kernel skips the row
             p.fb_list[atomicAdd(p.fb_count, 1)] = (int)row;
             if (p.counters) atomicAdd(&p.counters[3], 1ull);
         }
         __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------ apply kernel (psislw only)
+// out = (r - max r) - lse (psis.py:134,158) for one observation per CTA, then the smoothed tail
+// (psis.py:156) on top.  Pure streaming: 16 S bytes per observation.
+constexpr int APPLY_NT = 256;
+static __global__ void __launch_bounds__(APPLY_NT) psis_apply_kernel(const SplitParams p) {
+    const int S2 = p.S >> 1;
+    for (long long row = blockIdx.x; row < p.n_rows; row += gridDim.x) {
+        const SplitHeader* h = p.hdr + row;
+        if (h->flags) continue;  // block-uniform
+        const double mx = h->mx, lse = h->lse;
+        const int np = h->n_patch;
+        const double2* s2 = reinterpret_cast<const double2*>(p.in + row * p.in_stride);
+        double* dst = p.out + row * p.out_stride;
+        double2* d2 = reinterpret_cast<double2*>(dst);
+        int i2 = threadIdx.x;
+        for (; i2 + 3 * APPLY_NT < S2; i2 += 4 * APPLY_NT) {
+            double2 a0 = s2[i2], a1 = s2[i2 + APPLY_NT], a2 = s2[i2 + 2 * APPLY_NT], a3 = s2[i2 + 3 * APPLY_NT];
+            a0.x = (a0.x - mx) - lse; a0.y = (a0.y - mx) - lse;
+            a1.x = (a1.x - mx) - lse; a1.y = (a1.y - mx) - lse;
+            a2.x = (a2.x - mx) - lse; a2.y = (a2.y - mx) - lse;
+            a3.x = (a3.x - mx) - lse; a3.y = (a3.y - mx) - lse;
+            d2[i2] = a0; d2[i2 + APPLY_NT] = a1; d2[i2 + 2 * APPLY_NT] = a2; d2[i2 + 3 * APPLY_NT] = a3;
+        }
+        for (; i2 < S2; i2 += APPLY_NT) {
+            double2 a0 = s2[i2];
+            a0.x = (a0.x - mx) - lse; a0.y = (a0.y - mx) - lse;
+            d2[i2] = a0;
+        }
+        if (np > 0) {
+            __syncthreads();  // the patches must land after the streamed values of the same draws
+            const double* pv = p.cx + (size_t)row * (size_t)p.cap;
+            const unsigned short* ps = p.cs + (size_t)row * (size_t)p.cap;
+            for (int e = threadIdx.x; e < np; e += APPLY_NT) dst[ps[e]] = pv[e];
+        }
     }
 }
 

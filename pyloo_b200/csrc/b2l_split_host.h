@@ -11,4 +11,5 @@ cudaError_t split_stream_launch(int nt, int ept, int mode, int grid, size_t smem
                                 const SplitParams& q);
 cudaError_t split_tail_setup(int tl, int mode, size_t smem, int* occ);
 cudaError_t split_tail_launch(int tl, int mode, int grid, size_t smem, cudaStream_t st, const SplitParams& q);
+cudaError_t split_apply_launch(int grid, cudaStream_t st, const SplitParams& q);
 }  // namespace b2l

@@ -34,4 +34,9 @@ cudaError_t split_tail_launch(int tl, int mode, int grid, size_t smem, cudaStrea
     return cudaErrorInvalidValue;
 }
 
+cudaError_t split_apply_launch(int grid, cudaStream_t st, const SplitParams& q) {
+    psis_apply_kernel<<<grid, APPLY_NT, 0, st>>>(q);
+    return cudaGetLastError();
+}
+
 }  // namespace b2l

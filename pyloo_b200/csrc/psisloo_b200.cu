@@ -171,7 +171,7 @@ static int launch_rows(int mode, const RowPlan& pl, RowParams rp, cudaStream_t s
 // stream kernel (one CTA per observation, row in registers) + tail kernel (one warp per observation)
 // + the general row kernel on the rows those two hand over.  See b2l_split.cuh.
 struct SplitPlan {
-    int ok, nt, ept, tl, cap, q0, grid1, grid2, occ1, occ2;
+    int ok, nt, ept, tl, cap, q0, nbuf, grid1, grid2, occ1, occ2;
     size_t smem1, smem2;
     long long batch;  // observations per stream -> tail -> fallback round
 };
@@ -205,7 +205,9 @@ static bool split_shape(long long S, int M, long long n_rows, SplitPlan* sp) {
     b = std::min<long long>(16384, std::max<long long>(256, b / 64 * 64));
     if (const char* ev = getenv("B2L_BATCH")) b = std::max<long long>(1, atoll(ev));
     sp->batch = std::max<long long>(1, std::min<long long>(b, std::max<long long>(n_rows, 1)));
-    sp->smem1 = stream_smem((int)S).total;
+    sp->nbuf = (stream_smem((int)S, 2).total <= 200 * 1024) ? 2 : 1;
+    if (const char* ev = getenv("B2L_SNBUF")) sp->nbuf = (atoi(ev) == 1) ? 1 : sp->nbuf;
+    sp->smem1 = stream_smem((int)S, sp->nbuf).total;
     sp->smem2 = tail_smem(M, sp->tl, TAIL_WARPS).total;
     return true;
 }
@@ -230,7 +232,7 @@ static int plan_split(long long S, int M, int mode, long long n_rows, SplitPlan*
 static size_t split_ws_bytes(const SplitPlan& sp) {
     if (!sp.nt) return 0;
     return align_up((size_t)sp.batch * sizeof(SplitHeader), 256) + align_up((size_t)sp.batch * sp.cap * 8, 256) +
-           align_up((size_t)sp.batch * 4, 256) + 256;
+           align_up((size_t)sp.batch * sp.cap * 2, 256) + align_up((size_t)sp.batch * 4, 256) + 256;
 }
 
 static int launch_split(int mode, const RowPlan& pl, const SplitPlan& sp, const RowParams& rp, void* sws,
@@ -238,8 +240,10 @@ static int launch_split(int mode, const RowPlan& pl, const SplitPlan& sp, const 
     char* w = (char*)sws;
     SplitHeader* hdr = reinterpret_cast<SplitHeader*>(w);
     w += align_up((size_t)sp.batch * sizeof(SplitHeader), 256);
-    unsigned long long* ckey = reinterpret_cast<unsigned long long*>(w);
+    double* cx = reinterpret_cast<double*>(w);
     w += align_up((size_t)sp.batch * sp.cap * 8, 256);
+    unsigned short* cs = reinterpret_cast<unsigned short*>(w);
+    w += align_up((size_t)sp.batch * sp.cap * 2, 256);
     int* fb_list = reinterpret_cast<int*>(w);
     w += align_up((size_t)sp.batch * 4, 256);
     int* fb_count = reinterpret_cast<int*>(w);
@@ -256,13 +260,14 @@ static int launch_split(int mode, const RowPlan& pl, const SplitPlan& sp, const 
         q.elpd_i = rp.elpd_i ? rp.elpd_i + i0 : nullptr; q.lppd_i = rp.lppd_i ? rp.lppd_i + i0 : nullptr;
         q.var_i = rp.var_i ? rp.var_i + i0 : nullptr; q.lppdw_i = rp.lppdw_i ? rp.lppdw_i + i0 : nullptr;
         q.diag = rp.diag ? rp.diag + i0 * DIAG_STRIDE : nullptr;
-        q.n_rows = nb; q.S = rp.S; q.M = rp.M; q.cap = sp.cap; q.q0 = sp.q0; q.m_full = 30 + msq;
-        q.cutoffmin = rp.cutoffmin; q.counters = rp.counters; q.hdr = hdr; q.ckey = ckey; q.fb_list = fb_list; q.fb_count = fb_count;
+        q.n_rows = nb; q.S = rp.S; q.M = rp.M; q.cap = sp.cap; q.nbuf = sp.nbuf; q.q0 = sp.q0; q.m_full = 30 + msq;
+        q.cutoffmin = rp.cutoffmin; q.counters = rp.counters; q.hdr = hdr; q.cx = cx; q.cs = cs; q.fb_list = fb_list; q.fb_count = fb_count;
         CK(cudaMemsetAsync(fb_count, 0, sizeof(int), st));
         const int g1 = (int)std::min<long long>(sp.grid1, nb);
         const int g2 = (int)std::min<long long>(sp.grid2, (nb + TAIL_WARPS - 1) / TAIL_WARPS);
         CK(split_stream_launch(sp.nt, sp.ept, mode, g1, sp.smem1, st, q));
         CK(split_tail_launch(sp.tl, mode, g2, sp.smem2, st, q));
+        if (mode == MODE_PSISLW) CK(split_apply_launch((int)std::min<long long>(nb, 8ll * pl.sms), st, q));
         // rows handed over: general kernel driven by the device-side list (empty list = no work)
         RowParams r = rp;
         r.in = q.in; r.out = q.out; r.k_out = q.k_out; r.elpd_i = q.elpd_i; r.lppd_i = q.lppd_i;
