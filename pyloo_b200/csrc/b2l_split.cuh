@@ -109,6 +109,31 @@ __device__ __forceinline__ void exp_tab_pm(double x, const ExpTab& tb, double& e
     em = scale2(tb.tinv[j] * exp_poly5(-r), -n);
 }
 
+// log(y) for the smoothed tail: y = 2^e m, m = c_j (1 + r) with c_j the centre of the j-th of 64
+// mantissa intervals: log y = e ln2 + log c_j + log1p(r), |r| <= 2^-7, degree-6 series (absolute
+// error < 5e-16).  tab: [0..63] 1/c_j (rounded), [64..127] -log(1/c_j).  Zero, denormal, negative,
+// inf and NaN arguments take the library routine.
+__device__ __forceinline__ void log_tab_init(double* tab, int j) {  // j < 64
+    const double ic = 1.0 / (1.0 + ((double)j + 0.5) / 64.0);
+    tab[j] = ic;
+    tab[64 + j] = -log(ic);
+}
+__device__ __forceinline__ double log_tab(double y, const double* tab) {
+    const int hi = __double2hiint(y);
+    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return log(y);
+    const int e = (hi >> 20) - 1023;
+    const int j = (hi >> 14) & 63;
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(y));
+    const double r = fma(m, tab[j], -1.0);
+    double p = -1.0 / 6.0;
+    p = fma(p, r, 0.2);
+    p = fma(p, r, -0.25);
+    p = fma(p, r, 1.0 / 3.0);
+    p = fma(p, r, -0.5);
+    p = fma(p, r, 1.0);
+    return fma((double)e, 0.6931471805599453094, fma(p, r, tab[64 + j]));
+}
+
 __device__ __forceinline__ float warp_sort32_f(float v, int lane) {  // ascending across lanes
 #pragma unroll
     for (int k = 2; k <= 32; k <<= 1) {
@@ -625,8 +650,8 @@ __host__ __device__ inline TailSmem tail_smem(int M, int TL, int warps) {
     TailSmem L;
     L.off_l1p = 0;
     size_t o = align_up((size_t)(M + 1) * 8, 16);
-    L.off_tab = o;
-    o += 64 * 8;
+    L.off_tab = o;   // 64 doubles exp table + 128 doubles log table
+    o += (64 + 128) * 8;
     L.off_w = o;
     L.off_a = 0;
     L.off_x = (size_t)64 * TL * 8;
@@ -774,7 +799,7 @@ __device__ __forceinline__ bool tail_row(const SplitParams& p, long long row, co
     const double xc = xs[M];
     int n = M;
     while (n > 0 && xs[n - 1] == xc) --n;
-    bool bad = xc < p.cutoffmin;  // cutoff clamped at log(DBL_MIN): general kernel
+    bool bad = !(xc >= -690.0);  // cutoff near / below log(DBL_MIN) (clamp, psis.py:136): general kernel
     // safety net: the order inside the tail must be exact (descending x, descending index on ties)
     for (int e = lane; e + 1 < n; e += 32) {
         const double a = xs[e], b = xs[e + 1];
@@ -786,12 +811,12 @@ __device__ __forceinline__ bool tail_row(const SplitParams& p, long long row, co
     const double exp_c = exp(c);  // psis.py:138
     // staged candidates at or below the cutoff belong to the normaliser's body too
 #pragma unroll 1
-    for (int e = n + lane; e < min(C, 32 * TL); e += 32) nont += exp(xs[e]);
+    for (int e = n + lane; e < min(C, 32 * TL); e += 32) nont += exp_tab(xs[e], tab);
     // t_i = exp(x_i) - exp(c) (psis.py:146-147), descending
     double tsum = 0.0, traw = 0.0;
 #pragma unroll 1
     for (int e = lane; e < n; e += 32) {
-        const double ex = exp(xs[e]);
+        const double ex = exp_tab(xs[e], tab);  // x >= c >= -690
         const double ti = ex - exp_c;
         tb[e] = ti;
         tsum += ti;
@@ -821,25 +846,45 @@ __device__ __forceinline__ bool tail_row(const SplitParams& p, long long row, co
     if (smooth) {
         double tsm = 0.0;
         __syncwarp();
+        const double* ltab = tab.t + 64;
+        if (sigma > 0.0 && fabs(kk) >= 0.01 && fabs(kk) < 50.0 && n == M) {
+            // common case: expm1(u) = exp(u) - 1 is accurate enough once |k| is not tiny (|u| >=
+            // 2.5e-5; the lowest ranks, where the relative error of the difference peaks, add the
+            // least to q + exp(c)); table-driven exp and log
+            const double sk = sigma / kk;
 #pragma unroll 1
-        for (int e = lane; e < n; e += 32) {
-            const int rk = n - 1 - e;
-            double q;
-            if (sigma <= 0.0) {
-                q = nan_f64();
-            } else {
-                const double l1 = (n == M) ? l1p[rk] : log1p(-(((double)rk + 0.5) / (double)n));
-                q = (fabs(kk) < 2.220446049250313e-16) ? -l1 : expm1(-kk * l1) / kk;
-                q *= sigma;
+            for (int e = lane; e < n; e += 32) {
+                const double u = -kk * l1p[n - 1 - e];
+                double y = fma(exp_tab(u, tab) - 1.0, sk, exp_c);
+                double s_ = log_tab(y, ltab);
+                if (s_ > 0.0) {  // psis.py:157
+                    s_ = 0.0;
+                    y = 1.0;
+                }
+                tb[e] = s_;
+                tsm += y;
             }
-            double y = q + exp_c;
-            double s_ = log(y);
-            if (s_ > 0.0) {  // psis.py:157
-                s_ = 0.0;
-                y = 1.0;
+        } else {
+#pragma unroll 1
+            for (int e = lane; e < n; e += 32) {
+                const int rk = n - 1 - e;
+                double q;
+                if (sigma <= 0.0) {
+                    q = nan_f64();
+                } else {
+                    const double l1 = (n == M) ? l1p[rk] : log1p(-(((double)rk + 0.5) / (double)n));
+                    q = (fabs(kk) < 2.220446049250313e-16) ? -l1 : expm1(-kk * l1) / kk;
+                    q *= sigma;
+                }
+                double y = q + exp_c;
+                double s_ = log(y);
+                if (s_ > 0.0) {  // psis.py:157
+                    s_ = 0.0;
+                    y = 1.0;
+                }
+                tb[e] = s_;
+                tsm += y;
             }
-            tb[e] = s_;
-            tsm += y;
         }
         tails = warp_sum(tsm);
         __syncwarp();
@@ -921,6 +966,7 @@ __global__ void __launch_bounds__(TAIL_WARPS * 32, tail_min_blocks<TL>()) psis_t
         tabm[threadIdx.x] = exp2((double)threadIdx.x / 32.0);
         tabm[32 + threadIdx.x] = exp2(-(double)threadIdx.x / 32.0);
     }
+    if (threadIdx.x < 64) log_tab_init(tabm + 64, threadIdx.x);
     // per-CTA table for the smoothing step: depends only on (rank, M), psis.py:153 + :221
     for (int i = threadIdx.x; i < p.M; i += TAIL_WARPS * 32) l1p[i] = log1p(-(((double)i + 0.5) / (double)p.M));
     __syncthreads();

@@ -200,9 +200,10 @@ static bool split_shape(long long S, int M, long long n_rows, SplitPlan* sp) {
         if (const char* ev = getenv("B2L_Q0")) q = atoi(ev);
         sp->q0 = std::min(30, std::max(1, q));
     }
-    // observations per stream -> tail -> fallback round: ~128 MB of draws
-    long long b = (128ll << 20) / (S * 8);
-    b = std::min<long long>(16384, std::max<long long>(256, b / 64 * 64));
+    // observations per stream -> tail -> apply -> hand-over round: a multiple of every resident-CTA /
+    // resident-warp count the kernels reach on 148 SMs (no partial last wave), ~230 MB at S = 4000
+    long long b = 148ll * 48;
+    while (b > 148 * 6 && b * S * 8 > (1ll << 30)) b /= 2;
     if (const char* ev = getenv("B2L_BATCH")) b = std::max<long long>(1, atoll(ev));
     sp->batch = std::max<long long>(1, std::min<long long>(b, std::max<long long>(n_rows, 1)));
     sp->nbuf = (stream_smem((int)S, 2).total <= 200 * 1024) ? 2 : 1;

@@ -65,6 +65,6 @@ if os.environ.get("RANGES"):
     ranges = [tuple(map(int, r.split("-"))) for r in os.environ["RANGES"].split(",")]
     print("\nby line range:")
     for a, b in ranges:
-        n = sum(v[0] for ln, v in agg.items() if ln and ln[0] == "b2l_row_kernel.cuh" and a <= ln[1] <= b)
-        s = sum(v[1] for ln, v in agg.items() if ln and ln[0] == "b2l_row_kernel.cuh" and a <= ln[1] <= b)
+        n = sum(v[0] for ln, v in agg.items() if ln and ln[0] == os.environ.get("RANGE_FILE", "b2l_row_kernel.cuh") and a <= ln[1] <= b)
+        s = sum(v[1] for ln, v in agg.items() if ln and ln[0] == os.environ.get("RANGE_FILE", "b2l_row_kernel.cuh") and a <= ln[1] <= b)
         print(f"  {a:>4}-{b:<4} {n:>11} {100*n/tot:5.1f}%  stall {100*s/max(tots,1):5.1f}%")
