@@ -476,6 +476,8 @@ __global__ void __launch_bounds__(NT, (NT == 128) ? 4 : ((NT == 256) ? 3 : 1)) p
     const uint32_t row_tx = (uint32_t)S * 8u;
     const double NEG_INF = -inf_f64();
 
+    // nothing to do for this CTA (the usual case when it only serves the split path's hand-over list)
+    if ((long long)blockIdx.x >= (p.row_list ? (long long)*p.n_list : p.n_rows)) return;
     if (p.use_bulk && tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);

@@ -196,8 +196,13 @@ __device__ __forceinline__ double slots_sum(const double* s, int lane) {
     return warp_sum(lane < NW ? s[lane] : 0.0);
 }
 
+#ifndef B2L_STREAM_OCC
+#define B2L_STREAM_OCC 4  // resident 256-thread CTAs per SM the stream kernel is compiled for
+#endif
 template <int NT>
-constexpr int stream_min_blocks() { return NT == 128 ? 6 : (NT == 256 ? 3 : 1); }
+constexpr int stream_min_blocks() {
+    return NT == 128 ? 2 * B2L_STREAM_OCC : (NT == 256 ? B2L_STREAM_OCC : (NT == 512 ? B2L_STREAM_OCC / 2 : 1));
+}
 
 // ------------------------------------------------------------------ stream kernel
 template <int NT, int EPT, int MODE>
@@ -341,8 +346,20 @@ __global__ void __launch_bounds__(NT, stream_min_blocks<NT>()) psis_stream_kerne
 #pragma unroll
             for (int j = 0; j < EP2; ++j) {
 #pragma unroll
+                double2 vv;
+                if (j < nv) {
+                    vv = rowbuf[j * NT + tid];
+                    if (MODE == MODE_LOO) {
+                        vv.x = -vv.x;
+                        vv.y = -vv.y;
+                    }
+                } else {
+                    vv.x = NEG_INF;
+                    vv.y = NEG_INF;
+                }
+#pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const double r = h ? v[j].y : v[j].x;
+                    const double r = h ? vv.y : vv.x;
                     const double x = r - mxl;  // psis.py:134
                     const bool cand = x >= taux;
                     cmask |= cand ? (1u << (2 * j + h)) : 0u;

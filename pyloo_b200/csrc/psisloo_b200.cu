@@ -221,7 +221,15 @@ static int plan_split(long long S, int M, int mode, long long n_rows, SplitPlan*
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     CK(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     if (sp->smem1 > (size_t)smem_optin || sp->smem2 > (size_t)smem_optin) return 0;
-    CK(split_stream_setup(nt, ept, mode, sp->smem1, &sp->occ1));
+    // one or two row buffers: two (prefetch during the whole row) unless that costs resident CTAs
+    {
+        int occ1 = 0, occ2 = 0;
+        const size_t sm1 = stream_smem((int)S, 1).total, sm2 = stream_smem((int)S, 2).total;
+        if (sm2 <= (size_t)smem_optin && sp->nbuf == 2) CK(split_stream_setup(nt, ept, mode, sm2, &occ2));
+        CK(split_stream_setup(nt, ept, mode, sm1, &occ1));
+        if (occ2 >= occ1 && occ2 > 0) { sp->nbuf = 2; sp->smem1 = sm2; sp->occ1 = occ2; CK(split_stream_setup(nt, ept, mode, sm2, &occ2)); }
+        else { sp->nbuf = 1; sp->smem1 = sm1; sp->occ1 = occ1; }
+    }
     CK(split_tail_setup(sp->tl, mode, sp->smem2, &sp->occ2));
     if (sp->occ1 < 1 || sp->occ2 < 1) return 0;
     sp->grid1 = sms * sp->occ1;
