@@ -64,6 +64,15 @@ struct SplitParams {
     int* fb_list;              // [n_rows] rows for the general kernel
     int* fb_count;
     unsigned long long* counters;  // optional [4]; [3] += rows handed to the general kernel
+    long long row_base;        // index of row 0 of this batch in the caller's arrays (hand-over list entries)
+    // apply stage fused into the stream kernel (psislw): rows of the PREVIOUS batch, whose tail
+    // kernel has finished -- one extra warp per CTA streams them through shared memory with bulk TMA
+    const double* a_in;
+    double* a_out;
+    const SplitHeader* a_hdr;
+    const double* a_cx;
+    const unsigned short* a_cs;
+    long long a_rows;
 };
 
 // ------------------------------------------------------------------ table-driven exp for the sums
@@ -148,12 +157,14 @@ __device__ __forceinline__ float warp_sort32_f(float v, int lane) {  // ascendin
 }
 
 struct StreamSmem {
-    size_t row_bytes, off_tab, off_red, off_ctl, off_bar, total;
+    size_t row_bytes, off_apply, off_tab, off_red, off_ctl, off_bar, total;
 };
-__host__ __device__ inline StreamSmem stream_smem(int S, int nbuf) {
+__host__ __device__ inline StreamSmem stream_smem(int S, int nbuf, bool apply) {
     StreamSmem L;
     L.row_bytes = align_up((size_t)S * 8, 128);
     size_t o = L.row_bytes * (size_t)nbuf;
+    L.off_apply = o;  // one row buffer of the apply warp
+    o += apply ? L.row_bytes : 0;
     L.off_tab = o;   // 64 doubles
     o += 64 * 8;
     L.off_red = o;   // 2 x (5 x 32 doubles + 32 floats): sets alternate between consecutive rows
@@ -161,9 +172,28 @@ __host__ __device__ inline StreamSmem stream_smem(int S, int nbuf) {
     L.off_ctl = o;
     o += 16 * 4;
     L.off_bar = o;
-    o += 16;
+    o += 32;
     L.total = align_up(o, 128);
     return L;
+}
+
+// named barriers for the stream warps (the apply warp of the same CTA never joins them)
+__device__ __forceinline__ void bar_sync_n(int nthreads) {
+    asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
+__device__ __forceinline__ bool bar_or_n(int nthreads, bool pred) {
+    int r;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        "setp.ne.s32 p, %2, 0;\n\t"
+        "bar.red.or.pred q, 1, %1, p;\n\t"
+        "selp.s32 %0, 1, 0, q;\n\t"
+        "}"
+        : "=r"(r)
+        : "r"(nthreads), "r"((int)pred)
+        : "memory");
+    return r != 0;
 }
 
 // compare-select max / min: fmax / fmin on doubles expand to ~8 instructions each (IEEE NaN rules);
@@ -197,23 +227,73 @@ __device__ __forceinline__ double slots_sum(const double* s, int lane) {
 }
 
 #ifndef B2L_STREAM_OCC
-#define B2L_STREAM_OCC 4  // resident 256-thread CTAs per SM the stream kernel is compiled for
+#define B2L_STREAM_OCC 3  // resident 256(+32)-thread CTAs per SM the stream kernel is compiled for
 #endif
+// psislw stream CTAs carry one extra warp for the fused apply stage (not at 1024 threads: block limit)
+__host__ __device__ constexpr bool stream_has_apply(int nt, int mode) { return mode == MODE_PSISLW && nt <= 512; }
+__host__ __device__ constexpr int stream_block(int nt, int mode) { return nt + (stream_has_apply(nt, mode) ? 32 : 0); }
 template <int NT>
 constexpr int stream_min_blocks() {
     return NT == 128 ? 2 * B2L_STREAM_OCC : (NT == 256 ? B2L_STREAM_OCC : (NT == 512 ? B2L_STREAM_OCC / 2 : 1));
 }
 
 // ------------------------------------------------------------------ stream kernel
+// The apply warp (psislw only, threads NT .. NT + 31): out = (r - max r) - lse (psis.py:134,158)
+// plus the smoothed tail (psis.py:156) for the rows of the previous batch, one row at a time through
+// its own shared-memory buffer: bulk TMA load, in-place transform, patches, bulk TMA store.
+__device__ __forceinline__ void apply_warp_loop(const SplitParams& p, unsigned char* abuf_raw, uint64_t* abar,
+                                                int lane) {
+    const int S2 = p.S >> 1;
+    const uint32_t row_tx = (uint32_t)p.S * 8u;
+    double* abuf = reinterpret_cast<double*>(abuf_raw);
+    double2* abuf2 = reinterpret_cast<double2*>(abuf_raw);
+    uint32_t phase = 0;
+    for (long long row = blockIdx.x; row < p.a_rows; row += gridDim.x) {
+        const SplitHeader* h = p.a_hdr + row;
+        if (h->flags) continue;  // handed to the general kernel (warp-uniform)
+        const double mx = h->mx, lse = h->lse;
+        const int np = h->n_patch;
+        if (lane == 0) {
+            mbar_expect_tx(abar, row_tx);
+            bulk_g2s(abuf_raw, p.a_in + row * p.in_stride, row_tx, abar);
+        }
+        mbar_wait(abar, phase);
+        phase ^= 1u;
+#pragma unroll 4
+        for (int i2 = lane; i2 < S2; i2 += 32) {
+            double2 a = abuf2[i2];
+            a.x = (a.x - mx) - lse;
+            a.y = (a.y - mx) - lse;
+            abuf2[i2] = a;
+        }
+        __syncwarp();
+        if (np > 0) {  // smoothed draws land on top of the streamed values
+            const double* pv = p.a_cx + (size_t)row * (size_t)p.cap;
+            const unsigned short* ps = p.a_cs + (size_t)row * (size_t)p.cap;
+            for (int e = lane; e < np; e += 32) abuf[ps[e]] = pv[e];
+            __syncwarp();
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            bulk_s2g(p.a_out + row * p.out_stride, abuf_raw, row_tx);
+            bulk_commit();
+            bulk_wait_read0();  // the buffer may be refilled once the store has read it
+        }
+        __syncwarp();
+    }
+    if (lane == 0) bulk_wait0();
+}
+
 template <int NT, int EPT, int MODE>
-__global__ void __launch_bounds__(NT, stream_min_blocks<NT>()) psis_stream_kernel(const SplitParams p) {
+__global__ void __launch_bounds__(stream_block(NT, MODE), stream_min_blocks<NT>()) psis_stream_kernel(const SplitParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NW = NT / 32;
     constexpr int EP2 = EPT / 2;
     const int S = p.S, M = p.M, cap = p.cap;
     const int S2 = S >> 1;
     const int nbuf = p.nbuf;
-    const StreamSmem L = stream_smem(S, nbuf);
+    const StreamSmem L = stream_smem(S, nbuf, stream_has_apply(NT, MODE));
     double* tab = reinterpret_cast<double*>(smem_raw + L.off_tab);
     int* ctl_all = reinterpret_cast<int*>(smem_raw + L.off_ctl);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.off_bar);
@@ -227,6 +307,7 @@ __global__ void __launch_bounds__(NT, stream_min_blocks<NT>()) psis_stream_kerne
     if (tid == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
+        mbar_init(&bar[2], 1);
         fence_mbar_init();
     }
     if (tid < 32) {
@@ -234,6 +315,10 @@ __global__ void __launch_bounds__(NT, stream_min_blocks<NT>()) psis_stream_kerne
         tab[32 + tid] = exp2(-(double)tid / 32.0);
     }
     __syncthreads();
+    if (stream_has_apply(NT, MODE) && tid >= NT) {  // the apply warp goes its own way (no CTA-wide barrier below)
+        apply_warp_loop(p, smem_raw + L.off_apply, &bar[2], lane);
+        return;
+    }
     long long row = blockIdx.x;
     if (tid == 0 && row < p.n_rows) {
         mbar_expect_tx(&bar[0], row_tx);
@@ -296,7 +381,7 @@ __global__ void __launch_bounds__(NT, stream_min_blocks<NT>()) psis_stream_kerne
         }
         if (tid == 0) ctl[0] = 0;
         // (1) every warp is past the previous row: the other buffer can take the next row now
-        const bool special = __syncthreads_or(spec >= 0x7ff00000) != 0;
+        const bool special = bar_or_n(NT, spec >= 0x7ff00000);
         if (nbuf == 2 && tid == 0 && row + gridDim.x < p.n_rows) {
             fence_proxy_async();
             mbar_expect_tx(&bar[bsel ^ 1], row_tx);
@@ -320,7 +405,7 @@ __global__ void __launch_bounds__(NT, stream_min_blocks<NT>()) psis_stream_kerne
         bool ok = !special;
         while (ok) {
             if (lane == q - 1) redf[wid] = dsorted;
-            __syncthreads();  // (2)
+            bar_sync_n(NT);  // (2)
             double taux;
             {
                 const float mine = (lane < NW) ? redf[lane] : __int_as_float(0x7f800000);
@@ -428,7 +513,7 @@ __global__ void __launch_bounds__(NT, stream_min_blocks<NT>()) psis_stream_kerne
                     red[wid] = vs;  // slot 0 is free again (mx was read before barrier 2)
                 }
             }
-            __syncthreads();  // (3)
+            bar_sync_n(NT);  // (3)
             C = ctl[0];
             body = slots_sum<NW>(red + 96, lane);
             if (MODE == MODE_LOO) {
@@ -443,7 +528,7 @@ __global__ void __launch_bounds__(NT, stream_min_blocks<NT>()) psis_stream_kerne
             else qn = max(1, min(q - 1, (int)((double)q * 1.3 * (double)(M + 1) / (double)C)));
             if (attempts >= 3 || qn == q) ok = false;
             q = qn;
-            __syncthreads();  // everyone has read ctl[0] / red before they are reused
+            bar_sync_n(NT);  // everyone has read ctl[0] / red before they are reused
             if (tid == 0) ctl[0] = 0;
         }
         if (nbuf == 1 && tid == 0 && row + gridDim.x < p.n_rows) {
@@ -459,7 +544,7 @@ __global__ void __launch_bounds__(NT, stream_min_blocks<NT>()) psis_stream_kerne
             h.lse = 0.0; h.C = C; h.flags = ok ? 0 : 1; h.attempts = attempts; h.n_patch = 0;
             p.hdr[row] = h;
             if (!ok) {
-                p.fb_list[atomicAdd(p.fb_count, 1)] = (int)row;
+                p.fb_list[atomicAdd(p.fb_count, 1)] = (int)(p.row_base + row);
                 if (p.counters) atomicAdd(&p.counters[3], 1ull);
             }
         }
@@ -995,7 +1080,7 @@ __global__ void __launch_bounds__(TAIL_WARPS * 32, tail_min_blocks<TL>()) psis_t
         const bool ok = tail_row<TL, MODE>(p, row, h, l1p, st, tab, lane);
         if (!ok && lane == 0) {
             p.hdr[row].flags = 1;  // the apply kernel skips the row
-            p.fb_list[atomicAdd(p.fb_count, 1)] = (int)row;
+            p.fb_list[atomicAdd(p.fb_count, 1)] = (int)(p.row_base + row);
             if (p.counters) atomicAdd(&p.counters[3], 1ull);
         }
         __syncwarp();

@@ -11,7 +11,7 @@ static cudaError_t setup1(size_t smem, int* occ) {
     cudaError_t e = cudaFuncSetAttribute(psis_stream_kernel<NT, EPT, MODE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, psis_stream_kernel<NT, EPT, MODE>, NT, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, psis_stream_kernel<NT, EPT, MODE>, stream_block(NT, MODE), smem);
 }
 
 cudaError_t split_stream_setup(int nt, int ept, int mode, size_t smem, int* occ) {
@@ -28,7 +28,7 @@ cudaError_t split_stream_launch(int nt, int ept, int mode, int grid, size_t smem
                                 const SplitParams& q) {
 #define X(NT_, EPT_)                                                                               \
     if (nt == NT_ && ept == EPT_) {                                                                \
-        if (mode == MODE_PSISLW) psis_stream_kernel<NT_, EPT_, MODE_PSISLW><<<grid, NT_, smem, st>>>(q); \
+        if (mode == MODE_PSISLW) psis_stream_kernel<NT_, EPT_, MODE_PSISLW><<<grid, stream_block(NT_, MODE_PSISLW), smem, st>>>(q); \
         else psis_stream_kernel<NT_, EPT_, MODE_LOO><<<grid, NT_, smem, st>>>(q);                  \
         return cudaGetLastError();                                                                 \
     }

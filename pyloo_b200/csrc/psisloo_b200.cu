@@ -171,7 +171,7 @@ static int launch_rows(int mode, const RowPlan& pl, RowParams rp, cudaStream_t s
 // stream kernel (one CTA per observation, row in registers) + tail kernel (one warp per observation)
 // + the general row kernel on the rows those two hand over.  See b2l_split.cuh.
 struct SplitPlan {
-    int ok, nt, ept, tl, cap, q0, nbuf, grid1, grid2, occ1, occ2;
+    int ok, nt, ept, tl, cap, q0, nbuf, fused, grid1, grid2, occ1, occ2;
     size_t smem1, smem2;
     long long batch;  // observations per stream -> tail -> fallback round
 };
@@ -206,9 +206,9 @@ static bool split_shape(long long S, int M, long long n_rows, SplitPlan* sp) {
     while (b > 148 * 6 && b * S * 8 > (1ll << 30)) b /= 2;
     if (const char* ev = getenv("B2L_BATCH")) b = std::max<long long>(1, atoll(ev));
     sp->batch = std::max<long long>(1, std::min<long long>(b, std::max<long long>(n_rows, 1)));
-    sp->nbuf = (stream_smem((int)S, 2).total <= 200 * 1024) ? 2 : 1;
+    sp->nbuf = 2;
     if (const char* ev = getenv("B2L_SNBUF")) sp->nbuf = (atoi(ev) == 1) ? 1 : sp->nbuf;
-    sp->smem1 = stream_smem((int)S, sp->nbuf).total;
+    sp->smem1 = stream_smem((int)S, 1, false).total;  // refined per mode in plan_split
     sp->smem2 = tail_smem(M, sp->tl, TAIL_WARPS).total;
     return true;
 }
@@ -220,11 +220,14 @@ static int plan_split(long long S, int M, int mode, long long n_rows, SplitPlan*
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     CK(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    if (sp->smem1 > (size_t)smem_optin || sp->smem2 > (size_t)smem_optin) return 0;
+    if (sp->smem2 > (size_t)smem_optin) return 0;
     // one or two row buffers: two (prefetch during the whole row) unless that costs resident CTAs
     {
+        const bool ap = stream_has_apply(nt, mode);
+        sp->fused = (ap && !(getenv("B2L_FUSED_APPLY") && atoi(getenv("B2L_FUSED_APPLY")) == 0)) ? 1 : 0;
         int occ1 = 0, occ2 = 0;
-        const size_t sm1 = stream_smem((int)S, 1).total, sm2 = stream_smem((int)S, 2).total;
+        const size_t sm1 = stream_smem((int)S, 1, ap).total, sm2 = stream_smem((int)S, 2, ap).total;
+        if (sm1 > (size_t)smem_optin) return 0;
         if (sm2 <= (size_t)smem_optin && sp->nbuf == 2) CK(split_stream_setup(nt, ept, mode, sm2, &occ2));
         CK(split_stream_setup(nt, ept, mode, sm1, &occ1));
         if (occ2 >= occ1 && occ2 > 0) { sp->nbuf = 2; sp->smem1 = sm2; sp->occ1 = occ2; CK(split_stream_setup(nt, ept, mode, sm2, &occ2)); }
@@ -238,29 +241,44 @@ static int plan_split(long long S, int M, int mode, long long n_rows, SplitPlan*
     return 0;
 }
 
-static size_t split_ws_bytes(const SplitPlan& sp) {
-    if (!sp.nt) return 0;
+// scratch: two slots of [headers | candidate x | candidate s] (the apply stage of batch b runs inside the
+// stream kernel of batch b + 1), the hand-over list over all rows of the call, its counter
+static size_t split_slot_bytes(const SplitPlan& sp) {
     return align_up((size_t)sp.batch * sizeof(SplitHeader), 256) + align_up((size_t)sp.batch * sp.cap * 8, 256) +
-           align_up((size_t)sp.batch * sp.cap * 2, 256) + align_up((size_t)sp.batch * 4, 256) + 256;
+           align_up((size_t)sp.batch * sp.cap * 2, 256);
+}
+static size_t split_ws_bytes(const SplitPlan& sp, long long n_rows) {
+    if (!sp.nt) return 0;
+    return 2 * split_slot_bytes(sp) + align_up((size_t)std::max<long long>(n_rows, 1) * 4, 256) + 256;
 }
 
 static int launch_split(int mode, const RowPlan& pl, const SplitPlan& sp, const RowParams& rp, void* sws,
                         cudaStream_t st) {
     char* w = (char*)sws;
-    SplitHeader* hdr = reinterpret_cast<SplitHeader*>(w);
-    w += align_up((size_t)sp.batch * sizeof(SplitHeader), 256);
-    double* cx = reinterpret_cast<double*>(w);
-    w += align_up((size_t)sp.batch * sp.cap * 8, 256);
-    unsigned short* cs = reinterpret_cast<unsigned short*>(w);
-    w += align_up((size_t)sp.batch * sp.cap * 2, 256);
+    SplitHeader* hdr[2];
+    double* cx[2];
+    unsigned short* cs[2];
+    for (int k = 0; k < 2; ++k) {
+        hdr[k] = reinterpret_cast<SplitHeader*>(w);
+        w += align_up((size_t)sp.batch * sizeof(SplitHeader), 256);
+        cx[k] = reinterpret_cast<double*>(w);
+        w += align_up((size_t)sp.batch * sp.cap * 8, 256);
+        cs[k] = reinterpret_cast<unsigned short*>(w);
+        w += align_up((size_t)sp.batch * sp.cap * 2, 256);
+    }
     int* fb_list = reinterpret_cast<int*>(w);
-    w += align_up((size_t)sp.batch * 4, 256);
+    w += align_up((size_t)std::max<long long>(rp.n_rows, 1) * 4, 256);
     int* fb_count = reinterpret_cast<int*>(w);
     int msq = (int)std::sqrt((double)rp.M);
     while (msq * msq > rp.M) --msq;
     while ((msq + 1) * (msq + 1) <= rp.M) ++msq;
-    for (long long i0 = 0; i0 < rp.n_rows; i0 += sp.batch) {
-        const long long nb = std::min<long long>(sp.batch, rp.n_rows - i0);
+    CK(cudaMemsetAsync(fb_count, 0, sizeof(int), st));
+    SplitParams prev;
+    memset(&prev, 0, sizeof(prev));
+    long long prev_rows = 0;
+    int slot = 0;
+    for (long long i0 = 0; i0 < rp.n_rows || prev_rows > 0; i0 += sp.batch, slot ^= 1) {
+        const long long nb = std::max<long long>(0, std::min<long long>(sp.batch, rp.n_rows - i0));
         SplitParams q;
         memset(&q, 0, sizeof(q));
         q.in = rp.in + i0 * rp.in_stride; q.in_stride = rp.in_stride;
@@ -270,24 +288,30 @@ static int launch_split(int mode, const RowPlan& pl, const SplitPlan& sp, const 
         q.var_i = rp.var_i ? rp.var_i + i0 : nullptr; q.lppdw_i = rp.lppdw_i ? rp.lppdw_i + i0 : nullptr;
         q.diag = rp.diag ? rp.diag + i0 * DIAG_STRIDE : nullptr;
         q.n_rows = nb; q.S = rp.S; q.M = rp.M; q.cap = sp.cap; q.nbuf = sp.nbuf; q.q0 = sp.q0; q.m_full = 30 + msq;
-        q.cutoffmin = rp.cutoffmin; q.counters = rp.counters; q.hdr = hdr; q.cx = cx; q.cs = cs; q.fb_list = fb_list; q.fb_count = fb_count;
-        CK(cudaMemsetAsync(fb_count, 0, sizeof(int), st));
-        const int g1 = (int)std::min<long long>(sp.grid1, nb);
-        const int g2 = (int)std::min<long long>(sp.grid2, (nb + TAIL_WARPS - 1) / TAIL_WARPS);
-        CK(split_stream_launch(sp.nt, sp.ept, mode, g1, sp.smem1, st, q));
-        CK(split_tail_launch(sp.tl, mode, g2, sp.smem2, st, q));
-        if (mode == MODE_PSISLW) CK(split_apply_launch((int)std::min<long long>(nb, 8ll * pl.sms), st, q));
-        // rows handed over: general kernel driven by the device-side list (empty list = no work)
-        RowParams r = rp;
-        r.in = q.in; r.out = q.out; r.k_out = q.k_out; r.elpd_i = q.elpd_i; r.lppd_i = q.lppd_i;
-        r.var_i = q.var_i; r.lppdw_i = q.lppdw_i; r.diag = q.diag; r.n_rows = nb;
-        r.row_list = fb_list; r.n_list = fb_count;
-        RowPlan pf = pl;
-        pf.grid = std::min(pl.grid, pl.sms);
-        int rc = launch_rows(mode, pf, r, st);
-        if (rc) return rc;
+        q.cutoffmin = rp.cutoffmin; q.counters = rp.counters; q.hdr = hdr[slot]; q.cx = cx[slot]; q.cs = cs[slot];
+        q.fb_list = fb_list; q.fb_count = fb_count; q.row_base = i0;
+        if (sp.fused && prev_rows > 0) {  // the previous batch's apply stage rides along
+            q.a_in = prev.in; q.a_out = prev.out; q.a_hdr = prev.hdr; q.a_cx = prev.cx; q.a_cs = prev.cs;
+            q.a_rows = prev_rows;
+        }
+        if (nb > 0 || q.a_rows > 0) {
+            const int g1 = (int)std::min<long long>(sp.grid1, std::max<long long>(nb, q.a_rows));
+            CK(split_stream_launch(sp.nt, sp.ept, mode, g1, sp.smem1, st, q));
+        }
+        if (nb > 0) {
+            const int g2 = (int)std::min<long long>(sp.grid2, (nb + TAIL_WARPS - 1) / TAIL_WARPS);
+            CK(split_tail_launch(sp.tl, mode, g2, sp.smem2, st, q));
+            if (mode == MODE_PSISLW && !sp.fused) CK(split_apply_launch((int)std::min<long long>(nb, 8ll * pl.sms), st, q));
+        }
+        prev = q;
+        prev_rows = (mode == MODE_PSISLW && sp.fused) ? nb : 0;
     }
-    return 0;
+    // rows handed over: ONE launch of the general kernel driven by the device-side list (usually empty)
+    RowParams r = rp;
+    r.row_list = fb_list; r.n_list = fb_count;
+    RowPlan pf = pl;
+    pf.grid = std::min(pl.grid, pl.sms);
+    return launch_rows(mode, pf, r, st);
 }
 
 // rows contiguous: split path when the shape and alignment allow it, else the general kernel alone
@@ -473,8 +497,9 @@ extern "C" int b2l_workspace_bytes(int64_t S, int64_t N, int32_t M, int32_t layo
     size_t b = stats_ws_bytes() + grows_ws_bytes(S);
     {
         SplitPlan sp;
-        split_shape(S, M, layout_obs_fastest ? panel_obs(S, N) : N, &sp);
-        b += split_ws_bytes(sp);
+        const long long rows = layout_obs_fastest ? panel_obs(S, N) : N;
+        split_shape(S, M, rows, &sp);
+        b += split_ws_bytes(sp, rows);
     }
     if (layout_obs_fastest) b += 2 * align_up((size_t)panel_obs(S, N) * (size_t)S * 8, 256);
     *out_bytes = b;
@@ -511,7 +536,7 @@ extern "C" int b2l_psislw_dev_f64(const double* lw, int64_t S, int64_t N, int64_
                       (ostride_n % 2 == 0);
         rc = plan_split(S, M, MODE_PSISLW, N, &sp);
         if (rc) return rc;
-        void* sws = (ws && ws_bytes >= sws_off + split_ws_bytes(sp)) ? (char*)ws + sws_off : nullptr;
+        void* sws = (ws && ws_bytes >= sws_off + split_ws_bytes(sp, N)) ? (char*)ws + sws_off : nullptr;
         return process_rows(MODE_PSISLW, pl, sp, rp, sws, st);
     }
     if (!((stride_n == 1 || N == 1) || rows_in) || !((ostride_n == 1 || N == 1) || rows_out))
@@ -521,7 +546,7 @@ extern "C" int b2l_psislw_dev_f64(const double* lw, int64_t S, int64_t N, int64_
     const size_t panel_bytes = align_up((size_t)P * (size_t)S * 8, 256);
     rc = plan_split(S, M, MODE_PSISLW, P, &sp);
     if (rc) return rc;
-    const size_t pan_off = sws_off + split_ws_bytes(sp);
+    const size_t pan_off = sws_off + split_ws_bytes(sp, P);
     if (!ws || ws_bytes < pan_off + 2 * panel_bytes)
         return fail(B2L_E_WORKSPACE, "workspace too small: need %zu bytes", pan_off + 2 * panel_bytes);
     void* sws = (char*)ws + sws_off;
@@ -582,7 +607,7 @@ extern "C" int b2l_loo_dev_f64(const double* ll, int64_t S, int64_t N, int64_t s
         rp.use_bulk = (S % 2 == 0) && aligned16(ll) && (stride_n % 2 == 0);
         rc = plan_split(S, M, MODE_LOO, N, &sp);
         if (rc) return rc;
-        void* sws = (ws && ws_bytes >= sws_off + split_ws_bytes(sp)) ? (char*)ws + sws_off : nullptr;
+        void* sws = (ws && ws_bytes >= sws_off + split_ws_bytes(sp, N)) ? (char*)ws + sws_off : nullptr;
         return process_rows(MODE_LOO, pl, sp, rp, sws, st);
     }
     if (!(stride_n == 1 || N == 1))
@@ -591,7 +616,7 @@ extern "C" int b2l_loo_dev_f64(const double* ll, int64_t S, int64_t N, int64_t s
     const size_t panel_bytes = align_up((size_t)P * (size_t)S * 8, 256);
     rc = plan_split(S, M, MODE_LOO, P, &sp);
     if (rc) return rc;
-    const size_t pan_off = sws_off + split_ws_bytes(sp);
+    const size_t pan_off = sws_off + split_ws_bytes(sp, P);
     if (!ws || ws_bytes < pan_off + panel_bytes)
         return fail(B2L_E_WORKSPACE, "workspace too small: need %zu bytes", pan_off + panel_bytes);
     void* sws = (char*)ws + sws_off;
