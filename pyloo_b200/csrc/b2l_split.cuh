@@ -19,6 +19,8 @@
 // and re-done by the general row kernel (b2l_row_kernel.cuh), which handles every case.
 #pragma once
 
+#include <type_traits>
+
 #include "b2l_row_kernel.cuh"
 
 namespace b2l {
@@ -428,49 +430,56 @@ __global__ void __launch_bounds__(stream_block(NT, MODE), stream_min_blocks<NT>(
             if (MODE == MODE_LOO) asm volatile("" : "+d"(ll_mean_l), "+d"(ll_max_l));
             double bs = 0.0, ls = 0.0, vs = 0.0;
             unsigned cmask = 0;
+            // WIDE (LOO rows whose ll range exceeds 600): exp(ll - ll_min) could overflow, so the lppd
+            // sum takes the literal exp(ll - ll_max) (utils.py:349-351); compiled as its own loop so
+            // the common loop carries no library call
+            auto pass_b = [&](auto wide_tag) {
+                constexpr bool WIDE = decltype(wide_tag)::value;
 #pragma unroll
-            for (int j = 0; j < EP2; ++j) {
-#pragma unroll
-                double2 vv;
-                if (j < nv) {
-                    vv = rowbuf[j * NT + tid];
-                    if (MODE == MODE_LOO) {
-                        vv.x = -vv.x;
-                        vv.y = -vv.y;
-                    }
-                } else {
-                    vv.x = NEG_INF;
-                    vv.y = NEG_INF;
-                }
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const double r = h ? vv.y : vv.x;
-                    const double x = r - mxl;  // psis.py:134
-                    const bool cand = x >= taux;
-                    cmask |= cand ? (1u << (2 * j + h)) : 0u;
-                    // x < -700 (and the -inf padding) runs through the exp as garbage that is never added
-                    if (MODE == MODE_LOO && !wide) {
-                        double ep, em;
-                        exp_tab_pm(x, tb, ep, em);
-                        if (!cand && x >= -700.0) bs += ep;
-                        if (j < nv) {
-                            ls += em;  // exp(ll - ll_min)
-                            const double d = -r - ll_mean_l;
-                            vs = fma(d, d, vs);
+                for (int j = 0; j < EP2; ++j) {
+                    double2 vv;
+                    if (j < nv) {
+                        vv = rowbuf[j * NT + tid];
+                        if (MODE == MODE_LOO) {
+                            vv.x = -vv.x;
+                            vv.y = -vv.y;
                         }
                     } else {
-                        const double e = exp_tab(x, tb);
-                        if (!cand && x >= -700.0) bs += e;
-                        if (MODE == MODE_LOO && j < nv) {
-                            ls += exp(-r - ll_max_l);  // wide rows: literal (utils.py:349-351)
-                            const double d = -r - ll_mean_l;
-                            vs = fma(d, d, vs);
+                        vv.x = NEG_INF;
+                        vv.y = NEG_INF;
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const double r = h ? vv.y : vv.x;
+                        const double x = r - mxl;  // psis.py:134
+                        const bool cand = x >= taux;
+                        cmask |= cand ? (1u << (2 * j + h)) : 0u;
+                        // x < -700 (and the -inf padding) runs through the exp as garbage that is never added
+                        if (MODE == MODE_LOO && !WIDE) {
+                            double ep, em;
+                            exp_tab_pm(x, tb, ep, em);
+                            if (!cand && x >= -700.0) bs += ep;
+                            if (j < nv) {
+                                ls += em;  // exp(ll - ll_min)
+                                const double d = -r - ll_mean_l;
+                                vs = fma(d, d, vs);
+                            }
+                        } else {
+                            const double e = exp_tab(x, tb);
+                            if (!cand && x >= -700.0) bs += e;
+                            if (MODE == MODE_LOO && j < nv) {
+                                ls += exp(-r - ll_max_l);
+                                const double d = -r - ll_mean_l;
+                                vs = fma(d, d, vs);
+                            }
                         }
                     }
+                    // keep the scheduler from interleaving all EPT exp chains at once (register pressure)
+                    asm volatile("" ::: "memory");
                 }
-                // keep the scheduler from interleaving all EPT exp chains at once (register pressure)
-                asm volatile("" ::: "memory");
-            }
+            };
+            if (MODE == MODE_LOO && wide) pass_b(std::true_type{});
+            else pass_b(std::false_type{});
             // -------- emit candidates: one shared atomic per warp, packed keys to global scratch
             {
                 const int mine = __popc(cmask);

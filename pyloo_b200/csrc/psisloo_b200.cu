@@ -466,8 +466,10 @@ constexpr int STATS_BLOCKS = 148;
 // ------------------------------------------------------------------------------------ workspace
 // layout: [stats partials][panel A (obs-fastest input transposed to rows)][panel B (psislw rows out)]
 static long long panel_obs(long long S, long long N) {
-    long long p = (24ll << 20) / std::max<long long>(1, S * 8);  // ~24 MB panels stay L2-resident
-    p = std::max<long long>(p, 1184);                            // >= 2 waves of 148 x 4 CTAs
+    // one panel = one stream -> tail round of the split path (whole waves of both kernels)
+    long long p = 148ll * 48;
+    while (p > 148 * 6 && p * S * 8 > (1ll << 30)) p /= 2;
+    if (const char* ev = getenv("B2L_PANEL")) p = std::max<long long>(32, atoll(ev));
     p = (p + 31) / 32 * 32;
     return std::min(p, (N + 31) / 32 * 32);
 }
