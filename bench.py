@@ -12,7 +12,10 @@ One step = one pass of the hot path over that batch.  Weak scaling: every rank o
 Printed JSON (one line, rank 0):
   value      obs/s with the inputs resident in HBM (CUDA events, max over ranks)
   e2e        obs/s through the host-buffer C-ABI entry (pinned host in/out, H2D + D2H inside the timed region)
-  roofline   algorithmic bytes (16*S + 8 per observation) / kernel time vs the measured HBM copy peak
+  roofline   dominant kernel (psis_stream_kernel): algorithmic bytes (16*S + 8 per observation x the
+             observations its launches process) / its launch time, measured live with CUDA events around
+             every launch on the launching stream (b2l_profile), vs the measured HBM copy peak;
+             `path_frac` is the same bytes over the WHOLE step (all kernels), `kernels` the breakdown
   cpu_baseline  the oracle port (reference algorithm, NumPy, 1 core) on a bounded sample, same box
   loo        the fused loo + waic pass (configs[2] shard: S = 4000, (chain, draw, obs) layout), incl. the
              one NCCL exchange of the 32-double stats record when N > 1
@@ -231,7 +234,7 @@ def main():
     gen.manual_seed(20261018 + rank)
     x = torch.randn(N, S, dtype=torch.float64, device=dev, generator=gen)  # 3.2 GB > L2 (126 MB)
     out = torch.empty_like(x)
-    ws = torch.empty(1 << 20, dtype=torch.uint8, device=dev)
+    ws = engine.workspace_for(S, N, REFF, False, dev)   # sized by the library (b2l_workspace_bytes)
 
     def step():
         return engine.psislw_cuda(x, REFF, out=out, workspace=ws)
@@ -251,14 +254,41 @@ def main():
     clocks = clk.summary()
     assert bool(torch.isfinite(k).all())
 
+    # ---- per-kernel device time: a separate pass with CUDA events around every launch (b2l_profile)
+    prof_steps = 3
+    engine.profile(True)
+    for _ in range(prof_steps):
+        step()
+    torch.cuda.synchronize()
+    prof = engine.profile_read()
+    engine.profile(False)
+    kernel_names = {"stream": "psis_stream_kernel<256,16,PSISLW> (row pass + fused apply of the previous batch)",
+                    "tail": "psis_tail_kernel<8,PSISLW>", "apply": "psis_apply_kernel",
+                    "row": "psis_row_kernel<256,PSISLW> (hand-over rows)", "transpose": "transpose_f64_kernel",
+                    "stats": "stats kernels"}
+    tot_ms = sum(ms for ms, _ in prof.values()) or 1.0
+    kernels = {k: {"name": kernel_names[k], "ms_per_step": ms / prof_steps, "launches_per_step": cnt / prof_steps,
+                   "share": ms / tot_ms}
+               for k, (ms, cnt) in prof.items() if cnt}
+    launches_per_step = sum(v["launches_per_step"] for v in kernels.values())
+    dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+
     peak, peak_src = measured_peak()
     alg_bytes = N * (16 * S + 8)
-    achieved = alg_bytes / (ms_step * 1e-3) / 1e9
-    info = engine.row_launch_info(S, M, "psislw")
+    path_achieved = alg_bytes / (ms_step * 1e-3) / 1e9
+    dom_ms, dom_launches = kernels[dom]["ms_per_step"], kernels[dom]["launches_per_step"]
+    achieved = alg_bytes / (dom_ms * 1e-3) / 1e9   # = bytes per launch / average launch duration
+    try:
+        split = engine.split_launch_info(S, M, "psislw", N)
+    except Exception:
+        split = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": recorded_traffic("psis_row_kernel_psislw_s4000_n100000"),
-                "kernel": "psis_row_kernel<256, PSISLW>", "algorithmic_bytes_per_launch": alg_bytes,
-                "peak_source": peak_src, "launch": info}
+                "traffic": recorded_traffic("psis_stream_kernel_psislw_s4000"),
+                "kernel": kernels[dom]["name"],
+                "algorithmic_bytes_per_launch": alg_bytes / dom_launches,
+                "avg_launch_ms": dom_ms / dom_launches, "launches_per_step": dom_launches,
+                "path_achieved": path_achieved, "path_frac": path_achieved / peak,
+                "kernels": kernels, "peak_source": peak_src, "launch": split}
 
     # ---- fused loo + waic on the configs[2] shard shape: (chain, draw, obs) layout, reff = 1
     loo = None
@@ -272,7 +302,7 @@ def main():
         def loo_step():
             nonlocal wsl
             res = engine.loo_cuda(ll, LOO_REFF, workspace=wsl)
-            wsl = res["workspace"]
+            wsl = res["workspace"]  # first call sizes it (b2l_workspace_bytes), later calls reuse it
             st = engine.stats_cuda(res, gk, workspace=wsl)
             if world > 1:
                 dist.all_gather(gathered, st)   # the single exchange: 32 doubles per rank over NVLink
@@ -331,7 +361,8 @@ def main():
             "config": {"workload": f"pl.psislw S={S} x N={N} per GPU, FP64, r_eff={REFF} (M={M}), rows contiguous "
                                    f"(BASELINE configs[1])", "l2_policy": "inputs (3.2 GB) larger than L2",
                        "parallelism": f"obs-sharded x{world}, no data-path collective"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(round(launches_per_step * args.steps)), "clocks": clocks,
             "loo": loo,
         }
         print(json.dumps(line), flush=True)

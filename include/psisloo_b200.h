@@ -123,6 +123,26 @@ int b2l_loo_host_f64(const double* ll, int64_t S, int64_t N, int64_t stride_s, i
                      double* k_i, double* lppd_i, double* var_i, double* lppdw_i, double* stats_out,
                      int32_t device, int64_t chunk_obs);
 
+/* Per-kernel device timing for benchmarks (no reference counterpart): with b2l_profile(1) every kernel
+ * launch is bracketed by CUDA events on its stream; b2l_profile_read() synchronises them and returns
+ * summed milliseconds and launch counts per kernel kind since the last read.  Not thread safe.    */
+#define B2L_PROF_KINDS 6
+enum {
+    B2L_PROF_STREAM = 0,    /* psis_stream_kernel (row pass; psislw: + fused apply of the previous batch) */
+    B2L_PROF_TAIL = 1,      /* psis_tail_kernel (sort, GPD fit, smoothing, normaliser) */
+    B2L_PROF_APPLY = 2,     /* psis_apply_kernel (only when the fused apply is disabled) */
+    B2L_PROF_ROW = 3,       /* psis_row_kernel: general kernel, whole batch or hand-over rows */
+    B2L_PROF_TRANSPOSE = 4, /* transpose_f64_kernel */
+    B2L_PROF_STATS = 5      /* stats_partial_kernel + stats_final_kernel */
+};
+int b2l_profile(int32_t enable);
+int b2l_profile_read(double* ms_out /* [B2L_PROF_KINDS] */, int64_t* launches_out /* [B2L_PROF_KINDS] */);
+
+/* Launch shape of the split path for (S, M): info[16] = ok, stream threads, draws per thread, tail
+ * registers per lane, candidate capacity, q0, row buffers, fused apply, stream grid, tail grid,
+ * stream CTAs/SM, tail CTAs/SM, stream smem, tail smem, observations per round, stream block size. */
+int b2l_split_launch_info(int64_t S, int32_t M, int32_t mode, int64_t n_rows, int32_t* info);
+
 /* Launch-shape introspection for benchmarks / DESIGN.md (grid, block, smem, occupancy). */
 int b2l_row_launch_info(int64_t S, int32_t M, int32_t mode /*0 psislw, 1 loo*/, int32_t* grid,
                         int32_t* block, int32_t* smem_bytes, int32_t* ctas_per_sm, int32_t* nbuf);

@@ -33,8 +33,10 @@ E_NODEVICE = -4
 EXPORTS = [
     "b2l_version", "b2l_last_error", "b2l_device_count", "b2l_workspace_bytes",
     "b2l_psislw_dev_f64", "b2l_loo_dev_f64", "b2l_stats_dev_f64", "b2l_stats_merge",
-    "b2l_psislw_host_f64", "b2l_loo_host_f64", "b2l_row_launch_info",
+    "b2l_psislw_host_f64", "b2l_loo_host_f64", "b2l_row_launch_info", "b2l_profile", "b2l_profile_read",
+    "b2l_split_launch_info",
 ]
+PROF_KINDS = ("stream", "tail", "apply", "row", "transpose", "stats")
 
 _lock = threading.Lock()
 _lib = None
@@ -110,6 +112,12 @@ def _declare(lib) -> None:
     lib.b2l_psislw_host_f64.argtypes = [vp, i64, i64, i64, i64, i32, f64, vp, i64, i64, vp, i32, i64]
     lib.b2l_loo_host_f64.restype = c.c_int
     lib.b2l_loo_host_f64.argtypes = [vp, i64, i64, i64, i64, i32, f64, u32, f64, vp, vp, vp, vp, vp, vp, i32, i64]
+    lib.b2l_profile.restype = c.c_int
+    lib.b2l_profile.argtypes = [i32]
+    lib.b2l_profile_read.restype = c.c_int
+    lib.b2l_profile_read.argtypes = [vp, vp]
+    lib.b2l_split_launch_info.restype = c.c_int
+    lib.b2l_split_launch_info.argtypes = [i64, i32, i32, i64, vp]
     lib.b2l_row_launch_info.restype = c.c_int
     lib.b2l_row_launch_info.argtypes = [i64, i32, i32] + [c.POINTER(i32)] * 5
 

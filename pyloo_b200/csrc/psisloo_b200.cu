@@ -34,6 +34,32 @@ static int fail(int code, const char* fmt, ...) {
                         __FILE__, __LINE__);                                             \
     } while (0)
 
+// ------------------------------------------------------------------------------------ per-kernel timing
+// Optional (b2l_profile): CUDA events around every kernel launch on the launching stream, summed per
+// kernel kind.  Used by bench.py for the live roofline numbers; off in the timed throughput loop.
+namespace {
+struct ProfRec {
+    cudaEvent_t a, b;
+    int kind;
+};
+bool g_prof = false;
+std::vector<ProfRec> g_prof_recs;
+struct ProfScope {
+    cudaEvent_t a = nullptr, b = nullptr;
+    cudaStream_t st;
+    int kind;
+    ProfScope(int kind_, cudaStream_t st_) : st(st_), kind(kind_) {
+        if (g_prof && cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess) cudaEventRecord(a, st);
+    }
+    ~ProfScope() {
+        if (a && b) {
+            cudaEventRecord(b, st);
+            g_prof_recs.push_back({a, b, kind});
+        }
+    }
+};
+}  // namespace
+
 // ------------------------------------------------------------------------------------ planning
 constexpr int GROWS_MAX_CTAS = 192;  // global-memory row mode: at most this many resident rows
 struct RowPlan {
@@ -153,6 +179,7 @@ static int launch_rows(int mode, const RowPlan& pl, RowParams rp, cudaStream_t s
     }
     int grid = (int)std::max<long long>(1, std::min<long long>(pl.grid, rp.n_rows));
     if (rp.n_rows == 0) return 0;
+    ProfScope prof(B2L_PROF_ROW, st);
     if (mode == MODE_PSISLW) {
         if (pl.nt == 128) psis_row_kernel<128, MODE_PSISLW><<<grid, 128, pl.smem, st>>>(rp);
         else if (pl.nt == 256) psis_row_kernel<256, MODE_PSISLW><<<grid, 256, pl.smem, st>>>(rp);
@@ -296,12 +323,19 @@ static int launch_split(int mode, const RowPlan& pl, const SplitPlan& sp, const 
         }
         if (nb > 0 || q.a_rows > 0) {
             const int g1 = (int)std::min<long long>(sp.grid1, std::max<long long>(nb, q.a_rows));
+            ProfScope prof(B2L_PROF_STREAM, st);
             CK(split_stream_launch(sp.nt, sp.ept, mode, g1, sp.smem1, st, q));
         }
         if (nb > 0) {
             const int g2 = (int)std::min<long long>(sp.grid2, (nb + TAIL_WARPS - 1) / TAIL_WARPS);
-            CK(split_tail_launch(sp.tl, mode, g2, sp.smem2, st, q));
-            if (mode == MODE_PSISLW && !sp.fused) CK(split_apply_launch((int)std::min<long long>(nb, 8ll * pl.sms), st, q));
+            {
+                ProfScope prof(B2L_PROF_TAIL, st);
+                CK(split_tail_launch(sp.tl, mode, g2, sp.smem2, st, q));
+            }
+            if (mode == MODE_PSISLW && !sp.fused) {
+                ProfScope prof(B2L_PROF_APPLY, st);
+                CK(split_apply_launch((int)std::min<long long>(nb, 8ll * pl.sms), st, q));
+            }
         }
         prev = q;
         prev_rows = (mode == MODE_PSISLW && sp.fused) ? nb : 0;
@@ -349,6 +383,7 @@ static int launch_transpose(const double* src, long long src_ld, double* dst, lo
     if (rows == 0 || cols == 0) return 0;
     dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
     if (grid.y > 65535u) return fail(B2L_E_UNSUPPORTED, "transpose: too many rows (%lld)", rows);
+    ProfScope prof(B2L_PROF_TRANSPOSE, st);
     transpose_f64_kernel<<<grid, 256, 0, st>>>(src, src_ld, dst, dst_ld, (int)rows, (int)cols);
     CK(cudaGetLastError());
     return 0;
@@ -647,6 +682,7 @@ extern "C" int b2l_stats_dev_f64(const double* elpd_i, const double* k_i, const 
     if (!ws || ws_bytes < stats_ws_bytes()) return fail(B2L_E_WORKSPACE, "workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     StatAcc* partial = reinterpret_cast<StatAcc*>(ws);
+    ProfScope prof(B2L_PROF_STATS, st);
     stats_partial_kernel<<<STATS_BLOCKS, 256, 0, st>>>(elpd_i, k_i, lppd_i, var_i, lppdw_i, N, good_k, partial);
     CK(cudaGetLastError());
     stats_final_kernel<<<1, 32, 0, st>>>(partial, STATS_BLOCKS, counters, stats_out);
@@ -680,6 +716,47 @@ extern "C" int b2l_stats_merge(const double* shards, int32_t n_shards, double* m
     out[B2L_ST_N] = e.n; out[B2L_ST_ELPD_MEAN] = e.mean; out[B2L_ST_ELPD_M2] = e.m2;
     out[B2L_ST_WAIC_MEAN] = w.mean; out[B2L_ST_WAIC_M2] = w.m2;
     memcpy(merged, out, sizeof(out));
+    return 0;
+}
+
+extern "C" int b2l_profile(int32_t enable) {
+    for (auto& r : g_prof_recs) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    g_prof_recs.clear();
+    g_prof = enable != 0;
+    return 0;
+}
+
+extern "C" int b2l_profile_read(double* ms_out, int64_t* launches_out) {
+    if (!ms_out || !launches_out) return fail(B2L_E_INVALID, "null pointer");
+    for (int k = 0; k < B2L_PROF_KINDS; ++k) {
+        ms_out[k] = 0.0;
+        launches_out[k] = 0;
+    }
+    for (auto& r : g_prof_recs) {
+        CK(cudaEventSynchronize(r.b));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, r.a, r.b));
+        ms_out[r.kind] += ms;
+        launches_out[r.kind] += (r.kind == B2L_PROF_STATS) ? 2 : 1;
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    g_prof_recs.clear();
+    return 0;
+}
+
+extern "C" int b2l_split_launch_info(int64_t S, int32_t M, int32_t mode, int64_t n_rows, int32_t* info) {
+    if (!info) return fail(B2L_E_INVALID, "null pointer");
+    SplitPlan sp;
+    int rc = plan_split(S, M, mode ? MODE_LOO : MODE_PSISLW, n_rows, &sp);
+    if (rc) return rc;
+    info[0] = sp.ok; info[1] = sp.nt; info[2] = sp.ept; info[3] = sp.tl; info[4] = sp.cap; info[5] = sp.q0;
+    info[6] = sp.nbuf; info[7] = sp.fused; info[8] = sp.grid1; info[9] = sp.grid2; info[10] = sp.occ1;
+    info[11] = sp.occ2; info[12] = (int)sp.smem1; info[13] = (int)sp.smem2; info[14] = (int)sp.batch;
+    info[15] = stream_block(sp.nt, mode ? MODE_LOO : MODE_PSISLW);
     return 0;
 }
 
@@ -723,9 +800,9 @@ int slot_reserve(Slot& s, size_t bytes) {
     return 0;
 }
 long long default_chunk(long long S, long long N) {
-    long long c = (128ll << 20) / std::max<long long>(1, S * 8);
-    c = std::max<long long>(c, 1024);
-    c = (c + 31) / 32 * 32;
+    // one chunk = one round of the split path (whole waves of the stream and tail kernels)
+    long long c = 148ll * 48;
+    while (c > 148 * 6 && c * S * 8 > (1ll << 28)) c /= 2;
     return std::min(c, std::max<long long>(N, 1));
 }
 struct Carve {

@@ -17,6 +17,7 @@ from . import _native
 __all__ = [
     "CUTOFFMIN", "tail_length", "good_k_threshold", "psislw_host", "loo_host", "psislw_cuda",
     "loo_cuda", "stats_cuda", "stats_merge", "StatsRecord", "row_launch_info", "current_device",
+    "workspace_for", "profile", "profile_read", "split_launch_info",
 ]
 
 CUTOFFMIN = float(np.log(np.finfo(float).tiny))  # pyloo/psis.py:90
@@ -168,6 +169,35 @@ def _workspace(torch, lib, S, N, M, obs_fastest, device):
     need = ctypes.c_size_t(0)
     _native.check(lib.b2l_workspace_bytes(S, N, M, 1 if obs_fastest else 0, ctypes.byref(need)))
     return torch.empty(max(int(need.value), 256), dtype=torch.uint8, device=device)
+
+
+def workspace_for(S: int, N: int, reff: float, obs_fastest: bool, device):
+    """Device workspace (uint8 tensor) sized by the library for repeated calls on one problem shape."""
+    torch = _torch()
+    return _workspace(torch, _native.load(), S, N, tail_length(S, reff), obs_fastest, device)
+
+
+def profile(enable: bool) -> None:
+    """Per-kernel CUDA-event timing inside the library (benchmarks only; see include/psisloo_b200.h)."""
+    _native.check(_native.load().b2l_profile(1 if enable else 0))
+
+
+def profile_read() -> dict:
+    """{kind: (milliseconds, launches)} accumulated since the last read (synchronises the events)."""
+    ms = np.zeros(len(_native.PROF_KINDS))
+    cnt = np.zeros(len(_native.PROF_KINDS), dtype=np.int64)
+    _native.check(_native.load().b2l_profile_read(ms.ctypes.data, cnt.ctypes.data))
+    return {k: (float(m), int(c)) for k, m, c in zip(_native.PROF_KINDS, ms, cnt)}
+
+
+def split_launch_info(S: int, M: int, mode: str = "psislw", n_rows: int = 1 << 30) -> dict:
+    """Launch shape of the split (stream + tail kernel) path; needs a GPU (occupancy queries)."""
+    info = np.zeros(16, dtype=np.int32)
+    _native.check(_native.load().b2l_split_launch_info(S, M, 0 if mode == "psislw" else 1, n_rows, info.ctypes.data))
+    keys = ("eligible", "stream_threads", "draws_per_thread", "tail_regs_per_lane", "candidate_cap", "q0",
+            "row_buffers", "fused_apply", "stream_grid", "tail_grid", "stream_ctas_per_sm", "tail_ctas_per_sm",
+            "stream_smem_bytes", "tail_smem_bytes", "obs_per_round", "stream_block")
+    return {k: int(v) for k, v in zip(keys, info)}
 
 
 def psislw_cuda(lw, reff: float = 1.0, *, out=None, want_diag: bool = False, workspace=None):
