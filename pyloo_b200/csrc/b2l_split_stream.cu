@@ -11,6 +11,9 @@ static cudaError_t setup1(size_t smem, int* occ) {
     cudaError_t e = cudaFuncSetAttribute(psis_stream_kernel<NT, EPT, MODE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    // same (maximum) shared-memory carve-out for every kernel of the path: no SM reconfiguration between launches
+    e = cudaFuncSetAttribute(psis_stream_kernel<NT, EPT, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, psis_stream_kernel<NT, EPT, MODE>, stream_block(NT, MODE), smem);
 }
 

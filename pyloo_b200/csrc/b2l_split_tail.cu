@@ -8,6 +8,9 @@ static cudaError_t setup1(size_t smem, int* occ) {
     cudaError_t e = cudaFuncSetAttribute(psis_tail_kernel<TL, MODE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    // same (maximum) shared-memory carve-out for every kernel of the path: no SM reconfiguration between launches
+    e = cudaFuncSetAttribute(psis_tail_kernel<TL, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, psis_tail_kernel<TL, MODE>, TAIL_WARPS * 32, smem);
 }
 

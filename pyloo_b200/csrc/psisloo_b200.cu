@@ -78,6 +78,9 @@ static cudaError_t occupancy_of(size_t smem, int* out) {
     cudaError_t e = cudaFuncSetAttribute(psis_row_kernel<NT, MODE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(psis_row_kernel<NT, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             (int)cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, psis_row_kernel<NT, MODE>, NT, smem);
 }
 
