@@ -101,6 +101,30 @@ __device__ __forceinline__ double exp_poly5(double r) {
 __device__ __forceinline__ double scale2(double y, int n) {  // y * 2^n, result normal
     return __hiloint2double(__double2hiint(y) + (n << 20), __double2loint(y));
 }
+// exp(x) for finite x <= 0 with the result forced to (almost) zero when `drop`: the exponent
+// argument is clamped so that any finite x gives a finite, tiny value (no guard needed), and a
+// dropped term keeps only its low word (< 2^-1022): one SEL instead of a predicated FP64 add
+__device__ __forceinline__ double exp_tab_drop(double x, const ExpTab& tb, bool drop) {
+    const double t = fma(x, EXP_L, EXP_MAGIC);
+    const int ni = max(__double2loint(t), -1022 * 32);
+    const double nf = t - EXP_MAGIC;
+    const double r = fma(nf, EXP_C1, x);
+    const double y = tb.t[ni & 31] * exp_poly5(r);
+    const int hi = __double2hiint(y) + ((ni & ~31) << 15);
+    return __hiloint2double(drop ? 0 : hi, __double2loint(y));
+}
+__device__ __forceinline__ void exp_tab_pm_drop(double x, const ExpTab& tb, bool drop_p, bool drop_m, double& ep,
+                                                double& em) {
+    const double t = fma(x, EXP_L, EXP_MAGIC);
+    const int ni = max(__double2loint(t), -1022 * 32);
+    const double nf = t - EXP_MAGIC;
+    const double r = fma(nf, EXP_C1, x);
+    const int j = ni & 31, sh = (ni & ~31) << 15;
+    const double yp = tb.t[j] * exp_poly5(r);
+    const double ym = tb.tinv[j] * exp_poly5(-r);
+    ep = __hiloint2double(drop_p ? 0 : __double2hiint(yp) + sh, __double2loint(yp));
+    em = __hiloint2double(drop_m ? 0 : __double2hiint(ym) - sh, __double2loint(ym));
+}
 // x in [-700, 0]
 __device__ __forceinline__ double exp_tab(double x, const ExpTab& tb) {
     const double t = fma(x, EXP_L, EXP_MAGIC);
@@ -161,12 +185,14 @@ __device__ __forceinline__ float warp_sort32_f(float v, int lane) {  // ascendin
 struct StreamSmem {
     size_t row_bytes, off_apply, off_tab, off_red, off_ctl, off_bar, total;
 };
-__host__ __device__ inline StreamSmem stream_smem(int S, int nbuf, bool apply) {
+// `slots` = NT * EPT: the stream row buffers are padded to one slot per (thread, register) so the passes
+// carry no per-slot bounds logic; the pad is written once per CTA and never touched by the TMA loads
+__host__ __device__ inline StreamSmem stream_smem(int S, int slots, int nbuf, bool apply) {
     StreamSmem L;
-    L.row_bytes = align_up((size_t)S * 8, 128);
+    L.row_bytes = align_up((size_t)(slots > S ? slots : S) * 8, 128);
     size_t o = L.row_bytes * (size_t)nbuf;
     L.off_apply = o;  // one row buffer of the apply warp
-    o += apply ? L.row_bytes : 0;
+    o += apply ? align_up((size_t)S * 8, 128) : 0;
     L.off_tab = o;   // 64 doubles
     o += 64 * 8;
     L.off_red = o;   // 2 x (5 x 32 doubles + 32 floats): sets alternate between consecutive rows
@@ -295,7 +321,7 @@ __global__ void __launch_bounds__(stream_block(NT, MODE), stream_min_blocks<NT>(
     const int S = p.S, M = p.M, cap = p.cap;
     const int S2 = S >> 1;
     const int nbuf = p.nbuf;
-    const StreamSmem L = stream_smem(S, nbuf, stream_has_apply(NT, MODE));
+    const StreamSmem L = stream_smem(S, NT * EPT, nbuf, stream_has_apply(NT, MODE));
     double* tab = reinterpret_cast<double*>(smem_raw + L.off_tab);
     int* ctl_all = reinterpret_cast<int*>(smem_raw + L.off_ctl);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.off_bar);
@@ -316,19 +342,24 @@ __global__ void __launch_bounds__(stream_block(NT, MODE), stream_min_blocks<NT>(
         tab[tid] = exp2((double)tid / 32.0);
         tab[32 + tid] = exp2(-(double)tid / 32.0);
     }
+    // pad of the row buffers (draws S .. NT*EPT-1): r = -inf, i.e. ll = +inf in LOO mode
+    for (int b = 0; b < nbuf; ++b) {
+        double* rb = reinterpret_cast<double*>(smem_raw + (size_t)b * L.row_bytes);
+        for (int i = S + tid; i < NT * EPT; i += blockDim.x) rb[i] = (MODE == MODE_LOO) ? inf_f64() : NEG_INF;
+    }
     __syncthreads();
     if (stream_has_apply(NT, MODE) && tid >= NT) {  // the apply warp goes its own way (no CTA-wide barrier below)
         apply_warp_loop(p, smem_raw + L.off_apply, &bar[2], lane);
         return;
     }
+    // slots j < nfull hold draws for every thread, slot nfull for threads below `rem`, the rest are pads
+    const int nfull = S2 / NT;
+    const bool part_live = tid < S2 - nfull * NT;
     long long row = blockIdx.x;
     if (tid == 0 && row < p.n_rows) {
         mbar_expect_tx(&bar[0], row_tx);
         bulk_g2s(smem_raw, p.in + row * p.in_stride, row_tx, &bar[0]);
     }
-    int nv = 0;  // valid double2 slots of this thread
-#pragma unroll
-    for (int j = 0; j < EP2; ++j) nv += (j * NT + tid < S2) ? 1 : 0;
 
     for (int it = 0; row < p.n_rows; row += gridDim.x, ++it) {
         // reduction slots / candidate counter alternate between consecutive rows, so a warp that
@@ -343,15 +374,10 @@ __global__ void __launch_bounds__(stream_block(NT, MODE), stream_min_blocks<NT>(
         double2 v[EP2];
 #pragma unroll
         for (int j = 0; j < EP2; ++j) {
-            if (j < nv) {
-                v[j] = rowbuf[j * NT + tid];
-                if (MODE == MODE_LOO) {  // r = -ll (pyloo/loo.py:286-288)
-                    v[j].x = -v[j].x;
-                    v[j].y = -v[j].y;
-                }
-            } else {
-                v[j].x = NEG_INF;
-                v[j].y = NEG_INF;
+            v[j] = rowbuf[j * NT + tid];
+            if (MODE == MODE_LOO) {  // r = -ll (pyloo/loo.py:286-288)
+                v[j].x = -v[j].x;
+                v[j].y = -v[j].y;
             }
         }
         // ---------------- pass A: max r (+ min r, sum r in LOO mode), NaN / inf flag
@@ -360,26 +386,20 @@ __global__ void __launch_bounds__(stream_block(NT, MODE), stream_min_blocks<NT>(
 #pragma unroll
         for (int j = 0; j < EP2; ++j) {
             m0 = max_sel(m0, max_sel(v[j].x, v[j].y));  // NaN-free rows only matter; flagged rows leave
-            if (j < nv) {
+            if (j < nfull || (j == nfull && part_live)) {
                 spec = max(spec, max(__double2hiint(v[j].x) & 0x7fffffff, __double2hiint(v[j].y) & 0x7fffffff));
-                if (MODE == MODE_LOO) {
-                    n0 = min_sel(n0, min_sel(v[j].x, v[j].y));
-                    s0 += v[j].x + v[j].y;
-                }
+                n0 = min_sel(n0, min_sel(v[j].x, v[j].y));
+                if (MODE == MODE_LOO) s0 += v[j].x + v[j].y;
             }
         }
         const double tmax = m0;  // this thread's maximum: one "bin" of the threshold estimate
         m0 = warp_max_sel(m0);
-        if (MODE == MODE_LOO) {
-            n0 = -warp_max_sel(-n0);
-            s0 = warp_sum(s0);
-        }
+        n0 = -warp_max_sel(-n0);
+        if (MODE == MODE_LOO) s0 = warp_sum(s0);
         if (lane == 0) {
             red[wid] = m0;
-            if (MODE == MODE_LOO) {
-                red[32 + wid] = -n0;
-                red[64 + wid] = s0;
-            }
+            red[32 + wid] = -n0;
+            if (MODE == MODE_LOO) red[64 + wid] = s0;
         }
         if (tid == 0) ctl[0] = 0;
         // (1) every warp is past the previous row: the other buffer can take the next row now
@@ -391,11 +411,9 @@ __global__ void __launch_bounds__(stream_block(NT, MODE), stream_min_blocks<NT>(
                      &bar[bsel ^ 1]);
         }
         const double mx = slots_max<NW>(red, lane);
-        double r_min = 0.0, r_sum = 0.0;
-        if (MODE == MODE_LOO) {
-            r_min = -slots_max<NW>(red + 32, lane);
-            r_sum = slots_sum<NW>(red + 64, lane);
-        }
+        const double r_min = -slots_max<NW>(red + 32, lane);
+        double r_sum = 0.0;
+        if (MODE == MODE_LOO) r_sum = slots_sum<NW>(red + 64, lane);
         // LOO quantities in ll = -r terms
         const double ll_max = -r_min, ll_min = -mx, ll_mean = -r_sum / (double)S;
         const bool wide = (MODE == MODE_LOO) && !((ll_max - ll_min) <= 600.0);
@@ -404,7 +422,8 @@ __global__ void __launch_bounds__(stream_block(NT, MODE), stream_min_blocks<NT>(
         const float dsorted = warp_sort32_f((float)(mx - tmax), lane);
         int q = p.q0, attempts = 0, C = 0;
         double body = 0.0, lsum = 0.0, vsum = 0.0, taux_used = 0.0;
-        bool ok = !special;
+        // rows spanning more than 1e7 log units would overflow the integer part of the table exp: general kernel
+        bool ok = !special && (mx - r_min) <= 1e7;
         while (ok) {
             if (lane == q - 1) redf[wid] = dsorted;
             bar_sync_n(NT);  // (2)
@@ -437,39 +456,26 @@ __global__ void __launch_bounds__(stream_block(NT, MODE), stream_min_blocks<NT>(
                 constexpr bool WIDE = decltype(wide_tag)::value;
 #pragma unroll
                 for (int j = 0; j < EP2; ++j) {
-                    double2 vv;
-                    if (j < nv) {
-                        vv = rowbuf[j * NT + tid];
-                        if (MODE == MODE_LOO) {
-                            vv.x = -vv.x;
-                            vv.y = -vv.y;
-                        }
-                    } else {
-                        vv.x = NEG_INF;
-                        vv.y = NEG_INF;
-                    }
+                    double2 vv = rowbuf[j * NT + tid];
+                    const bool live = (j < nfull) || (j == nfull && part_live);
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const double r = h ? vv.y : vv.x;
-                        const double x = r - mxl;  // psis.py:134
+                        const double raw = h ? vv.y : vv.x;
+                        const double x = ((MODE == MODE_LOO) ? -raw : raw) - mxl;  // psis.py:134
                         const bool cand = x >= taux;
                         cmask |= cand ? (1u << (2 * j + h)) : 0u;
-                        // x < -700 (and the -inf padding) runs through the exp as garbage that is never added
                         if (MODE == MODE_LOO && !WIDE) {
                             double ep, em;
-                            exp_tab_pm(x, tb, ep, em);
-                            if (!cand && x >= -700.0) bs += ep;
-                            if (j < nv) {
-                                ls += em;  // exp(ll - ll_min)
-                                const double d = -r - ll_mean_l;
-                                vs = fma(d, d, vs);
-                            }
+                            exp_tab_pm_drop(x, tb, cand || !live, !live, ep, em);
+                            bs += ep;
+                            ls += em;  // exp(ll - ll_min)
+                            const double d = live ? raw - ll_mean_l : 0.0;
+                            vs = fma(d, d, vs);
                         } else {
-                            const double e = exp_tab(x, tb);
-                            if (!cand && x >= -700.0) bs += e;
-                            if (MODE == MODE_LOO && j < nv) {
-                                ls += exp(-r - ll_max_l);
-                                const double d = -r - ll_mean_l;
+                            bs += exp_tab_drop(x, tb, cand || !live);
+                            if (MODE == MODE_LOO && live) {
+                                ls += exp(raw - ll_max_l);
+                                const double d = raw - ll_mean_l;
                                 vs = fma(d, d, vs);
                             }
                         }

@@ -238,7 +238,7 @@ static bool split_shape(long long S, int M, long long n_rows, SplitPlan* sp) {
     sp->batch = std::max<long long>(1, std::min<long long>(b, std::max<long long>(n_rows, 1)));
     sp->nbuf = 2;
     if (const char* ev = getenv("B2L_SNBUF")) sp->nbuf = (atoi(ev) == 1) ? 1 : sp->nbuf;
-    sp->smem1 = stream_smem((int)S, 1, false).total;  // refined per mode in plan_split
+    sp->smem1 = stream_smem((int)S, sp->nt * sp->ept, 1, false).total;  // refined per mode in plan_split
     sp->smem2 = tail_smem(M, sp->tl, TAIL_WARPS).total;
     return true;
 }
@@ -256,7 +256,7 @@ static int plan_split(long long S, int M, int mode, long long n_rows, SplitPlan*
         const bool ap = stream_has_apply(nt, mode);
         sp->fused = (ap && !(getenv("B2L_FUSED_APPLY") && atoi(getenv("B2L_FUSED_APPLY")) == 0)) ? 1 : 0;
         int occ1 = 0, occ2 = 0;
-        const size_t sm1 = stream_smem((int)S, 1, ap).total, sm2 = stream_smem((int)S, 2, ap).total;
+        const size_t sm1 = stream_smem((int)S, nt * ept, 1, ap).total, sm2 = stream_smem((int)S, nt * ept, 2, ap).total;
         if (sm1 > (size_t)smem_optin) return 0;
         if (sm2 <= (size_t)smem_optin && sp->nbuf == 2) CK(split_stream_setup(nt, ept, mode, sm2, &occ2));
         CK(split_stream_setup(nt, ept, mode, sm1, &occ1));
