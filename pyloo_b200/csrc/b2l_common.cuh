@@ -110,6 +110,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+// pull a 1-D range into L2 ahead of the bulk load that will need it (no shared-memory destination)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
 // shared -> global, 1-D bulk store (bulk_group completion).
 __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),

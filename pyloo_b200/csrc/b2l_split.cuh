@@ -287,6 +287,8 @@ __device__ __forceinline__ void apply_warp_loop(const SplitParams& p, unsigned c
         }
         mbar_wait(abar, phase);
         phase ^= 1u;
+        // next row of this warp: HBM -> L2 while this one is transformed and stored
+        if (lane == 0 && row + gridDim.x < p.a_rows) bulk_prefetch_l2(p.a_in + (row + gridDim.x) * p.in_stride, row_tx);
 #pragma unroll 4
         for (int i2 = lane; i2 < S2; i2 += 32) {
             double2 a = abuf2[i2];
@@ -410,6 +412,9 @@ __global__ void __launch_bounds__(stream_block(NT, MODE), stream_min_blocks<NT>(
             bulk_g2s(smem_raw + (size_t)(bsel ^ 1) * L.row_bytes, p.in + (row + gridDim.x) * p.in_stride, row_tx,
                      &bar[bsel ^ 1]);
         }
+        // single buffer: the refill has to wait for the end of this row, so at least start the HBM -> L2 leg now
+        if (nbuf == 1 && tid == 0 && row + gridDim.x < p.n_rows)
+            bulk_prefetch_l2(p.in + (row + gridDim.x) * p.in_stride, row_tx);
         const double mx = slots_max<NW>(red, lane);
         const double r_min = -slots_max<NW>(red + 32, lane);
         double r_sum = 0.0;
