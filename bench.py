@@ -57,10 +57,12 @@ def measured_peak():
 
 
 def recorded_traffic(kernel_tag):
-    """dram bytes per launch from the committed ncu capture (profiles/traffic.json), else None."""
+    """dram read + write bytes of one full launch (7104 observations) from the committed ncu --set full
+    capture (profiles/traffic.json), else None."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            return json.load(fh).get(kernel_tag)
+            rec = json.load(fh).get(kernel_tag)
+            return rec if rec is None else rec.get("dram_bytes_per_launch", rec)
     except Exception:
         return None
 
