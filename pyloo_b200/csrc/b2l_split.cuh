@@ -153,9 +153,10 @@ __device__ __forceinline__ void log_tab_init(double* tab, int j) {  // j < 64
     tab[j] = ic;
     tab[64 + j] = -log(ic);
 }
+static __device__ __noinline__ double log_slow(double y) { return log(y); }
 __device__ __forceinline__ double log_tab(double y, const double* tab) {
     const int hi = __double2hiint(y);
-    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return log(y);
+    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return log_slow(y);
     const int e = (hi >> 20) - 1023;
     const int j = (hi >> 14) & 63;
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(y));
@@ -597,8 +598,10 @@ __device__ __forceinline__ void warp_bitonic_sort32(unsigned (&k)[CAPL], int lan
             }
         }
         const bool upl = ((lane & kk) == 0);  // kk < 32: direction depends on the lane
+        int jstart = (kk >> 1) < 16 ? (kk >> 1) : 16;
+        asm volatile("" : "+r"(jstart));  // opaque trip count: the compiler must not unroll this loop (code size)
 #pragma unroll 1
-        for (int j = (kk >> 1) < 16 ? (kk >> 1) : 16; j > 0; j >>= 1) {
+        for (int j = jstart; j > 0; j >>= 1) {
             const bool lower = ((lane & j) == 0);
 #pragma unroll
             for (int i = 0; i < CAPL; ++i) {
@@ -629,7 +632,7 @@ static __device__ __noinline__ double warp_log1p_sum(const double* t, int n, dou
 
 // log prod_i (1 + nb t_i) for two grid points per lane (t broadcast from shared memory)
 __device__ __forceinline__ bool gpd_products2(const double* t, int n, double nb0, double nb1, int every,
-                                              double& out0, double& out1) {
+                                              const double* ltab, double& out0, double& out1) {
     double P0 = 1.0, P1 = 1.0;
     int E0 = 0, E1 = 0;
     bool ok = true;
@@ -654,16 +657,18 @@ __device__ __forceinline__ bool gpd_products2(const double* t, int n, double nb0
         ok = rescale_pos_w(P0, E0) && ok;
         ok = rescale_pos_w(P1, E1) && ok;
     }
-    out0 = log(P0) + (double)E0 * 0.6931471805599453094;
-    out1 = log(P1) + (double)E1 * 0.6931471805599453094;
+    out0 = log_tab(P0, ltab) + (double)E0 * 0.6931471805599453094;  // P in [1, 2): the table log is exact enough
+    out1 = log_tab(P1, ltab) + (double)E1 * 0.6931471805599453094;
     return ok;
 }
 
 // Zhang-Stephens fit for one warp (pyloo/psis.py:181-208).  t: shared memory, DESCENDING (t[0] is
 // the largest), n >= 5, grid size m <= 64 (two grid points per lane).  Returns false when the row
 // must go to the general kernel.
-__device__ __forceinline__ bool gpdfit_warp(const double* t, int n, int m, double tsum, int lane, double& k_out,
-                                            double& sigma_out) {
+__device__ __forceinline__ bool gpdfit_warp(const double* t, int n, int m, double tsum, int lane,
+                                            const ExpTab& tab, double& k_out, double& sigma_out) {
+    const double* ltab = tab.t + 64;
+    const double inv_n = 1.0 / (double)n;
     const double tq = t[n - ((int)((double)n / 4.0 + 0.5))];  // ascending index int(n/4+.5)-1 (psis.py:187)
     const double tn = t[0];
     if (!(tq > 0.0) || !is_finite(tn) || m > 64) return false;
@@ -687,7 +692,7 @@ __device__ __forceinline__ bool gpdfit_warp(const double* t, int n, int m, doubl
     const double fmx = 1.0 + bmag * tn;
     if (!(fmx < 0x1p31)) return false;
     // (2^31)^32 < 2^1023 and (1 - b_max t_n)^32 > 2^-340: rescaling every 32 factors cannot over/underflow
-    const bool ok = gpd_products2(t, n, -b[0], -b[1], 32, ks[0], ks[1]);
+    const bool ok = gpd_products2(t, n, -b[0], -b[1], 32, ltab, ks[0], ks[1]);
     if (!__all_sync(FULL, ok)) return false;
     // grid points where the product form loses relative accuracy: literal log1p sum
 #pragma unroll
@@ -708,8 +713,8 @@ __device__ __forceinline__ bool gpdfit_warp(const double* t, int n, int m, doubl
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
         const bool live = (lane + 32 * r) < m;
-        const double kj = ks[r] / (double)n;
-        Lj[r] = live ? (double)n * (log(-(b[r] / kj)) - kj - 1.0) : -inf_f64();
+        const double kj = ks[r] * inv_n;
+        Lj[r] = live ? (double)n * (log_tab(-(b[r] / kj), ltab) - kj - 1.0) : -inf_f64();
         if (live) {
             fin = fin && is_finite(Lj[r]);
             lm = (Lj[r] > lm) ? Lj[r] : lm;
@@ -720,23 +725,26 @@ __device__ __forceinline__ bool gpdfit_warp(const double* t, int n, int m, doubl
     double w[2], es = 0.0;
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-        w[r] = ((lane + 32 * r) < m) ? exp(Lj[r] - lm) : 0.0;
+        const double dl = Lj[r] - lm;  // <= 0
+        w[r] = ((lane + 32 * r) < m && dl > -700.0) ? exp_tab(dl, tab) : 0.0;
         es += w[r];
     }
     es = warp_sum(es);
     const double thr = 10.0 * 2.220446049250313e-16;
     double ws = 0.0;
 #pragma unroll
+    const double inv_es = 1.0 / es;
     for (int r = 0; r < 2; ++r) {
-        w[r] = w[r] / es;
+        w[r] = w[r] * inv_es;
         if (w[r] < thr) w[r] = 0.0;  // psis.py:194-197 (dead grid points already carry 0)
         ws += w[r];
     }
     ws = warp_sum(ws);
+    const double inv_ws = 1.0 / ws;
     double bp = 0.0;
 #pragma unroll
     for (int r = 0; r < 2; ++r)
-        if (w[r] != 0.0) bp += b[r] * (w[r] / ws);  // psis.py:198-201
+        if (w[r] != 0.0) bp += b[r] * (w[r] * inv_ws);  // psis.py:198-201
     bp = warp_sum(bp);
     // k_post = mean log1p(-b_post t) (psis.py:203): product form unless it loses accuracy
     double lsum;
@@ -753,13 +761,40 @@ __device__ __forceinline__ bool gpdfit_warp(const double* t, int n, int m, doubl
         }
         okp = rescale_pos_w(P, E) && okp;
         if (!__all_sync(FULL, okp)) literal = true;
-        else lsum = log(P) + (double)E * 0.6931471805599453094;
+        else lsum = log_tab(P, ltab) + (double)E * 0.6931471805599453094;
     }
     if (literal) lsum = warp_log1p_sum(t, n, -bp, lane);
-    const double k_post = lsum / (double)n;
+    const double k_post = lsum * inv_n;
     sigma_out = -k_post / bp;                                  // psis.py:205
     k_out = ((double)n * k_post + 5.0) / ((double)n + 10.0);   // psis.py:206
     return true;
+}
+
+// literal _gpinv + log (psis.py:153-157, :211-222) for rows outside the fast path's range of k / sigma:
+// returns this lane's share of sum_i min(q_i + e^c, 1), smoothed values to tb (descending order)
+static __device__ __noinline__ double smooth_tail_literal(double* tb, const double* l1p, int n, int M, double kk,
+                                                          double sigma, double exp_c, int lane) {
+    double tsm = 0.0;
+    for (int e = lane; e < n; e += 32) {
+        const int rk = n - 1 - e;
+        double q;
+        if (sigma <= 0.0) {
+            q = nan_f64();
+        } else {
+            const double l1 = (n == M) ? l1p[rk] : log1p(-(((double)rk + 0.5) / (double)n));
+            q = (fabs(kk) < 2.220446049250313e-16) ? -l1 : expm1(-kk * l1) / kk;
+            q *= sigma;
+        }
+        double y = q + exp_c;
+        double s_ = log(y);
+        if (s_ > 0.0) {  // psis.py:157
+            s_ = 0.0;
+            y = 1.0;
+        }
+        tb[e] = s_;
+        tsm += y;
+    }
+    return tsm;
 }
 
 struct TailSmem {
@@ -854,45 +889,48 @@ __device__ __forceinline__ bool fix_runs(const TailStage& st, int C, double taux
     constexpr int NS = 32 * TL;
     constexpr int PB = (TL == 4) ? 8 : ((TL == 8) ? 9 : 10);
     constexpr int QB = 32 - PB;
-    bool bad = false;
-    double myx[TL];
-    int mys[TL], npos[TL];
-    unsigned moved = 0;
+    // temporaries in the (now free) candidate region: moved values, their draw indices and new positions
+    double* mvx = st.tb;
+    int* mvs = reinterpret_cast<int*>(st.tb + NS);
+    int* mvn = mvs + NS;
+    bool bad = false, any_moved = false;
     const int lim = (C < NS) ? C : NS;
-#pragma unroll
-    for (int i = 0; i < TL; ++i) {
-        const int e = 32 * i + lane;
-        npos[i] = e;
-        if (32 * i < lim) {  // warp-uniform
-            myx[i] = st.xs[e];
-            const unsigned q = quant_key<QB>(myx[i], taux);
-            const bool in_run = (e < lim) && ((e > 0 && quant_key<QB>(st.xs[e - 1], taux) == q) ||
-                                              (e + 1 < lim && quant_key<QB>(st.xs[e + 1], taux) == q));
-            if (__any_sync(FULL, in_run)) {
-                if (in_run) {
-                    int lo = e, hi = e;
-                    while (lo > 0 && e - lo < 33 && quant_key<QB>(st.xs[lo - 1], taux) == q) --lo;
-                    while (hi + 1 < lim && hi - e < 33 && quant_key<QB>(st.xs[hi + 1], taux) == q) ++hi;
-                    if (hi - lo > 32 || (hi == NS - 1 && C > NS)) bad = true;
-                    mys[i] = st.ss[e];
-                    int cnt = 0;
-                    for (int f = lo; f <= hi; ++f) {
-                        const double xf = st.xs[f];
-                        cnt += (xf > myx[i] || (xf == myx[i] && (int)st.ss[f] > mys[i])) ? 1 : 0;
-                    }
-                    npos[i] = lo + cnt;
-                    moved |= 1u << i;
+#pragma unroll 1
+    for (int e0 = 0; e0 < lim; e0 += 32) {
+        const int e = e0 + lane;
+        int npos = -1;
+        if (e < lim) {
+            const double myx = st.xs[e];
+            const unsigned q = quant_key<QB>(myx, taux);
+            const bool in_run = (e > 0 && quant_key<QB>(st.xs[e - 1], taux) == q) ||
+                                (e + 1 < lim && quant_key<QB>(st.xs[e + 1], taux) == q);
+            if (in_run) {
+                int lo = e, hi = e;
+                while (lo > 0 && e - lo < 33 && quant_key<QB>(st.xs[lo - 1], taux) == q) --lo;
+                while (hi + 1 < lim && hi - e < 33 && quant_key<QB>(st.xs[hi + 1], taux) == q) ++hi;
+                if (hi - lo > 32 || (hi == NS - 1 && C > NS)) bad = true;
+                const int mys = st.ss[e];
+                int cnt = 0;
+                for (int f = lo; f <= hi; ++f) {
+                    const double xf = st.xs[f];
+                    cnt += (xf > myx || (xf == myx && (int)st.ss[f] > mys)) ? 1 : 0;
                 }
+                npos = lo + cnt;
+                mvx[e] = myx;
+                mvs[e] = mys;
             }
+            mvn[e] = npos;
         }
+        any_moved = any_moved || (npos >= 0);
     }
     __syncwarp();
-    if (__any_sync(FULL, moved != 0)) {
-#pragma unroll
-        for (int i = 0; i < TL; ++i) {
-            if (moved & (1u << i)) {
-                st.xs[npos[i]] = myx[i];
-                st.ss[npos[i]] = (unsigned short)mys[i];
+    if (__any_sync(FULL, any_moved)) {
+#pragma unroll 1
+        for (int e = lane; e < lim; e += 32) {
+            const int npos = mvn[e];
+            if (npos >= 0) {
+                st.xs[npos] = mvx[e];
+                st.ss[npos] = (unsigned short)mvs[e];
             }
         }
         __syncwarp();
@@ -959,7 +997,7 @@ __device__ __forceinline__ bool tail_row(const SplitParams& p, long long row, co
             while ((m + 1) * (m + 1) <= n) ++m;
             m += 30;
         }
-        if (!gpdfit_warp(tb, n, m, tsum, lane, kk, sigma)) return false;
+        if (!gpdfit_warp(tb, n, m, tsum, lane, tab, kk, sigma)) return false;
         smooth = is_finite(kk);  // psis.py:150
     }
     // smoothed tail (psis.py:153-157, _gpinv :211-222); element e has ascending rank n-1-e.
@@ -987,32 +1025,13 @@ __device__ __forceinline__ bool tail_row(const SplitParams& p, long long row, co
                 tsm += y;
             }
         } else {
-#pragma unroll 1
-            for (int e = lane; e < n; e += 32) {
-                const int rk = n - 1 - e;
-                double q;
-                if (sigma <= 0.0) {
-                    q = nan_f64();
-                } else {
-                    const double l1 = (n == M) ? l1p[rk] : log1p(-(((double)rk + 0.5) / (double)n));
-                    q = (fabs(kk) < 2.220446049250313e-16) ? -l1 : expm1(-kk * l1) / kk;
-                    q *= sigma;
-                }
-                double y = q + exp_c;
-                double s_ = log(y);
-                if (s_ > 0.0) {  // psis.py:157
-                    s_ = 0.0;
-                    y = 1.0;
-                }
-                tb[e] = s_;
-                tsm += y;
-            }
+            tsm = smooth_tail_literal(tb, l1p, n, M, kk, sigma, exp_c, lane);
         }
         tails = warp_sum(tsm);
         __syncwarp();
     }
     const double body = h.body + nont;
-    const double lse = log(body + tails);  // psis.py:158
+    const double lse = log_tab(body + tails, tab.t + 64);  // psis.py:158
 
     if (MODE == MODE_PSISLW) {
         // hand the normaliser and the smoothed tail to the apply kernel (the candidate scratch of this
@@ -1072,7 +1091,10 @@ __global__ void __launch_bounds__(TAIL_WARPS * 32, tail_min_blocks<TL>()) psis_t
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const TailSmem L = tail_smem(p.M, TL, TAIL_WARPS);
     double* l1p = reinterpret_cast<double*>(smem_raw + L.off_l1p);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    // broadcast: lets the compiler see that everything derived from the warp index (row, header, branch
+    // conditions) is warp-uniform, so the shuffles below need no re-convergence code around them
+    const int wid = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0);
     unsigned char* wbase = smem_raw + L.off_w + L.w_stride * wid;
     TailStage st;
     st.xp = reinterpret_cast<double*>(wbase + L.off_a);
