@@ -138,6 +138,12 @@ enum {
 int b2l_profile(int32_t enable);
 int b2l_profile_read(double* ms_out /* [B2L_PROF_KINDS] */, int64_t* launches_out /* [B2L_PROF_KINDS] */);
 
+/* Diagnostics: why observations were handed from the split path to the general kernel on the current
+ * device since the last reset; out16[reason]: 1 NaN/inf row, 2 range > 1e7, 3 threshold retries exhausted,
+ * 4 long run of equal sort keys, 5 order check, 6-9 GPD fit (quantile <= 0, factor overflow, product,
+ * non-finite profile).  Synchronises the device.                                                    */
+int b2l_handover_reasons(uint64_t* out16, int32_t reset);
+
 /* Launch shape of the split path for (S, M): info[16] = ok, stream threads, draws per thread, tail
  * registers per lane, candidate capacity, q0, row buffers, fused apply, stream grid, tail grid,
  * stream CTAs/SM, tail CTAs/SM, stream smem, tail smem, observations per round, stream block size. */

@@ -34,7 +34,7 @@ EXPORTS = [
     "b2l_version", "b2l_last_error", "b2l_device_count", "b2l_workspace_bytes",
     "b2l_psislw_dev_f64", "b2l_loo_dev_f64", "b2l_stats_dev_f64", "b2l_stats_merge",
     "b2l_psislw_host_f64", "b2l_loo_host_f64", "b2l_row_launch_info", "b2l_profile", "b2l_profile_read",
-    "b2l_split_launch_info",
+    "b2l_split_launch_info", "b2l_handover_reasons",
 ]
 PROF_KINDS = ("stream", "tail", "apply", "row", "transpose", "stats")
 
@@ -116,6 +116,8 @@ def _declare(lib) -> None:
     lib.b2l_profile.argtypes = [i32]
     lib.b2l_profile_read.restype = c.c_int
     lib.b2l_profile_read.argtypes = [vp, vp]
+    lib.b2l_handover_reasons.restype = c.c_int
+    lib.b2l_handover_reasons.argtypes = [vp, i32]
     lib.b2l_split_launch_info.restype = c.c_int
     lib.b2l_split_launch_info.argtypes = [i64, i32, i32, i64, vp]
     lib.b2l_row_launch_info.restype = c.c_int

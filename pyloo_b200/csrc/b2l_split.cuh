@@ -25,6 +25,12 @@
 
 namespace b2l {
 
+// why rows leave the split path (debug histogram, read by b2l_handover_reasons): one copy per kernel TU
+enum : int { HO_SPECIAL = 1, HO_RANGE = 2, HO_RETRY = 3, HO_RUNS = 4, HO_ORDER = 5, HO_GPD_TQ = 6, HO_GPD_FMX = 7,
+             HO_GPD_PROD = 8, HO_GPD_PROFILE = 9, HO_REASONS = 16 };
+static __device__ unsigned long long g_handover[HO_REASONS];
+__device__ __forceinline__ void note_handover(int reason) { atomicAdd(&g_handover[reason], 1ull); }
+
 constexpr int KEY_IDX_BITS = 14;               // draw index lives in the low bits of a candidate key
 constexpr int SPLIT_MAX_S = 1 << KEY_IDX_BITS;
 constexpr unsigned KEY_IDX_MASK = (1u << KEY_IDX_BITS) - 1u;
@@ -567,6 +573,7 @@ __global__ void __launch_bounds__(stream_block(NT, MODE), stream_min_blocks<NT>(
             if (!ok) {
                 p.fb_list[atomicAdd(p.fb_count, 1)] = (int)(p.row_base + row);
                 if (p.counters) atomicAdd(&p.counters[3], 1ull);
+                note_handover(special ? HO_SPECIAL : (((mx - r_min) <= 1e7) ? HO_RETRY : HO_RANGE));
             }
         }
     }
@@ -665,13 +672,13 @@ __device__ __forceinline__ bool gpd_products2(const double* t, int n, double nb0
 // Zhang-Stephens fit for one warp (pyloo/psis.py:181-208).  t: shared memory, DESCENDING (t[0] is
 // the largest), n >= 5, grid size m <= 64 (two grid points per lane).  Returns false when the row
 // must go to the general kernel.
-__device__ __forceinline__ bool gpdfit_warp(const double* t, int n, int m, double tsum, int lane,
-                                            const ExpTab& tab, double& k_out, double& sigma_out) {
+__device__ __forceinline__ int gpdfit_warp(const double* t, int n, int m, double tsum, int lane,
+                                           const ExpTab& tab, double& k_out, double& sigma_out) {
     const double* ltab = tab.t + 64;
     const double inv_n = 1.0 / (double)n;
     const double tq = t[n - ((int)((double)n / 4.0 + 0.5))];  // ascending index int(n/4+.5)-1 (psis.py:187)
     const double tn = t[0];
-    if (!(tq > 0.0) || !is_finite(tn) || m > 64) return false;
+    if (!(tq > 0.0) || !is_finite(tn) || m > 64) return HO_GPD_TQ;
     double b[2], ks[2];
     bool flag[2];
     double bmag = 0.0;
@@ -690,10 +697,12 @@ __device__ __forceinline__ bool gpdfit_warp(const double* t, int n, int m, doubl
     }
     bmag = warp_max(bmag);
     const double fmx = 1.0 + bmag * tn;
-    if (!(fmx < 0x1p31)) return false;
-    // (2^31)^32 < 2^1023 and (1 - b_max t_n)^32 > 2^-340: rescaling every 32 factors cannot over/underflow
-    const bool ok = gpd_products2(t, n, -b[0], -b[1], 32, ltab, ks[0], ks[1]);
-    if (!__all_sync(FULL, ok)) return false;
+    if (!(fmx < 0x1p1020)) return HO_GPD_FMX;
+    // factors lie in [(1 - b_max t_n) > 6e-4, fmx]: (2^31)^32 < 2^1023 and (6e-4)^32 > 2^-340, so rescaling
+    // every 32 factors cannot over/underflow; heavy-tailed rows (huge |b| t_n) rescale more often
+    const int every = (fmx < 0x1p31) ? 32 : ((fmx < 0x1p250) ? 4 : 1);
+    const bool ok = gpd_products2(t, n, -b[0], -b[1], every, ltab, ks[0], ks[1]);
+    if (!__all_sync(FULL, ok)) return HO_GPD_PROD;
     // grid points where the product form loses relative accuracy: literal log1p sum
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -720,7 +729,7 @@ __device__ __forceinline__ bool gpdfit_warp(const double* t, int n, int m, doubl
             lm = (Lj[r] > lm) ? Lj[r] : lm;
         }
     }
-    if (!__all_sync(FULL, fin)) return false;
+    if (!__all_sync(FULL, fin)) return HO_GPD_PROFILE;
     lm = warp_max(lm);
     double w[2], es = 0.0;
 #pragma unroll
@@ -752,8 +761,12 @@ __device__ __forceinline__ bool gpdfit_warp(const double* t, int n, int m, doubl
     if (!literal) {
         double P = 1.0;
         int E = 0;
-        for (int i = lane; i < n; i += 32) P *= fma(-bp, t[i], 1.0);  // <= 16 factors < 2^31 each
-        bool okp = rescale_pos_w(P, E);
+        bool okp = true;
+        for (int i = lane; i < n; i += 32) {
+            P *= fma(-bp, t[i], 1.0);
+            if (every < 32) okp = rescale_pos_w(P, E) && okp;  // (else <= 16 factors < 2^31 each)
+        }
+        okp = rescale_pos_w(P, E) && okp;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             P *= __shfl_xor_sync(FULL, P, o);
@@ -767,7 +780,7 @@ __device__ __forceinline__ bool gpdfit_warp(const double* t, int n, int m, doubl
     const double k_post = lsum * inv_n;
     sigma_out = -k_post / bp;                                  // psis.py:205
     k_out = ((double)n * k_post + 5.0) / ((double)n + 10.0);   // psis.py:206
-    return true;
+    return 0;
 }
 
 // literal _gpinv + log (psis.py:153-157, :211-222) for rows outside the fast path's range of k / sigma:
@@ -795,6 +808,19 @@ static __device__ __noinline__ double smooth_tail_literal(double* tb, const doub
         tsm += y;
     }
     return tsm;
+}
+
+// heavy-tailed rows (cutoff clamped at log(DBL_MIN)): t_i and the body terms with the library exp
+static __device__ __noinline__ void tail_t_literal(const double* xs, double* tb, int n, int staged, double exp_c,
+                                                   int lane, double& nont, double& tsum, double& traw) {
+    for (int e = n + lane; e < staged; e += 32) nont += exp(xs[e]);
+    for (int e = lane; e < n; e += 32) {
+        const double ex = exp(xs[e]);
+        const double ti = ex - exp_c;
+        tb[e] = ti;
+        tsum += ti;
+        traw += ex;
+    }
 }
 
 struct TailSmem {
@@ -940,7 +966,7 @@ __device__ __forceinline__ bool fix_runs(const TailStage& st, int C, double taux
 
 // One row for one warp.  Returns false -> general kernel.
 template <int TL, int MODE>
-__device__ __forceinline__ bool tail_row(const SplitParams& p, long long row, const SplitHeader& h,
+__device__ __forceinline__ int tail_row(const SplitParams& p, long long row, const SplitHeader& h,
                                          const double* l1p, const TailStage& st, const ExpTab& tab, int lane) {
     const int S = p.S, M = p.M, C = h.C;
     const double mx = h.mx;
@@ -953,34 +979,47 @@ __device__ __forceinline__ bool tail_row(const SplitParams& p, long long row, co
     double nont;
     if (C <= 32 * TL) nont = sort_and_stage<TL, TL>(cx, cs, C, h.taux, st, tab, lane);
     else nont = sort_and_stage<2 * TL, TL>(cx, cs, C, h.taux, st, tab, lane);
-    if (!fix_runs<TL>(st, C, h.taux, lane)) return false;
+    if (!fix_runs<TL>(st, C, h.taux, lane)) return HO_RUNS;
     // cutoff = (M+1)-th largest = element M of the order (psis.py:135-136); draws equal to it are
     // not in the tail (psis.py:139)
     const double xc = xs[M];
     int n = M;
     while (n > 0 && xs[n - 1] == xc) --n;
-    bool bad = !(xc >= -690.0);  // cutoff near / below log(DBL_MIN) (clamp, psis.py:136): general kernel
+    // heavy-tailed rows: the cutoff sits near / below log(DBL_MIN) and is clamped there (psis.py:136);
+    // the tail is then whatever lies above the clamp, and the table exp (no denormals) is not used
+    const bool deep = !(xc >= -690.0);
+    double c = xc;
+    if (deep) {
+        c = (xc > p.cutoffmin) ? xc : p.cutoffmin;
+        int cnt = 0;
+        for (int e = lane; e < M; e += 32) cnt += (xs[e] > c) ? 1 : 0;
+        n = warp_isum(cnt);  // the order is descending: these are the first n elements
+    }
     // safety net: the order inside the tail must be exact (descending x, descending index on ties)
+    bool bad = false;
     for (int e = lane; e + 1 < n; e += 32) {
         const double a = xs[e], b = xs[e + 1];
         if (!(a > b || (a == b && ss[e] > ss[e + 1]))) bad = true;
     }
-    if (__any_sync(FULL, bad)) return false;
+    if (__any_sync(FULL, bad)) return HO_ORDER;
 
-    const double c = xc;          // >= cutoffmin here
     const double exp_c = exp(c);  // psis.py:138
-    // staged candidates at or below the cutoff belong to the normaliser's body too
-#pragma unroll 1
-    for (int e = n + lane; e < min(C, 32 * TL); e += 32) nont += exp_tab(xs[e], tab);
-    // t_i = exp(x_i) - exp(c) (psis.py:146-147), descending
     double tsum = 0.0, traw = 0.0;
+    if (!deep) {
+        // staged candidates at or below the cutoff belong to the normaliser's body too
 #pragma unroll 1
-    for (int e = lane; e < n; e += 32) {
-        const double ex = exp_tab(xs[e], tab);  // x >= c >= -690
-        const double ti = ex - exp_c;
-        tb[e] = ti;
-        tsum += ti;
-        traw += ex;
+        for (int e = n + lane; e < min(C, 32 * TL); e += 32) nont += exp_tab(xs[e], tab);
+        // t_i = exp(x_i) - exp(c) (psis.py:146-147), descending
+#pragma unroll 1
+        for (int e = lane; e < n; e += 32) {
+            const double ex = exp_tab(xs[e], tab);  // x >= c >= -690
+            const double ti = ex - exp_c;
+            tb[e] = ti;
+            tsum += ti;
+            traw += ex;
+        }
+    } else {
+        tail_t_literal(xs, tb, n, min(C, 32 * TL), exp_c, lane, nont, tsum, traw);
     }
     tsum = warp_sum(tsum);
     traw = warp_sum(traw);
@@ -997,7 +1036,8 @@ __device__ __forceinline__ bool tail_row(const SplitParams& p, long long row, co
             while ((m + 1) * (m + 1) <= n) ++m;
             m += 30;
         }
-        if (!gpdfit_warp(tb, n, m, tsum, lane, tab, kk, sigma)) return false;
+        const int why = gpdfit_warp(tb, n, m, tsum, lane, tab, kk, sigma);
+        if (why) return why;
         smooth = is_finite(kk);  // psis.py:150
     }
     // smoothed tail (psis.py:153-157, _gpinv :211-222); element e has ascending rank n-1-e.
@@ -1080,7 +1120,7 @@ __device__ __forceinline__ bool tail_row(const SplitParams& p, long long row, co
         d[0] = mx; d[1] = c; d[2] = (double)n; d[3] = (double)C;
         d[4] = (double)h.attempts; d[5] = body; d[6] = tails; d[7] = sigma;
     }
-    return true;
+    return 0;
 }
 
 template <int TL>
@@ -1119,8 +1159,9 @@ __global__ void __launch_bounds__(TAIL_WARPS * 32, tail_min_blocks<TL>()) psis_t
     for (long long row = (long long)blockIdx.x * TAIL_WARPS + wid; row < p.n_rows; row += nwarps) {
         const SplitHeader h = p.hdr[row];
         if (h.flags) continue;
-        const bool ok = tail_row<TL, MODE>(p, row, h, l1p, st, tab, lane);
-        if (!ok && lane == 0) {
+        const int why = tail_row<TL, MODE>(p, row, h, l1p, st, tab, lane);
+        if (why && lane == 0) {
+            note_handover(why);
             p.hdr[row].flags = 1;  // the apply kernel skips the row
             p.fb_list[atomicAdd(p.fb_count, 1)] = (int)(p.row_base + row);
             if (p.counters) atomicAdd(&p.counters[3], 1ull);

@@ -40,4 +40,13 @@ cudaError_t split_stream_launch(int nt, int ept, int mode, int grid, size_t smem
     return cudaErrorInvalidValue;
 }
 
+cudaError_t split_stream_reasons(unsigned long long* out, int reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_handover, sizeof(unsigned long long) * HO_REASONS);
+    if (e == cudaSuccess && reset) {
+        unsigned long long z[HO_REASONS] = {0};
+        e = cudaMemcpyToSymbol(g_handover, z, sizeof(z));
+    }
+    return e;
+}
+
 }  // namespace b2l

@@ -42,4 +42,13 @@ cudaError_t split_apply_launch(int grid, cudaStream_t st, const SplitParams& q) 
     return cudaGetLastError();
 }
 
+cudaError_t split_tail_reasons(unsigned long long* out, int reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_handover, sizeof(unsigned long long) * HO_REASONS);
+    if (e == cudaSuccess && reset) {
+        unsigned long long z[HO_REASONS] = {0};
+        e = cudaMemcpyToSymbol(g_handover, z, sizeof(z));
+    }
+    return e;
+}
+
 }  // namespace b2l

@@ -726,6 +726,16 @@ extern "C" int b2l_stats_merge(const double* shards, int32_t n_shards, double* m
     return 0;
 }
 
+extern "C" int b2l_handover_reasons(uint64_t* out16, int32_t reset) {
+    if (!out16) return fail(B2L_E_INVALID, "null pointer");
+    unsigned long long a[HO_REASONS], b[HO_REASONS];
+    CK(cudaDeviceSynchronize());
+    CK(split_stream_reasons(a, reset));
+    CK(split_tail_reasons(b, reset));
+    for (int i = 0; i < HO_REASONS; ++i) out16[i] = a[i] + b[i];
+    return 0;
+}
+
 extern "C" int b2l_profile(int32_t enable) {
     for (auto& r : g_prof_recs) {
         cudaEventDestroy(r.a);

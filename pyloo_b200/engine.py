@@ -17,7 +17,7 @@ from . import _native
 __all__ = [
     "CUTOFFMIN", "tail_length", "good_k_threshold", "psislw_host", "loo_host", "psislw_cuda",
     "loo_cuda", "stats_cuda", "stats_merge", "StatsRecord", "row_launch_info", "current_device",
-    "workspace_for", "profile", "profile_read", "split_launch_info",
+    "workspace_for", "profile", "profile_read", "split_launch_info", "handover_reasons",
 ]
 
 CUTOFFMIN = float(np.log(np.finfo(float).tiny))  # pyloo/psis.py:90
@@ -188,6 +188,15 @@ def profile_read() -> dict:
     cnt = np.zeros(len(_native.PROF_KINDS), dtype=np.int64)
     _native.check(_native.load().b2l_profile_read(ms.ctypes.data, cnt.ctypes.data))
     return {k: (float(m), int(c)) for k, m, c in zip(_native.PROF_KINDS, ms, cnt)}
+
+
+def handover_reasons(reset: bool = True) -> dict:
+    """Diagnostics: observations handed from the split path to the general kernel, by reason."""
+    names = {1: "nan_inf", 2: "range", 3: "threshold_retries", 4: "key_runs", 5: "order_check",
+             6: "gpd_quantile", 7: "gpd_factor_overflow", 8: "gpd_product", 9: "gpd_profile"}
+    out = np.zeros(16, dtype=np.uint64)
+    _native.check(_native.load().b2l_handover_reasons(out.ctypes.data, 1 if reset else 0))
+    return {names[i]: int(out[i]) for i in names if out[i]}
 
 
 def split_launch_info(S: int, M: int, mode: str = "psislw", n_rows: int = 1 << 30) -> dict:

@@ -419,3 +419,20 @@ def test_split_path_is_batch_invariant():
     lw, k = gpu_psislw(x, 1.0)
     lw2, k2 = gpu_psislw(x[4321:4400], 1.0)
     assert np.array_equal(lw[4321:4400], lw2) and np.array_equal(k[4321:4400], k2)
+
+
+def test_heavy_tailed_rows_stay_on_the_split_path():
+    """BASELINE configs[4] shape: Student-t(1.5) log-ratios, S = 8000.  Almost every row has its cutoff
+    clamped at log(DBL_MIN) (psis.py:136) and k > 0.7; the split path must handle them itself (hand-overs to
+    the general kernel are counted) and agree with the oracle."""
+    rng = np.random.default_rng(56)
+    x = rng.standard_t(1.5, size=(256, 8000))
+    r = gpu_loo(np.ascontiguousarray(-x.T), 1.0)
+    with np.errstate(all="ignore"):
+        pw = orc.loo_pointwise(-x.T, 1.0)
+    close(r["pareto_k"], pw["pareto_k"], atol=1e-13)
+    same_special(r["pareto_k"], pw["pareto_k"])
+    close(r["elpd_i"], pw["elpd_i"])
+    close(r["lppd_i"], pw["lppd_i"])
+    assert (pw["pareto_k"] > 0.7).mean() > 0.9
+    assert int(r["counters"][3]) <= 26          # <= 10 % of the rows handed over
