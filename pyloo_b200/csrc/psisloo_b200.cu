@@ -802,10 +802,23 @@ struct Slot {
 struct DevCtx {
     Slot slot[NSLOT];
     bool init = false;
+    // pinned staging for the small per-observation outputs: an async copy into the caller's (usually
+    // pageable) vectors would block the host until the whole chunk is done and serialise the pipeline
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
 };
 std::mutex g_ctx_mu;
 DevCtx g_ctx[64];
 
+int pinned_reserve(DevCtx& cx, size_t bytes) {
+    if (cx.pinned_bytes < bytes) {
+        if (cx.pinned) CK(cudaFreeHost(cx.pinned));
+        cx.pinned = nullptr; cx.pinned_bytes = 0;
+        CK(cudaHostAlloc(&cx.pinned, bytes, cudaHostAllocDefault));
+        cx.pinned_bytes = bytes;
+    }
+    return 0;
+}
 int slot_reserve(Slot& s, size_t bytes) {
     if (!s.st) CK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
     if (s.bytes < bytes) {
@@ -855,6 +868,11 @@ extern "C" int b2l_psislw_host_f64(const double* lw, int64_t S, int64_t N, int64
         int rc = slot_reserve(cx.slot[s], need);
         if (rc) return rc;
     }
+    {
+        int rc = pinned_reserve(cx, (size_t)N * 8);
+        if (rc) return rc;
+    }
+    double* pk = reinterpret_cast<double*>(cx.pinned);
     int ci = 0;
     for (long long i0 = 0; i0 < N; i0 += chunk, ++ci) {
         const long long nc = std::min<long long>(chunk, N - i0);
@@ -866,8 +884,11 @@ extern "C" int b2l_psislw_host_f64(const double* lw, int64_t S, int64_t N, int64
         void* d_ws = cv.take<char>(wsb);
         long long dss, dsn, oss, osn;
         if (rows_in) {  // rows [i0, i0+nc) -> dense nc x S
-            CK(cudaMemcpy2DAsync(d_in, (size_t)S * 8, lw + i0 * stride_n, (size_t)stride_n * 8,
-                                 (size_t)S * 8, (size_t)nc, cudaMemcpyHostToDevice, sl.st));
+            if (stride_n == S)  // dense on the host too: one linear DMA instead of one descriptor per row
+                CK(cudaMemcpyAsync(d_in, lw + i0 * stride_n, (size_t)nc * S * 8, cudaMemcpyHostToDevice, sl.st));
+            else
+                CK(cudaMemcpy2DAsync(d_in, (size_t)S * 8, lw + i0 * stride_n, (size_t)stride_n * 8,
+                                     (size_t)S * 8, (size_t)nc, cudaMemcpyHostToDevice, sl.st));
             dss = 1; dsn = S;
         } else {        // columns [i0, i0+nc) of the S x N matrix -> dense S x nc
             CK(cudaMemcpy2DAsync(d_in, (size_t)nc * 8, lw + i0, (size_t)stride_s * 8, (size_t)nc * 8,
@@ -878,15 +899,18 @@ extern "C" int b2l_psislw_host_f64(const double* lw, int64_t S, int64_t N, int64
         int rc = b2l_psislw_dev_f64(d_in, S, nc, dss, dsn, M, cutoffmin, d_out, oss, osn, d_k, nullptr,
                                     d_ws, wsb, sl.st);
         if (rc) return rc;
-        if (rows_out)
+        if (rows_out && ostride_n == S)
+            CK(cudaMemcpyAsync(lw_out + i0 * ostride_n, d_out, (size_t)nc * S * 8, cudaMemcpyDeviceToHost, sl.st));
+        else if (rows_out)
             CK(cudaMemcpy2DAsync(lw_out + i0 * ostride_n, (size_t)ostride_n * 8, d_out, (size_t)S * 8,
                                  (size_t)S * 8, (size_t)nc, cudaMemcpyDeviceToHost, sl.st));
         else
             CK(cudaMemcpy2DAsync(lw_out + i0, (size_t)ostride_s * 8, d_out, (size_t)nc * 8,
                                  (size_t)nc * 8, (size_t)S, cudaMemcpyDeviceToHost, sl.st));
-        CK(cudaMemcpyAsync(k_out + i0, d_k, (size_t)nc * 8, cudaMemcpyDeviceToHost, sl.st));
+        CK(cudaMemcpyAsync(pk + i0, d_k, (size_t)nc * 8, cudaMemcpyDeviceToHost, sl.st));
     }
     for (int s = 0; s < NSLOT; ++s) CK(cudaStreamSynchronize(cx.slot[s].st));
+    memcpy(k_out, pk, (size_t)N * 8);
     return 0;
 }
 
@@ -915,6 +939,12 @@ extern "C" int b2l_loo_host_f64(const double* ll, int64_t S, int64_t N, int64_t 
     }
     const long long nchunks = N > 0 ? (N + chunk - 1) / chunk : 0;
     std::vector<double> recs((size_t)std::max<long long>(nchunks, 1) * B2L_STATS_LEN, 0.0);
+    {
+        int rc = pinned_reserve(cx, (size_t)(5 * std::max<long long>(N, 1) + std::max<long long>(nchunks, 1) * B2L_STATS_LEN) * 8);
+        if (rc) return rc;
+    }
+    double* pv = reinterpret_cast<double*>(cx.pinned);                 // [5][N]
+    double* prec = pv + 5 * std::max<long long>(N, 1);                 // [nchunks][B2L_STATS_LEN]
     int ci = 0;
     for (long long i0 = 0; i0 < N; i0 += chunk, ++ci) {
         const long long nc = std::min<long long>(chunk, N - i0);
@@ -945,15 +975,23 @@ extern "C" int b2l_loo_host_f64(const double* ll, int64_t S, int64_t N, int64_t 
         if (rc) return rc;
         rc = b2l_stats_dev_f64(d_e, d_k, d_l, d_v, d_lw, nc, good_k, d_cnt, d_stats, d_ws, wsb, sl.st);
         if (rc) return rc;
-        CK(cudaMemcpyAsync(elpd_i + i0, d_e, (size_t)nc * 8, cudaMemcpyDeviceToHost, sl.st));
-        CK(cudaMemcpyAsync(k_i + i0, d_k, (size_t)nc * 8, cudaMemcpyDeviceToHost, sl.st));
-        CK(cudaMemcpyAsync(lppd_i + i0, d_l, (size_t)nc * 8, cudaMemcpyDeviceToHost, sl.st));
-        CK(cudaMemcpyAsync(var_i + i0, d_v, (size_t)nc * 8, cudaMemcpyDeviceToHost, sl.st));
-        CK(cudaMemcpyAsync(lppdw_i + i0, d_lw, (size_t)nc * 8, cudaMemcpyDeviceToHost, sl.st));
-        CK(cudaMemcpyAsync(recs.data() + (size_t)ci * B2L_STATS_LEN, d_stats, B2L_STATS_LEN * 8,
-                           cudaMemcpyDeviceToHost, sl.st));
+        CK(cudaMemcpyAsync(pv + 0 * N + i0, d_e, (size_t)nc * 8, cudaMemcpyDeviceToHost, sl.st));
+        CK(cudaMemcpyAsync(pv + 1 * N + i0, d_k, (size_t)nc * 8, cudaMemcpyDeviceToHost, sl.st));
+        CK(cudaMemcpyAsync(pv + 2 * N + i0, d_l, (size_t)nc * 8, cudaMemcpyDeviceToHost, sl.st));
+        CK(cudaMemcpyAsync(pv + 3 * N + i0, d_v, (size_t)nc * 8, cudaMemcpyDeviceToHost, sl.st));
+        CK(cudaMemcpyAsync(pv + 4 * N + i0, d_lw, (size_t)nc * 8, cudaMemcpyDeviceToHost, sl.st));
+        CK(cudaMemcpyAsync(prec + (size_t)ci * B2L_STATS_LEN, d_stats, B2L_STATS_LEN * 8, cudaMemcpyDeviceToHost,
+                           sl.st));
     }
     for (int s = 0; s < NSLOT; ++s) CK(cudaStreamSynchronize(cx.slot[s].st));
+    if (N > 0) {
+        memcpy(elpd_i, pv + 0 * N, (size_t)N * 8);
+        memcpy(k_i, pv + 1 * N, (size_t)N * 8);
+        memcpy(lppd_i, pv + 2 * N, (size_t)N * 8);
+        memcpy(var_i, pv + 3 * N, (size_t)N * 8);
+        memcpy(lppdw_i, pv + 4 * N, (size_t)N * 8);
+        memcpy(recs.data(), prec, (size_t)nchunks * B2L_STATS_LEN * 8);
+    }
     if (stats_out) {
         if (nchunks == 0) {
             double z[B2L_STATS_LEN] = {0};
