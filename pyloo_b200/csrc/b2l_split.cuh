@@ -81,6 +81,7 @@ struct SplitParams {
     const double* a_cx;
     const unsigned short* a_cs;
     long long a_rows;
+    int a_chunk;               // draws per apply transfer (S, or a fraction of it when shared memory is short)
 };
 
 // ------------------------------------------------------------------ table-driven exp for the sums
@@ -194,12 +195,12 @@ struct StreamSmem {
 };
 // `slots` = NT * EPT: the stream row buffers are padded to one slot per (thread, register) so the passes
 // carry no per-slot bounds logic; the pad is written once per CTA and never touched by the TMA loads
-__host__ __device__ inline StreamSmem stream_smem(int S, int slots, int nbuf, bool apply) {
+__host__ __device__ inline StreamSmem stream_smem(int S, int slots, int nbuf, int apply_chunk) {
     StreamSmem L;
     L.row_bytes = align_up((size_t)(slots > S ? slots : S) * 8, 128);
     size_t o = L.row_bytes * (size_t)nbuf;
     L.off_apply = o;  // one row buffer of the apply warp
-    o += apply ? align_up((size_t)S * 8, 128) : 0;
+    o += align_up((size_t)apply_chunk * 8, 128);  // apply_chunk = 0: no apply warp
     L.off_tab = o;   // 64 doubles
     o += 64 * 8;
     L.off_red = o;   // 2 x (5 x 32 doubles + 32 floats): sets alternate between consecutive rows
@@ -269,15 +270,77 @@ __host__ __device__ constexpr bool stream_has_apply(int nt, int mode) { return m
 __host__ __device__ constexpr int stream_block(int nt, int mode) { return nt + (stream_has_apply(nt, mode) ? 32 : 0); }
 template <int NT>
 constexpr int stream_min_blocks() {
-    return NT == 128 ? 2 * B2L_STREAM_OCC : (NT == 256 ? B2L_STREAM_OCC : (NT == 512 ? B2L_STREAM_OCC / 2 : 1));
+    return NT == 128 ? 2 * B2L_STREAM_OCC : (NT == 256 ? B2L_STREAM_OCC : (NT == 512 ? (B2L_STREAM_OCC + 1) / 2 : 1));
 }
 
 // ------------------------------------------------------------------ stream kernel
 // The apply warp (psislw only, threads NT .. NT + 31): out = (r - max r) - lse (psis.py:134,158)
 // plus the smoothed tail (psis.py:156) for the rows of the previous batch, one row at a time through
 // its own shared-memory buffer: bulk TMA load, in-place transform, patches, bulk TMA store.
+__device__ __forceinline__ void apply_warp_loop_chunked(const SplitParams& p, unsigned char* abuf_raw, uint64_t* abar,
+                                                int lane) {
+    const int S = p.S, chunk = p.a_chunk;
+    double* abuf = reinterpret_cast<double*>(abuf_raw);
+    double2* abuf2 = reinterpret_cast<double2*>(abuf_raw);
+    uint32_t phase = 0;
+    for (long long row = blockIdx.x; row < p.a_rows; row += gridDim.x) {
+        const SplitHeader* h = p.a_hdr + row;
+        if (h->flags) continue;  // handed to the general kernel (warp-uniform)
+        const double mx = h->mx, lse = h->lse;
+        const int np = h->n_patch;
+        // the row in pieces of `chunk` draws (one piece unless shared memory is short)
+        for (int off = 0; off < S; off += chunk) {
+            const int len = min(chunk, S - off);  // even
+            const uint32_t bytes = (uint32_t)len * 8u;
+            if (lane == 0) {
+                mbar_expect_tx(abar, bytes);
+                bulk_g2s(abuf_raw, p.a_in + row * p.in_stride + off, bytes, abar);
+            }
+            mbar_wait(abar, phase);
+            phase ^= 1u;
+            // what this warp loads next: HBM -> L2 while this piece is transformed and stored
+            if (lane == 0) {
+                if (off + chunk < S)
+                    bulk_prefetch_l2(p.a_in + row * p.in_stride + off + chunk, (uint32_t)min(chunk, S - off - chunk) * 8u);
+                else if (row + gridDim.x < p.a_rows)
+                    bulk_prefetch_l2(p.a_in + (row + gridDim.x) * p.in_stride, (uint32_t)min(chunk, S) * 8u);
+            }
+#pragma unroll 4
+            for (int i2 = lane; i2 < (len >> 1); i2 += 32) {
+                double2 a = abuf2[i2];
+                a.x = (a.x - mx) - lse;
+                a.y = (a.y - mx) - lse;
+                abuf2[i2] = a;
+            }
+            __syncwarp();
+            if (np > 0) {  // smoothed draws land on top of the streamed values
+                const double* pv = p.a_cx + (size_t)row * (size_t)p.cap;
+                const unsigned short* ps = p.a_cs + (size_t)row * (size_t)p.cap;
+                for (int e = lane; e < np; e += 32) {
+                    const int s = (int)ps[e] - off;
+                    if (s >= 0 && s < len) abuf[s] = pv[e];
+                }
+                __syncwarp();
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                bulk_s2g(p.a_out + row * p.out_stride + off, abuf_raw, bytes);
+                bulk_commit();
+                bulk_wait_read0();  // the buffer may be refilled once the store has read it
+            }
+            __syncwarp();
+        }
+    }
+    if (lane == 0) bulk_wait0();
+}
+
 __device__ __forceinline__ void apply_warp_loop(const SplitParams& p, unsigned char* abuf_raw, uint64_t* abar,
                                                 int lane) {
+    if (p.a_chunk < p.S) {  // shared memory too short for a whole row: piecewise variant
+        apply_warp_loop_chunked(p, abuf_raw, abar, lane);
+        return;
+    }
     const int S2 = p.S >> 1;
     const uint32_t row_tx = (uint32_t)p.S * 8u;
     double* abuf = reinterpret_cast<double*>(abuf_raw);
@@ -330,7 +393,7 @@ __global__ void __launch_bounds__(stream_block(NT, MODE), stream_min_blocks<NT>(
     const int S = p.S, M = p.M, cap = p.cap;
     const int S2 = S >> 1;
     const int nbuf = p.nbuf;
-    const StreamSmem L = stream_smem(S, NT * EPT, nbuf, stream_has_apply(NT, MODE));
+    const StreamSmem L = stream_smem(S, NT * EPT, nbuf, stream_has_apply(NT, MODE) ? p.a_chunk : 0);
     double* tab = reinterpret_cast<double*>(smem_raw + L.off_tab);
     int* ctl_all = reinterpret_cast<int*>(smem_raw + L.off_ctl);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.off_bar);

@@ -201,7 +201,7 @@ static int launch_rows(int mode, const RowPlan& pl, RowParams rp, cudaStream_t s
 // stream kernel (one CTA per observation, row in registers) + tail kernel (one warp per observation)
 // + the general row kernel on the rows those two hand over.  See b2l_split.cuh.
 struct SplitPlan {
-    int ok, nt, ept, tl, cap, q0, nbuf, fused, grid1, grid2, occ1, occ2;
+    int ok, nt, ept, tl, cap, q0, nbuf, fused, a_chunk, grid1, grid2, occ1, occ2;
     size_t smem1, smem2;
     long long batch;  // observations per stream -> tail -> fallback round
 };
@@ -242,7 +242,7 @@ static bool split_shape(long long S, int M, long long n_rows, SplitPlan* sp) {
     sp->batch = std::max<long long>(1, std::min<long long>(b, std::max<long long>(n_rows, 1)));
     sp->nbuf = 2;
     if (const char* ev = getenv("B2L_SNBUF")) sp->nbuf = (atoi(ev) == 1) ? 1 : sp->nbuf;
-    sp->smem1 = stream_smem((int)S, sp->nt * sp->ept, 1, false).total;  // refined per mode in plan_split
+    sp->smem1 = stream_smem((int)S, sp->nt * sp->ept, 1, 0).total;  // refined per mode in plan_split
     sp->smem2 = tail_smem(M, sp->tl, TAIL_WARPS).total;
     return true;
 }
@@ -255,17 +255,29 @@ static int plan_split(long long S, int M, int mode, long long n_rows, SplitPlan*
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     CK(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     if (sp->smem2 > (size_t)smem_optin) return 0;
-    // one or two row buffers: two (prefetch during the whole row) unless that costs resident CTAs
+    // shared-memory shape of the stream kernel: most resident CTAs first, then whole-row apply transfers,
+    // then two row buffers (prefetch during the whole row)
     {
         const bool ap = stream_has_apply(nt, mode);
         sp->fused = (ap && !(getenv("B2L_FUSED_APPLY") && atoi(getenv("B2L_FUSED_APPLY")) == 0)) ? 1 : 0;
-        int occ1 = 0, occ2 = 0;
-        const size_t sm1 = stream_smem((int)S, nt * ept, 1, ap).total, sm2 = stream_smem((int)S, nt * ept, 2, ap).total;
-        if (sm1 > (size_t)smem_optin) return 0;
-        if (sm2 <= (size_t)smem_optin && sp->nbuf == 2) CK(split_stream_setup(nt, ept, mode, sm2, &occ2));
-        CK(split_stream_setup(nt, ept, mode, sm1, &occ1));
-        if (occ2 >= occ1 && occ2 > 0) { sp->nbuf = 2; sp->smem1 = sm2; sp->occ1 = occ2; CK(split_stream_setup(nt, ept, mode, sm2, &occ2)); }
-        else { sp->nbuf = 1; sp->smem1 = sm1; sp->occ1 = occ1; }
+        const int max_nbuf = sp->nbuf;
+        int best_occ = 0;
+        for (int pieces : {1, 2, 4}) {
+            if (!ap && pieces > 1) break;
+            const int chunk = ap ? (int)(((S / pieces) + 1) / 2 * 2) : 0;  // even number of draws
+            for (int nb = max_nbuf; nb >= 1; --nb) {
+                const size_t sm = stream_smem((int)S, nt * ept, nb, chunk).total;
+                if (sm > (size_t)smem_optin) continue;
+                int occ = 0;
+                CK(split_stream_setup(nt, ept, mode, sm, &occ));
+                if (occ > best_occ) {
+                    best_occ = occ; sp->nbuf = nb; sp->a_chunk = chunk; sp->smem1 = sm; sp->occ1 = occ;
+                }
+            }
+        }
+        if (best_occ < 1) return 0;
+        int occ = 0;
+        CK(split_stream_setup(nt, ept, mode, sp->smem1, &occ));  // leave the chosen size as the function attribute
     }
     CK(split_tail_setup(sp->tl, mode, sp->smem2, &sp->occ2));
     if (sp->occ1 < 1 || sp->occ2 < 1) return 0;
@@ -323,7 +335,7 @@ static int launch_split(int mode, const RowPlan& pl, const SplitPlan& sp, const 
         q.diag = rp.diag ? rp.diag + i0 * DIAG_STRIDE : nullptr;
         q.n_rows = nb; q.S = rp.S; q.M = rp.M; q.cap = sp.cap; q.nbuf = sp.nbuf; q.q0 = sp.q0; q.m_full = 30 + msq;
         q.cutoffmin = rp.cutoffmin; q.counters = rp.counters; q.hdr = hdr[slot]; q.cx = cx[slot]; q.cs = cs[slot];
-        q.fb_list = fb_list; q.fb_count = fb_count; q.row_base = i0;
+        q.fb_list = fb_list; q.fb_count = fb_count; q.row_base = i0; q.a_chunk = sp.a_chunk;
         if (sp.fused && prev_rows > 0) {  // the previous batch's apply stage rides along
             q.a_in = prev.in; q.a_out = prev.out; q.a_hdr = prev.hdr; q.a_cx = prev.cx; q.a_cs = prev.cs;
             q.a_rows = prev_rows;
@@ -774,6 +786,7 @@ extern "C" int b2l_split_launch_info(int64_t S, int32_t M, int32_t mode, int64_t
     info[6] = sp.nbuf; info[7] = sp.fused; info[8] = sp.grid1; info[9] = sp.grid2; info[10] = sp.occ1;
     info[11] = sp.occ2; info[12] = (int)sp.smem1; info[13] = (int)sp.smem2; info[14] = (int)sp.batch;
     info[15] = stream_block(sp.nt, mode ? MODE_LOO : MODE_PSISLW);
+    info[7] = sp.fused ? (int)((S + sp.a_chunk - 1) / std::max(sp.a_chunk, 1)) : 0;  // apply transfers per row
     return 0;
 }
 
