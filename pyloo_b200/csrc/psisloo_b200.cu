@@ -323,8 +323,11 @@ static int launch_split(int mode, const RowPlan& pl, const SplitPlan& sp, const 
     memset(&prev, 0, sizeof(prev));
     long long prev_rows = 0;
     int slot = 0;
-    for (long long i0 = 0; i0 < rp.n_rows || prev_rows > 0; i0 += sp.batch, slot ^= 1) {
-        const long long nb = std::max<long long>(0, std::min<long long>(sp.batch, rp.n_rows - i0));
+    // equal rounds (no short last round whose stream kernel would be nothing but the previous apply stage)
+    const long long n_rounds = std::max<long long>(1, (rp.n_rows + sp.batch - 1) / sp.batch);
+    const long long per_round = std::min<long long>(sp.batch, ((rp.n_rows + n_rounds - 1) / n_rounds + 7) / 8 * 8);
+    for (long long i0 = 0; i0 < rp.n_rows || prev_rows > 0; i0 += per_round, slot ^= 1) {
+        const long long nb = std::max<long long>(0, std::min<long long>(per_round, rp.n_rows - i0));
         SplitParams q;
         memset(&q, 0, sizeof(q));
         q.in = rp.in + i0 * rp.in_stride; q.in_stride = rp.in_stride;
@@ -340,7 +343,11 @@ static int launch_split(int mode, const RowPlan& pl, const SplitPlan& sp, const 
             q.a_in = prev.in; q.a_out = prev.out; q.a_hdr = prev.hdr; q.a_cx = prev.cx; q.a_cs = prev.cs;
             q.a_rows = prev_rows;
         }
-        if (nb > 0 || q.a_rows > 0) {
+        if (nb == 0 && q.a_rows > 0) {
+            // after the last round: its apply stage alone, on the dedicated streaming kernel (all warps copy)
+            ProfScope prof(B2L_PROF_APPLY, st);
+            CK(split_apply_launch((int)std::min<long long>(prev_rows, 8ll * pl.sms), st, prev));
+        } else if (nb > 0) {
             const int g1 = (int)std::min<long long>(sp.grid1, std::max<long long>(nb, q.a_rows));
             ProfScope prof(B2L_PROF_STREAM, st);
             CK(split_stream_launch(sp.nt, sp.ept, mode, g1, sp.smem1, st, q));
