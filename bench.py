@@ -68,7 +68,7 @@ def recorded_traffic(kernel_tag):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 20 ms during the timed region."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -81,7 +81,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200",
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -251,11 +251,22 @@ def main():
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
+        # nvidia-smi needs ~0.3 s to start: keep the same step running (untimed) around the timed region so that
+        # every clock / throttle sample is taken under this load
+        t_pre = time.perf_counter()
+        while time.perf_counter() - t_pre < 0.6:
+            step()
+            torch.cuda.synchronize()
+        barrier()
         ev0.record()
         for _ in range(args.steps):
             _, k = step()
         ev1.record()
         barrier()
+        t_post = time.perf_counter()
+        while time.perf_counter() - t_post < 0.3:
+            step()
+            torch.cuda.synchronize()
     ms_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
     value = world * N / (ms_step * 1e-3)
     clocks = clk.summary()
