@@ -887,11 +887,11 @@ static __device__ __noinline__ void tail_t_literal(const double* xs, double* tb,
 }
 
 struct TailSmem {
-    size_t off_l1p, off_tab, off_w, w_stride, off_a, off_x, off_s, off_p, total;
+    size_t off_l1p, off_tab, off_w, w_stride, off_x, off_t, off_s, total;
 };
-// per CTA: l1p table, exp table.  Per warp: region A = xp[64 TL] candidate x by slot, later tb[32 TL]
-// (t_i, then smoothed values); xs[32 TL] exact x of the head of the order; ss[32 TL] their draw
-// indices; sp[64 TL] draw index by candidate slot.
+// per CTA: l1p table, exp / log tables.  Per warp (18 B per staged element, 4.5 KB at TL = 8, so that
+// shared memory does not cap the resident warps): xs[32 TL] exact x of the head of the order,
+// tb[32 TL] t_i, then the smoothed values; ss[32 TL] draw indices.
 __host__ __device__ inline TailSmem tail_smem(int M, int TL, int warps) {
     TailSmem L;
     L.off_l1p = 0;
@@ -899,11 +899,10 @@ __host__ __device__ inline TailSmem tail_smem(int M, int TL, int warps) {
     L.off_tab = o;   // 64 doubles exp table + 128 doubles log table
     o += (64 + 128) * 8;
     L.off_w = o;
-    L.off_a = 0;
-    L.off_x = (size_t)64 * TL * 8;
-    L.off_s = L.off_x + (size_t)32 * TL * 8;
-    L.off_p = L.off_s + (size_t)32 * TL * 2;
-    L.w_stride = L.off_p + (size_t)64 * TL * 2;
+    L.off_x = 0;
+    L.off_t = (size_t)32 * TL * 8;
+    L.off_s = (size_t)32 * TL * 16;
+    L.w_stride = (size_t)32 * TL * 18;
     o += L.w_stride * warps;
     L.total = align_up(o, 128);
     return L;
@@ -912,11 +911,11 @@ __host__ __device__ inline TailSmem tail_smem(int M, int TL, int warps) {
 constexpr int TAIL_WARPS = 4;
 
 struct TailStage {
-    double* xp;           // candidate x by slot (aliases tb)
     double* tb;
     double* xs;
     unsigned short* ss;
-    unsigned short* sp;
+    double* gx;           // this row's candidate scratch in global memory: x by slot (cap doubles) ...
+    unsigned short* gs;   // ... and draw index by slot; both free again once the head is staged
 };
 
 // quantised image of x for the sort: the float image of (x - taux) >= 0, top QB bits, inverted so that
@@ -933,35 +932,29 @@ __device__ __forceinline__ unsigned quant_key(double x, double taux) {
 // further down can never be in the tail: their exp goes straight to the normaliser (returned).
 // Equal quantised values leave a short run in unspecified order; fix_runs() orders it exactly.
 template <int CAPL, int TL>
-__device__ __forceinline__ double sort_and_stage(const double* cx, const unsigned short* cs, int C, double taux,
-                                                 const TailStage& st, const ExpTab& tab, int lane) {
+__device__ __forceinline__ double sort_and_stage(int C, double taux, const TailStage& st, const ExpTab& tab, int lane) {
     constexpr int PB = (TL == 4) ? 8 : ((TL == 8) ? 9 : 10);  // bits of a candidate slot (cap = 64 TL)
     constexpr int QB = 32 - PB;
     unsigned k[CAPL];
 #pragma unroll
     for (int i = 0; i < CAPL; ++i) {
         const int e = 32 * i + lane;
-        k[i] = 0xffffffffu;
-        if (e < C) {
-            const double x = cx[e];
-            st.xp[e] = x;
-            st.sp[e] = cs[e];
-            k[i] = (quant_key<QB>(x, taux) << PB) | (unsigned)e;
-        }
+        k[i] = (e < C) ? ((quant_key<QB>(st.gx[e], taux) << PB) | (unsigned)e) : 0xffffffffu;
     }
-    __syncwarp();
     warp_bitonic_sort32<CAPL>(k, lane);
+    // exact value and draw index of every element of the order: gathered by slot from the row's scratch
+    // (4 KB, just read: L1 / L2 hits)
     double rest = 0.0;
 #pragma unroll
     for (int i = 0; i < CAPL; ++i) {
         const int e = 32 * i + lane;
         const unsigned pidx = k[i] & ((1u << PB) - 1u);
         if (i < TL) {
-            st.xs[e] = (e < C) ? st.xp[pidx] : -inf_f64();
-            st.ss[e] = (e < C) ? st.sp[pidx] : (unsigned short)0;
+            st.xs[e] = (e < C) ? st.gx[pidx] : -inf_f64();
+            st.ss[e] = (e < C) ? st.gs[pidx] : (unsigned short)0;
         } else if (32 * i < C) {
             if (e < C) {
-                const double x = st.xp[pidx];
+                const double x = st.gx[pidx];
                 if (x >= -700.0) rest += exp_tab(x, tab);
             }
         }
@@ -978,16 +971,17 @@ __device__ __forceinline__ bool fix_runs(const TailStage& st, int C, double taux
     constexpr int NS = 32 * TL;
     constexpr int PB = (TL == 4) ? 8 : ((TL == 8) ? 9 : 10);
     constexpr int QB = 32 - PB;
-    // temporaries in the (now free) candidate region: moved values, their draw indices and new positions
+    // temporaries (only touched when a run exists): moved values in tb, their draw indices and new
+    // positions in the upper half of the row's candidate scratch (free once the head is staged)
     double* mvx = st.tb;
-    int* mvs = reinterpret_cast<int*>(st.tb + NS);
+    int* mvs = reinterpret_cast<int*>(st.gx + NS);
     int* mvn = mvs + NS;
-    bool bad = false, any_moved = false;
+    bool bad = false;
+    unsigned moved = 0;  // bit i: this lane's element of the i-th group of 32 moves
     const int lim = (C < NS) ? C : NS;
 #pragma unroll 1
-    for (int e0 = 0; e0 < lim; e0 += 32) {
-        const int e = e0 + lane;
-        int npos = -1;
+    for (int i = 0; 32 * i < lim; ++i) {
+        const int e = 32 * i + lane;
         if (e < lim) {
             const double myx = st.xs[e];
             const unsigned q = quant_key<QB>(myx, taux);
@@ -1004,20 +998,20 @@ __device__ __forceinline__ bool fix_runs(const TailStage& st, int C, double taux
                     const double xf = st.xs[f];
                     cnt += (xf > myx || (xf == myx && (int)st.ss[f] > mys)) ? 1 : 0;
                 }
-                npos = lo + cnt;
                 mvx[e] = myx;
                 mvs[e] = mys;
+                mvn[e] = lo + cnt;
+                moved |= 1u << i;
             }
-            mvn[e] = npos;
         }
-        any_moved = any_moved || (npos >= 0);
     }
     __syncwarp();
-    if (__any_sync(FULL, any_moved)) {
+    if (__any_sync(FULL, moved != 0)) {
 #pragma unroll 1
-        for (int e = lane; e < lim; e += 32) {
-            const int npos = mvn[e];
-            if (npos >= 0) {
+        for (int i = 0; 32 * i < lim; ++i) {
+            if (moved & (1u << i)) {
+                const int e = 32 * i + lane;
+                const int npos = mvn[e];
                 st.xs[npos] = mvx[e];
                 st.ss[npos] = (unsigned short)mvs[e];
             }
@@ -1037,11 +1031,11 @@ __device__ __forceinline__ int tail_row(const SplitParams& p, long long row, con
     double* tb = st.tb;
     unsigned short* ss = st.ss;
 
-    double* cx = p.cx + (size_t)row * (size_t)p.cap;
-    unsigned short* cs = p.cs + (size_t)row * (size_t)p.cap;
+    double* cx = st.gx;
+    unsigned short* cs = st.gs;
     double nont;
-    if (C <= 32 * TL) nont = sort_and_stage<TL, TL>(cx, cs, C, h.taux, st, tab, lane);
-    else nont = sort_and_stage<2 * TL, TL>(cx, cs, C, h.taux, st, tab, lane);
+    if (C <= 32 * TL) nont = sort_and_stage<TL, TL>(C, h.taux, st, tab, lane);
+    else nont = sort_and_stage<2 * TL, TL>(C, h.taux, st, tab, lane);
     if (!fix_runs<TL>(st, C, h.taux, lane)) return HO_RUNS;
     // cutoff = (M+1)-th largest = element M of the order (psis.py:135-136); draws equal to it are
     // not in the tail (psis.py:139)
@@ -1187,7 +1181,7 @@ __device__ __forceinline__ int tail_row(const SplitParams& p, long long row, con
 }
 
 template <int TL>
-constexpr int tail_min_blocks() { return TL <= 8 ? 6 : 3; }
+constexpr int tail_min_blocks() { return TL <= 8 ? 8 : 3; }
 
 template <int TL, int MODE>
 __global__ void __launch_bounds__(TAIL_WARPS * 32, tail_min_blocks<TL>()) psis_tail_kernel(const SplitParams p) {
@@ -1200,11 +1194,11 @@ __global__ void __launch_bounds__(TAIL_WARPS * 32, tail_min_blocks<TL>()) psis_t
     const int wid = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0);
     unsigned char* wbase = smem_raw + L.off_w + L.w_stride * wid;
     TailStage st;
-    st.xp = reinterpret_cast<double*>(wbase + L.off_a);
-    st.tb = st.xp;
     st.xs = reinterpret_cast<double*>(wbase + L.off_x);
+    st.tb = reinterpret_cast<double*>(wbase + L.off_t);
     st.ss = reinterpret_cast<unsigned short*>(wbase + L.off_s);
-    st.sp = reinterpret_cast<unsigned short*>(wbase + L.off_p);
+    st.gx = nullptr;
+    st.gs = nullptr;
     double* tabm = reinterpret_cast<double*>(smem_raw + L.off_tab);
     ExpTab tab;
     tab.t = tabm;
@@ -1222,6 +1216,8 @@ __global__ void __launch_bounds__(TAIL_WARPS * 32, tail_min_blocks<TL>()) psis_t
     for (long long row = (long long)blockIdx.x * TAIL_WARPS + wid; row < p.n_rows; row += nwarps) {
         const SplitHeader h = p.hdr[row];
         if (h.flags) continue;
+        st.gx = p.cx + (size_t)row * (size_t)p.cap;
+        st.gs = p.cs + (size_t)row * (size_t)p.cap;
         const int why = tail_row<TL, MODE>(p, row, h, l1p, st, tab, lane);
         if (why && lane == 0) {
             note_handover(why);

@@ -236,7 +236,7 @@ static bool split_shape(long long S, int M, long long n_rows, SplitPlan* sp) {
     }
     // observations per stream -> tail -> apply -> hand-over round: a multiple of every resident-CTA /
     // resident-warp count the kernels reach on 148 SMs (no partial last wave), ~230 MB at S = 4000
-    long long b = 148ll * 48;
+    long long b = 148ll * 64;
     while (b > 148 * 6 && b * S * 8 > (1ll << 30)) b /= 2;
     if (const char* ev = getenv("B2L_BATCH")) b = std::max<long long>(1, atoll(ev));
     sp->batch = std::max<long long>(1, std::min<long long>(b, std::max<long long>(n_rows, 1)));
@@ -528,7 +528,7 @@ constexpr int STATS_BLOCKS = 148;
 // layout: [stats partials][panel A (obs-fastest input transposed to rows)][panel B (psislw rows out)]
 static long long panel_obs(long long S, long long N) {
     // one panel = one stream -> tail round of the split path (whole waves of both kernels)
-    long long p = 148ll * 48;
+    long long p = 148ll * 64;
     while (p > 148 * 6 && p * S * 8 > (1ll << 30)) p /= 2;
     if (const char* ev = getenv("B2L_PANEL")) p = std::max<long long>(32, atoll(ev));
     p = (p + 31) / 32 * 32;
@@ -851,7 +851,7 @@ int slot_reserve(Slot& s, size_t bytes) {
 }
 long long default_chunk(long long S, long long N) {
     // one chunk = one round of the split path (whole waves of the stream and tail kernels)
-    long long c = 148ll * 48;
+    long long c = 148ll * 64;
     while (c > 148 * 6 && c * S * 8 > (1ll << 28)) c /= 2;
     return std::min(c, std::max<long long>(N, 1));
 }
