@@ -967,7 +967,7 @@ __device__ __forceinline__ double sort_and_stage(int C, double taux, const TailS
 // counts the run members that precede it in (x descending, draw index descending) order and moves
 // there.  Returns false if a run is too long or may continue past the staged range.
 template <int TL>
-__device__ __forceinline__ bool fix_runs(const TailStage& st, int C, double taux, int lane) {
+__device__ __forceinline__ bool fix_runs(const TailStage& st, int C, int M, double taux, int lane) {
     constexpr int NS = 32 * TL;
     constexpr int PB = (TL == 4) ? 8 : ((TL == 8) ? 9 : 10);
     constexpr int QB = 32 - PB;
@@ -979,10 +979,17 @@ __device__ __forceinline__ bool fix_runs(const TailStage& st, int C, double taux
     bool bad = false;
     unsigned moved = 0;  // bit i: this lane's element of the i-th group of 32 moves
     const int lim = (C < NS) ? C : NS;
+    // only the order of elements 0 .. M (tail + cutoff) matters: runs that start above M are left alone,
+    // the run that holds element M is fixed as a whole
+    int need = (M + 1 < lim) ? M + 1 : lim;
+    if (need == M + 1) {
+        const unsigned qm = quant_key<QB>(st.xs[M], taux);
+        while (need < lim && need - M < 35 && quant_key<QB>(st.xs[need], taux) == qm) ++need;
+    }
 #pragma unroll 1
-    for (int i = 0; 32 * i < lim; ++i) {
+    for (int i = 0; 32 * i < need; ++i) {
         const int e = 32 * i + lane;
-        if (e < lim) {
+        if (e < need) {
             const double myx = st.xs[e];
             const unsigned q = quant_key<QB>(myx, taux);
             const bool in_run = (e > 0 && quant_key<QB>(st.xs[e - 1], taux) == q) ||
@@ -1008,7 +1015,7 @@ __device__ __forceinline__ bool fix_runs(const TailStage& st, int C, double taux
     __syncwarp();
     if (__any_sync(FULL, moved != 0)) {
 #pragma unroll 1
-        for (int i = 0; 32 * i < lim; ++i) {
+        for (int i = 0; 32 * i < need; ++i) {
             if (moved & (1u << i)) {
                 const int e = 32 * i + lane;
                 const int npos = mvn[e];
@@ -1036,7 +1043,7 @@ __device__ __forceinline__ int tail_row(const SplitParams& p, long long row, con
     double nont;
     if (C <= 32 * TL) nont = sort_and_stage<TL, TL>(C, h.taux, st, tab, lane);
     else nont = sort_and_stage<2 * TL, TL>(C, h.taux, st, tab, lane);
-    if (!fix_runs<TL>(st, C, h.taux, lane)) return HO_RUNS;
+    if (!fix_runs<TL>(st, C, M, h.taux, lane)) return HO_RUNS;
     // cutoff = (M+1)-th largest = element M of the order (psis.py:135-136); draws equal to it are
     // not in the tail (psis.py:139)
     const double xc = xs[M];
