@@ -436,3 +436,44 @@ def test_heavy_tailed_rows_stay_on_the_split_path():
     close(r["lppd_i"], pw["lppd_i"])
     assert (pw["pareto_k"] > 0.7).mean() > 0.9
     assert int(r["counters"][3]) <= 26          # <= 10 % of the rows handed over
+
+
+@pytest.mark.parametrize("S", [64, 130, 1022, 2050, 3000, 4002, 4094, 4096, 4098, 6002, 12288])
+def test_split_path_shape_boundaries(S):
+    """Draw counts around the stream kernel's thread x register shapes (partial last slots, pads, the
+    switch to the next shape) and piecewise apply transfers."""
+    rng = np.random.default_rng(S)
+    N = 37
+    x = rng.normal(size=(N, S)) * 1.7
+    lw, k, diag = gpu_psislw(x, 1.0, diag=True)
+    ref_lw, ref_k = orc.psislw(x, 1.0)
+    close(k, ref_k, atol=1e-13)
+    close(lw, ref_lw, atol=1e-12)
+    M = orc.tail_length(S, 1.0)
+    cut, cnt = oracle_tail(x, M)
+    assert np.array_equal(diag[:, 1], cut) and np.array_equal(diag[:, 2].astype(int), cnt)
+    r = gpu_loo(np.ascontiguousarray(-x.T), 1.0)
+    pw = orc.loo_pointwise(-x.T, 1.0)
+    close(r["elpd_i"], pw["elpd_i"])
+    close(r["pareto_k"], pw["pareto_k"], atol=1e-13)
+    close(r["lppd_i"], pw["lppd_i"])
+
+
+def test_split_path_padded_rows_and_many_rounds(monkeypatch):
+    """Row stride larger than S (aligned padding) on input and output, and more than three rounds of the
+    stream -> tail -> apply pipeline (scratch slots alternate, the last apply stage runs alone)."""
+    rng = np.random.default_rng(77)
+    N, S, pad = 700, 2000, 6
+    x = rng.normal(size=(N, S))
+    buf = torch.zeros((N, S + pad), dtype=torch.float64, device="cuda")
+    buf[:, :S] = torch.from_numpy(x).cuda()
+    out = torch.full((N, S + pad), 7.0, dtype=torch.float64, device="cuda")
+    monkeypatch.setenv("B2L_BATCH", "96")          # 8 rounds
+    lw, k = engine.psislw_cuda(buf[:, :S], 1.0, out=out[:, :S])
+    torch.cuda.synchronize()
+    monkeypatch.delenv("B2L_BATCH")
+    ref_lw, ref_k = orc.psislw(x, 1.0)
+    close(k.cpu().numpy(), ref_k, atol=1e-13)
+    close(out[:, :S].cpu().numpy(), ref_lw, atol=1e-12)
+    assert bool((out[:, S:] == 7.0).all())          # nothing written past the rows
+    assert bool((buf[:, :S].cpu() == torch.from_numpy(x)).all())   # input untouched (psis.py:78)
