@@ -1,22 +1,24 @@
-// Split PSIS path (sm_100a): a streaming kernel and a tail kernel per observation batch.
+// Split PSIS path (sm_100a): a streaming kernel and a tail kernel per round of observations.
 //
-//   psis_stream_kernel  one CTA per observation.  The S draws are prefetched by 1-D bulk TMA into
-//                       shared memory and then held in REGISTERS (EPT per thread), so the row is
-//                       read once: max (pyloo/psis.py:134), a threshold below the (M+1)-th largest
-//                       draw estimated from the per-thread maxima, then one pass that forms
+//   psis_stream_kernel  one CTA per observation.  The S draws arrive by 1-D bulk TMA in a padded
+//                       shared-memory row: max (pyloo/psis.py:134), a threshold below the (M+1)-th
+//                       largest draw estimated from the per-thread maxima, then one pass that forms
 //                       x = fl(r - max r), sums exp(x) over the body (pyloo/utils.py:349-351) and
-//                       emits the ~1.2 (M+1) candidate draws above the threshold as packed 64-bit
-//                       keys.  LOO mode adds the lppd / variance sums (pyloo/loo.py:329-337,
-//                       pyloo/waic.py:137-145).
-//   psis_tail_kernel    one WARP per observation, no block barriers: register bitonic sort of the
-//                       candidate keys, exact cutoff / tail (psis.py:135-141), Zhang-Stephens GPD
-//                       fit (psis.py:181-208), _gpinv smoothing (psis.py:149-157,211-222),
-//                       normaliser (psis.py:158), then either the normalised row with the smoothed
-//                       tail patched in (psislw) or elpd_i / lppd_i / var_i (loo.py:319-337).
+//                       emits the ~1.15 (M+1) candidate draws above the threshold (exact x + draw
+//                       index) to a per-round scratch.  LOO mode adds the lppd / variance sums
+//                       (pyloo/loo.py:329-337, pyloo/waic.py:137-145).  In psislw mode one extra
+//                       warp per CTA applies the PREVIOUS round: out = (r - max r) - lse with the
+//                       smoothed tail on top (psis.py:156-158), bulk TMA in and out.
+//   psis_tail_kernel    one WARP per observation, no block barriers: register bitonic sort of
+//                       32-bit quantised keys + exact re-ranking of equal-key runs, cutoff / tail
+//                       (psis.py:135-141), Zhang-Stephens GPD fit (psis.py:181-208), _gpinv
+//                       smoothing (psis.py:149-157,211-222), normaliser (psis.py:158); output: lse, k
+//                       and the patch list (psislw) or elpd_i / lppd_i / var_i (loo.py:319-337).
+//   psis_apply_kernel   the apply stage alone (after the last round; NT = 1024 shapes).
 //
-// Rows the fast path cannot decide exactly (NaN / inf, ties or key collisions at the cutoff,
-// candidate overflow, non-finite GPD profiles, cutoff below log(DBL_MIN)) are appended to a list
-// and re-done by the general row kernel (b2l_row_kernel.cuh), which handles every case.
+// Rows the fast path cannot decide exactly (NaN / inf, range > 1e7, threshold retries exhausted, long
+// runs of equal keys at the cutoff, non-finite GPD profiles) are appended to a list and re-done by
+// the general row kernel (b2l_row_kernel.cuh), which handles every case.
 #pragma once
 
 #include <type_traits>
@@ -31,9 +33,8 @@ enum : int { HO_SPECIAL = 1, HO_RANGE = 2, HO_RETRY = 3, HO_RUNS = 4, HO_ORDER =
 static __device__ unsigned long long g_handover[HO_REASONS];
 __device__ __forceinline__ void note_handover(int reason) { atomicAdd(&g_handover[reason], 1ull); }
 
-constexpr int KEY_IDX_BITS = 14;               // draw index lives in the low bits of a candidate key
+constexpr int KEY_IDX_BITS = 14;               // draw indices travel as 16-bit values: S <= 2^14
 constexpr int SPLIT_MAX_S = 1 << KEY_IDX_BITS;
-constexpr unsigned KEY_IDX_MASK = (1u << KEY_IDX_BITS) - 1u;
 
 struct __align__(16) SplitHeader {  // 80 B per observation: stream kernel -> tail kernel -> apply kernel
     double mx;      // max_s r_s
@@ -561,7 +562,7 @@ __global__ void __launch_bounds__(stream_block(NT, MODE), stream_min_blocks<NT>(
             };
             if (MODE == MODE_LOO && wide) pass_b(std::true_type{});
             else pass_b(std::false_type{});
-            // -------- emit candidates: one shared atomic per warp, packed keys to global scratch
+            // -------- emit candidates: one shared atomic per warp, (exact x, draw index) to the round's scratch
             {
                 const int mine = __popc(cmask);
                 int incl = mine;
