@@ -874,10 +874,36 @@ static __device__ __noinline__ double smooth_tail_literal(double* tb, const doub
     return tsm;
 }
 
+// The candidates that end up outside the tail are summed in double-double arithmetic (error-free TwoSum):
+// the result is exact to ~1e-32, so after rounding it does not depend on the (atomics-dependent) order in
+// which the stream kernel emitted candidates with equal sort keys -- runs are bit-reproducible.
+struct DD {
+    double hi, lo;
+};
+__device__ __forceinline__ void dd_add(DD& a, double e) {
+    const double s = a.hi + e;
+    const double bb = s - a.hi;
+    a.lo += (a.hi - (s - bb)) + (e - bb);
+    a.hi = s;
+}
+__device__ __forceinline__ double warp_dd_sum(DD a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ohi = __shfl_xor_sync(FULL, a.hi, o), olo = __shfl_xor_sync(FULL, a.lo, o);
+        const double s = a.hi + ohi;
+        const double bb = s - a.hi;
+        const double err = (a.hi - (s - bb)) + (ohi - bb);
+        const double lo = (a.lo + olo) + err;
+        a.hi = s + lo;              // renormalise (fast two-sum)
+        a.lo = lo - (a.hi - s);
+    }
+    return a.hi + a.lo;
+}
+
 // heavy-tailed rows (cutoff clamped at log(DBL_MIN)): t_i and the body terms with the library exp
 static __device__ __noinline__ void tail_t_literal(const double* xs, double* tb, int n, int staged, double exp_c,
-                                                   int lane, double& nont, double& tsum, double& traw) {
-    for (int e = n + lane; e < staged; e += 32) nont += exp(xs[e]);
+                                                   int lane, DD& nont, double& tsum, double& traw) {
+    for (int e = n + lane; e < staged; e += 32) dd_add(nont, exp(xs[e]));
     for (int e = lane; e < n; e += 32) {
         const double ex = exp(xs[e]);
         const double ti = ex - exp_c;
@@ -933,7 +959,7 @@ __device__ __forceinline__ unsigned quant_key(double x, double taux) {
 // further down can never be in the tail: their exp goes straight to the normaliser (returned).
 // Equal quantised values leave a short run in unspecified order; fix_runs() orders it exactly.
 template <int CAPL, int TL>
-__device__ __forceinline__ double sort_and_stage(int C, double taux, const TailStage& st, const ExpTab& tab, int lane) {
+__device__ __forceinline__ DD sort_and_stage(int C, double taux, const TailStage& st, const ExpTab& tab, int lane) {
     constexpr int PB = (TL == 4) ? 8 : ((TL == 8) ? 9 : 10);  // bits of a candidate slot (cap = 64 TL)
     constexpr int QB = 32 - PB;
     unsigned k[CAPL];
@@ -945,7 +971,7 @@ __device__ __forceinline__ double sort_and_stage(int C, double taux, const TailS
     warp_bitonic_sort32<CAPL>(k, lane);
     // exact value and draw index of every element of the order: gathered by slot from the row's scratch
     // (4 KB, just read: L1 / L2 hits)
-    double rest = 0.0;
+    DD rest = {0.0, 0.0};
 #pragma unroll
     for (int i = 0; i < CAPL; ++i) {
         const int e = 32 * i + lane;
@@ -956,7 +982,7 @@ __device__ __forceinline__ double sort_and_stage(int C, double taux, const TailS
         } else if (32 * i < C) {
             if (e < C) {
                 const double x = st.gx[pidx];
-                if (x >= -700.0) rest += exp_tab(x, tab);
+                if (x >= -700.0) dd_add(rest, exp_tab(x, tab));
             }
         }
     }
@@ -1041,7 +1067,7 @@ __device__ __forceinline__ int tail_row(const SplitParams& p, long long row, con
 
     double* cx = st.gx;
     unsigned short* cs = st.gs;
-    double nont;
+    DD nont;  // double-double: order-independent sum
     if (C <= 32 * TL) nont = sort_and_stage<TL, TL>(C, h.taux, st, tab, lane);
     else nont = sort_and_stage<2 * TL, TL>(C, h.taux, st, tab, lane);
     if (!fix_runs<TL>(st, C, M, h.taux, lane)) return HO_RUNS;
@@ -1073,7 +1099,7 @@ __device__ __forceinline__ int tail_row(const SplitParams& p, long long row, con
     if (!deep) {
         // staged candidates at or below the cutoff belong to the normaliser's body too
 #pragma unroll 1
-        for (int e = n + lane; e < min(C, 32 * TL); e += 32) nont += exp_tab(xs[e], tab);
+        for (int e = n + lane; e < min(C, 32 * TL); e += 32) dd_add(nont, exp_tab(xs[e], tab));
         // t_i = exp(x_i) - exp(c) (psis.py:146-147), descending
 #pragma unroll 1
         for (int e = lane; e < n; e += 32) {
@@ -1088,7 +1114,7 @@ __device__ __forceinline__ int tail_row(const SplitParams& p, long long row, con
     }
     tsum = warp_sum(tsum);
     traw = warp_sum(traw);
-    nont = warp_sum(nont);
+    const double nont_sum = warp_dd_sum(nont);
     __syncwarp();
 
     double kk = inf_f64(), sigma = nan_f64();
@@ -1135,7 +1161,7 @@ __device__ __forceinline__ int tail_row(const SplitParams& p, long long row, con
         tails = warp_sum(tsm);
         __syncwarp();
     }
-    const double body = h.body + nont;
+    const double body = h.body + nont_sum;
     const double lse = log_tab(body + tails, tab.t + 64);  // psis.py:158
 
     if (MODE == MODE_PSISLW) {
