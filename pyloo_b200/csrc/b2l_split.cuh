@@ -759,7 +759,7 @@ __device__ __forceinline__ int gpdfit_warp(const double* t, int n, int m, double
         if (live) bmag = (fabs(bj) > bmag) ? fabs(bj) : bmag;
         if (live && !is_finite(bj)) bmag = inf_f64();
     }
-    bmag = warp_max(bmag);
+    bmag = warp_max_sel(bmag);  // (+inf marks a non-finite grid point; no NaN can reach this)
     const double fmx = 1.0 + bmag * tn;
     if (!(fmx < 0x1p1020)) return HO_GPD_FMX;
     // factors lie in [(1 - b_max t_n) > 6e-4, fmx]: (2^31)^32 < 2^1023 and (6e-4)^32 > 2^-340, so rescaling
@@ -794,7 +794,7 @@ __device__ __forceinline__ int gpdfit_warp(const double* t, int n, int m, double
         }
     }
     if (!__all_sync(FULL, fin)) return HO_GPD_PROFILE;
-    lm = warp_max(lm);
+    lm = warp_max_sel(lm);
     double w[2], es = 0.0;
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -1188,7 +1188,7 @@ __device__ __forceinline__ int tail_row(const SplitParams& p, long long row, con
                 const double d = tb[e] - xs[e];
                 dm = (d > dm) ? d : dm;
             }
-            dmax = warp_max(dm);
+            dmax = warp_max_sel(dm);
             double e2 = 0.0;
 #pragma unroll 1
             for (int e = lane; e < n; e += 32) e2 += exp((tb[e] - xs[e]) - dmax);
