@@ -2,7 +2,7 @@
 against the CPU oracle (dev tool; the real parity tests live in tests/)."""
 import os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from pyloo_b200 import engine
 from oracle import psis_oracle as orc

@@ -1,6 +1,6 @@
 """Dev tool: BASELINE.json configs[2] and configs[4] at FULL single-GPU size (size-independent checks + timing)."""
 import os, sys, json, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from pyloo_b200 import engine
 from oracle import psis_oracle as orc

@@ -1,6 +1,6 @@
 """Dev tool: small split-path check against the oracle (psislw + loo), prints max errors."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from pyloo_b200 import engine
 from oracle import psis_oracle as orc

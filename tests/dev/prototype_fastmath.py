@@ -3,7 +3,7 @@ the oracle: product-form GPD profile, shifted posterior weights, exp-free tail s
 elpd_i.  Dev tool; not imported by the product."""
 import sys, os
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import psis_oracle as orc
 
 EPS = np.finfo(float).eps
