@@ -123,17 +123,60 @@ int b2l_loo_host_f64(const double* ll, int64_t S, int64_t N, int64_t stride_s, i
                      double* k_i, double* lppd_i, double* var_i, double* lppdw_i, double* stats_out,
                      int32_t device, int64_t chunk_obs);
 
+/* ---------------------------------------------------------------------------------------------------
+ * The callers either side of psislw ("next" rows 3 and 1).  Device pointers, asynchronous
+ * on `stream`, rows of S doubles with element stride 1 unless stated otherwise.
+ * ------------------------------------------------------------------------------------------------- */
+#define B2L_IS_SIS 1 /* standard importance sampling, pyloo/sis.py:86-106 */
+#define B2L_IS_TIS 2 /* truncated importance sampling, pyloo/tis.py:91-120 */
+
+/* SIS / TIS branch of compute_importance_weights (pyloo/base.py:146-152,160-166): replaces the
+ * per-observation loop over _sislw / _tislw.  lw: N rows (row i at lw + i*stride_n), never modified;
+ * lw_out: N rows at lw_out + i*ostride_n; ess_out: N effective sample sizes 1 / sum(w^2).          */
+int b2l_islw_dev_f64(const double* lw, int64_t S, int64_t N, int64_t stride_n, int32_t method,
+                     double* lw_out, int64_t ostride_n, double* ess_out, void* stream);
+
+/* loo(method="sis"|"tis") pointwise pass: replaces pyloo/loo.py:286-289 (weights of -ll, lw += ll),
+ * :319-324 (elpd_i = logsumexp) and :329-337 (lppd_i).  ll element (s, i) at ll[s*stride_s + i*stride_n]
+ * with one of the strides equal to 1 (stride_n == 1 is the ArviZ layout and goes through transposed
+ * panels in the workspace); NaN -> -1e10 (loo.py:227).  counters: nullable, 3 x uint64 (+=) NaN / +inf /
+ * -inf inputs.  Workspace: b2l_is_workspace_bytes.                                                   */
+int b2l_is_workspace_bytes(int64_t S, int64_t N, int32_t layout_obs_fastest, size_t* out_bytes);
+int b2l_loo_is_dev_f64(const double* ll, int64_t S, int64_t N, int64_t stride_s, int64_t stride_n,
+                       int32_t method, double* elpd_i, double* ess_i, double* lppd_i,
+                       unsigned long long* counters, void* ws, size_t ws_bytes, void* stream);
+
+/* e_loo weighted expectations with their Pareto-k diagnostic: replaces pyloo/e_loo.py:429-463,518-531
+ * (_compute_weighted_mean / _variance / _sd over normalised weights) and :266-390 (compute_pareto_k ->
+ * k_hat, three top-`tail_len` tails + _gpdfit each) for a batch of N observations.
+ *   x   : the draws, N rows; moments are taken of x, and k_hat's h is x (mean) or x*x (variance, sd;
+ *         e_loo.py:234-239); NULL with B2L_ELOO_NONE (quantiles: k_hat of the ratios only)
+ *   lw  : log weights rows, any normalisation (normalised inside, e_loo.py:557-559)
+ *   lr  : raw log ratios rows for k_hat, or NULL to use lw (e_loo.py:229-230)
+ *   value_out, khat_out : N doubles each.                                                            */
+#define B2L_ELOO_MEAN 0
+#define B2L_ELOO_VARIANCE 1
+#define B2L_ELOO_SD 2
+#define B2L_ELOO_NONE 3
+int b2l_eloo_workspace_bytes(int64_t S, int64_t N, int32_t has_lr, int32_t type, size_t* out_bytes);
+int b2l_eloo_dev_f64(const double* x, int64_t x_stride_n, const double* lw, int64_t lw_stride_n,
+                     const double* lr, int64_t lr_stride_n, int64_t S, int64_t N, int32_t type,
+                     int32_t tail_len, double* value_out, double* khat_out, void* ws, size_t ws_bytes,
+                     void* stream);
+
 /* Per-kernel device timing for benchmarks (no reference counterpart): with b2l_profile(1) every kernel
  * launch is bracketed by CUDA events on its stream; b2l_profile_read() synchronises them and returns
  * summed milliseconds and launch counts per kernel kind since the last read.  Not thread safe.    */
-#define B2L_PROF_KINDS 6
+#define B2L_PROF_KINDS 8
 enum {
     B2L_PROF_STREAM = 0,    /* psis_stream_kernel (row pass; psislw: + fused apply of the previous batch) */
     B2L_PROF_TAIL = 1,      /* psis_tail_kernel (sort, GPD fit, smoothing, normaliser) */
     B2L_PROF_APPLY = 2,     /* psis_apply_kernel (only when the fused apply is disabled) */
     B2L_PROF_ROW = 3,       /* psis_row_kernel: general kernel, whole batch or hand-over rows */
     B2L_PROF_TRANSPOSE = 4, /* transpose_f64_kernel */
-    B2L_PROF_STATS = 5      /* stats_partial_kernel + stats_final_kernel */
+    B2L_PROF_STATS = 5,     /* stats_partial_kernel + stats_final_kernel */
+    B2L_PROF_IS = 6,        /* is_row_kernel (SIS / TIS weights or loo) */
+    B2L_PROF_ELOO = 7       /* eloo_row_kernel (weighted expectations + k_hat) */
 };
 int b2l_profile(int32_t enable);
 int b2l_profile_read(double* ms_out /* [B2L_PROF_KINDS] */, int64_t* launches_out /* [B2L_PROF_KINDS] */);

@@ -30,11 +30,14 @@ def _stub(name: str, **attrs) -> types.ModuleType:
     return mod
 
 
-def load_reference():
-    """Return ``(psis_module, utils_module)`` holding the reference's own functions."""
+def load_reference_modules(names=("utils", "psis")):
+    """Load ``pyloo/<name>.py`` for each name (in order) from the reference tree under stub ``xarray`` /
+    ``arviz`` modules and return ``{name: module}``.  Besides ``utils`` and ``psis`` this works for the
+    NumPy-only numerics of ``sis``, ``tis`` and ``e_loo`` (their xarray drivers are not callable)."""
     if not reference_available():
         raise RuntimeError(f"reference tree not found under {REFERENCE_ROOT}")
-    saved = {k: sys.modules.get(k) for k in ("xarray", "arviz", "pyloo", "pyloo.utils", "pyloo.psis")}
+    keys = ["xarray", "arviz", "pyloo"] + [f"pyloo.{n}" for n in names]
+    saved = {k: sys.modules.get(k) for k in keys}
     try:
         class _DataArray:  # placeholder type for isinstance checks only
             pass
@@ -53,20 +56,26 @@ def load_reference():
         pkg.__path__ = [os.path.join(REFERENCE_ROOT, "pyloo")]
         sys.modules["pyloo"] = pkg
         mods = {}
-        for short in ("utils", "psis"):
+        for short in names:
             spec = importlib.util.spec_from_file_location(
                 f"pyloo.{short}", os.path.join(REFERENCE_ROOT, "pyloo", f"{short}.py"))
             mod = importlib.util.module_from_spec(spec)
             sys.modules[f"pyloo.{short}"] = mod
             spec.loader.exec_module(mod)
             mods[short] = mod
-        return mods["psis"], mods["utils"]
+        return mods
     finally:
         for key, val in saved.items():
             if val is None:
                 sys.modules.pop(key, None)
             else:
                 sys.modules[key] = val
+
+
+def load_reference():
+    """Return ``(psis_module, utils_module)`` holding the reference's own functions."""
+    mods = load_reference_modules(("utils", "psis"))
+    return mods["psis"], mods["utils"]
 
 
 def reference_psislw_batch(lw_ns, reff):

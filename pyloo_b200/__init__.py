@@ -1,7 +1,8 @@
 """pyloo_b200 -- B200-native PSIS-LOO engine behind pyloo's call signatures.
 
-Drop-in for ``pl.psislw``, ``pl.compute_importance_weights`` (PSIS branch), ``pl.loo(method="psis")``,
-``pl.waic`` and ``pl.loo_compare`` (reference: jordandeklerk/pyloo).  The numerics run in hand-written
+Drop-in for ``pl.psislw`` / ``pl.sislw`` / ``pl.tislw``, ``pl.compute_importance_weights``,
+``pl.loo(method="psis" | "sis" | "tis")``, ``pl.waic``, ``pl.loo_compare`` and ``pl.e_loo`` (reference:
+jordandeklerk/pyloo).  The numerics run in hand-written
 sm_100a CUDA kernels behind a C ABI (``include/psisloo_b200.h``); there is no CPU fallback.
 """
 
@@ -9,6 +10,9 @@ from .rcparams import rcParams  # noqa: F401
 from .elpd import ELPDData  # noqa: F401
 from .base import ISMethod, compute_importance_weights  # noqa: F401
 from .psis import psislw  # noqa: F401
+from .sis import sislw  # noqa: F401
+from .tis import tislw  # noqa: F401
+from .e_loo import ExpectationResult, compute_pareto_k, e_loo, k_hat  # noqa: F401
 from .loo import loo  # noqa: F401
 from .waic import waic  # noqa: F401
 from .compare import loo_compare  # noqa: F401
@@ -17,6 +21,7 @@ from .data import InferenceDataLite, LiteDataArray, from_dict  # noqa: F401
 __version__ = "0.1.0"
 
 __all__ = [
-    "psislw", "compute_importance_weights", "ISMethod", "loo", "waic", "loo_compare", "ELPDData",
+    "psislw", "sislw", "tislw", "e_loo", "ExpectationResult", "compute_pareto_k", "k_hat",
+    "compute_importance_weights", "ISMethod", "loo", "waic", "loo_compare", "ELPDData",
     "rcParams", "InferenceDataLite", "LiteDataArray", "from_dict",
 ]

@@ -15,13 +15,14 @@ import threading
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "lib", "libpsisloo_b200.so")
-SRCS = [os.path.join(_PKG, "csrc", n) for n in ("psisloo_b200.cu", "b2l_split_stream.cu", "b2l_split_tail.cu")]
+SRCS = [os.path.join(_PKG, "csrc", n) for n in ("psisloo_b200.cu", "b2l_split_stream.cu", "b2l_split_tail.cu", "b2l_is.cu")]
 SRC = SRCS[0]
 HEADERS = [
     os.path.join(_PKG, "csrc", "b2l_common.cuh"),
     os.path.join(_PKG, "csrc", "b2l_row_kernel.cuh"),
     os.path.join(_PKG, "csrc", "b2l_split.cuh"),
     os.path.join(_PKG, "csrc", "b2l_split_host.h"),
+    os.path.join(_PKG, "csrc", "b2l_is_host.h"),
     os.path.join(_ROOT, "include", "psisloo_b200.h"),
 ]
 
@@ -35,8 +36,12 @@ EXPORTS = [
     "b2l_psislw_dev_f64", "b2l_loo_dev_f64", "b2l_stats_dev_f64", "b2l_stats_merge",
     "b2l_psislw_host_f64", "b2l_loo_host_f64", "b2l_row_launch_info", "b2l_profile", "b2l_profile_read",
     "b2l_split_launch_info", "b2l_handover_reasons",
+    "b2l_islw_dev_f64", "b2l_is_workspace_bytes", "b2l_loo_is_dev_f64", "b2l_eloo_workspace_bytes",
+    "b2l_eloo_dev_f64",
 ]
-PROF_KINDS = ("stream", "tail", "apply", "row", "transpose", "stats")
+PROF_KINDS = ("stream", "tail", "apply", "row", "transpose", "stats", "is", "eloo")
+IS_SIS, IS_TIS = 1, 2
+ELOO_TYPES = {"mean": 0, "variance": 1, "sd": 2, "none": 3}
 
 _lock = threading.Lock()
 _lib = None
@@ -120,6 +125,16 @@ def _declare(lib) -> None:
     lib.b2l_handover_reasons.argtypes = [vp, i32]
     lib.b2l_split_launch_info.restype = c.c_int
     lib.b2l_split_launch_info.argtypes = [i64, i32, i32, i64, vp]
+    lib.b2l_islw_dev_f64.restype = c.c_int
+    lib.b2l_islw_dev_f64.argtypes = [vp, i64, i64, i64, i32, vp, i64, vp, vp]
+    lib.b2l_is_workspace_bytes.restype = c.c_int
+    lib.b2l_is_workspace_bytes.argtypes = [i64, i64, i32, c.POINTER(sz)]
+    lib.b2l_loo_is_dev_f64.restype = c.c_int
+    lib.b2l_loo_is_dev_f64.argtypes = [vp, i64, i64, i64, i64, i32, vp, vp, vp, vp, vp, sz, vp]
+    lib.b2l_eloo_workspace_bytes.restype = c.c_int
+    lib.b2l_eloo_workspace_bytes.argtypes = [i64, i64, i32, i32, c.POINTER(sz)]
+    lib.b2l_eloo_dev_f64.restype = c.c_int
+    lib.b2l_eloo_dev_f64.argtypes = [vp, i64, vp, i64, vp, i64, i64, i64, i32, i32, vp, vp, vp, sz, vp]
     lib.b2l_row_launch_info.restype = c.c_int
     lib.b2l_row_launch_info.argtypes = [i64, i32, i32] + [c.POINTER(i32)] * 5
 

@@ -1,0 +1,615 @@
+// SIS / TIS importance weights and e_loo weighted expectations for sm_100a.
+//
+// These are the callers either side of psislw.  One CTA per observation
+// row; the row (e_loo: up to three rows) is staged in shared memory by 1-D bulk TMA when it fits and is
+// read straight from global memory otherwise, so every S is supported.  All arithmetic is IEEE FP64 with
+// the CUDA math library (no table exps here): the kernels move 16*S (weights) / 8*S (loo) / 16-24*S
+// (e_loo) bytes per observation and are bound by HBM, not by the FP64 pipe.
+//
+// Reference semantics
+//   SIS   pyloo/sis.py:101-106    x -= max; x -= logsumexp(x); ess = 1 / sum(exp(x)^2)
+//   TIS   pyloo/tis.py:108-120    x -= max; log_Z = lse(x) - log S; cut = log_Z + 0.5 log S;
+//                                 x = minimum(x, cut); x -= logsumexp(x); ess = 1 / sum(exp(x)^2)
+//   loo   pyloo/loo.py:286-289    lw += ll;  :319-324 elpd_i = lse(lw);  :329-337 lppd_i = lse(ll) - log S
+//   e_loo pyloo/e_loo.py:429-463,518-531 (weighted mean / variance / sd), :328-390 (k_hat)
+// NaN handling follows NumPy: np.max and np.minimum propagate NaN, so a row holding NaN (or whose
+// maximum is not finite) comes out all-NaN through ordinary IEEE arithmetic.
+#include <math_constants.h>
+
+#include "b2l_common.cuh"
+#include "b2l_is_host.h"
+
+namespace b2l {
+
+constexpr int IS_NT = 256;
+constexpr int IS_NW = IS_NT / 32;
+constexpr int IS_RED_WORDS = 130;  // 128 reduction words + mbarrier (16 B)
+
+__device__ __forceinline__ double np_minimum(double a, double b) {
+    return (a != a || b != b) ? nan_f64() : fmin(a, b);
+}
+// Python's max(a, b): returns b only if b > a (so a NaN first argument wins, a NaN second loses)
+__device__ __forceinline__ double py_max(double a, double b) { return (b > a) ? b : a; }
+// np.isclose(a, b) with the default rtol = 1e-5, atol = 1e-8 (equal infinities are close)
+__device__ __forceinline__ bool np_isclose(double a, double b) {
+    return (a == b) || (fabs(a - b) <= 1e-8 + 1e-5 * fabs(b));
+}
+
+// bitwise OR over the block (every thread returns the same word); __syncthreads_or only returns a boolean
+__device__ __forceinline__ int block_or(int v, double* red_) {
+    int* red = reinterpret_cast<int*>(red_ + 64);
+    v = __reduce_or_sync(FULL, v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < IS_NW; ++w) t |= red[w];
+    __syncthreads();
+    return t;
+}
+
+template <bool STAGED>
+__device__ __forceinline__ const double* stage_rows(double* const* dst, const double* const* src, int n_arr,
+                                                    int S, int bulk, uint64_t* bar, uint32_t& parity) {
+    if (!STAGED) return nullptr;
+    const int tid = threadIdx.x;
+    if (bulk) {
+        if (tid == 0) {
+            mbar_expect_tx(bar, (uint32_t)(n_arr * S * 8));
+            for (int a = 0; a < n_arr; ++a) bulk_g2s(dst[a], src[a], (uint32_t)(S * 8), bar);
+        }
+        mbar_wait(bar, parity);
+        parity ^= 1;
+    } else {
+        for (int a = 0; a < n_arr; ++a)
+            for (int s = tid; s < S; s += IS_NT) dst[a][s] = src[a][s];
+        __syncthreads();
+    }
+    return dst[0];
+}
+
+// ===================================================================================== SIS / TIS
+template <int METHOD, int MODE, bool STAGED>
+__global__ void __launch_bounds__(IS_NT) is_row_kernel(const IsParams p) {
+    extern __shared__ __align__(16) unsigned char is_smem[];
+    double* red = reinterpret_cast<double*>(is_smem);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(red + 128);
+    double* buf = red + IS_RED_WORDS;
+    const int tid = threadIdx.x, S = p.S;
+    if (STAGED && p.bulk && tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    uint32_t parity = 0;
+    unsigned c_nan = 0, c_pinf = 0, c_ninf = 0;
+
+    for (long long row = blockIdx.x; row < p.n_rows; row += gridDim.x) {
+        const double* src = p.in + row * p.in_stride;
+        double* dsts[1] = {buf};
+        const double* srcs[1] = {src};
+        stage_rows<STAGED>(dsts, srcs, 1, S, p.bulk, bar, parity);
+        const double* r = STAGED ? buf : src;
+
+        // raw log weight of draw s: weights mode reads it, loo mode negates the sanitised log-likelihood
+        auto lwraw = [&](int s) -> double {
+            double v = r[s];
+            if (MODE == IS_MODE_LOO) {
+                if (v != v) v = -1e10;  // pyloo/loo.py:227
+                v = -v;
+            }
+            return v;
+        };
+
+        // ---- pass 1: maximum (NaN-propagating), loo: also min (= -max ll) and input counters
+        double mx = -inf_f64(), mn = inf_f64();
+        int bad = 0;
+        for (int s = tid; s < S; s += IS_NT) {
+            if (MODE == IS_MODE_LOO) {
+                const double raw = r[s];
+                c_nan += (raw != raw);
+                c_pinf += (raw == inf_f64());
+                c_ninf += (raw == -inf_f64());
+            }
+            const double v = lwraw(s);
+            bad |= (v != v);
+            mx = fmax(mx, v);
+            mn = fmin(mn, v);
+        }
+        mx = block_max<IS_NT>(mx, red);
+        if (MODE == IS_MODE_LOO) mn = block_min<IS_NT>(mn, red);
+        if (__syncthreads_or(bad)) mx = nan_f64();
+
+        // ---- pass 2: first logsumexp (max of x is 0 by construction)
+        double s1 = 0.0, s2 = 0.0, sl = 0.0;
+        for (int s = tid; s < S; s += IS_NT) {
+            const double v = lwraw(s);
+            const double e = exp(v - mx);
+            s1 += e;
+            s2 += e * e;
+            if (MODE == IS_MODE_LOO) sl += exp(mn - v);  // exp(ll - max ll)
+        }
+        s1 = block_sum<IS_NT>(s1, red);
+        if (MODE == IS_MODE_LOO) sl = block_sum<IS_NT>(sl, red);
+        double lse, cut = inf_f64(), ess;
+        if (METHOD == IS_METHOD_SIS) {
+            s2 = block_sum<IS_NT>(s2, red);
+            lse = log(s1);
+            ess = (s1 * s1) / s2;
+        } else {
+            const double log_z = log(s1) - p.log_S;  // tis.py:112
+            cut = log_z + 0.5 * p.log_S;             // tis.py:114
+            const double mx2 = np_minimum(0.0, cut); // max of the truncated row
+            double t1 = 0.0, t2 = 0.0;
+            for (int s = tid; s < S; s += IS_NT) {
+                const double a = exp(np_minimum(lwraw(s) - mx, cut) - mx2);
+                t1 += a;
+                t2 += a * a;
+            }
+            t1 = block_sum<IS_NT>(t1, red);
+            t2 = block_sum<IS_NT>(t2, red);
+            lse = log(t1) + mx2;
+            ess = (t1 * t1) / t2;
+        }
+
+        // ---- output
+        if (MODE == IS_MODE_WEIGHTS) {
+            double* dst = p.out + row * p.out_stride;
+            for (int s = tid; s < S; s += IS_NT) {
+                double x = lwraw(s) - mx;
+                if (METHOD == IS_METHOD_TIS) x = np_minimum(x, cut);
+                dst[s] = x - lse;
+            }
+            if (tid == 0) p.ess[row] = ess;
+        } else {
+            // elpd_i = logsumexp(lw + ll)  (loo.py:289, :319-324)
+            double tmax = -inf_f64();
+            for (int s = tid; s < S; s += IS_NT) {
+                const double v = lwraw(s);
+                double x = v - mx;
+                if (METHOD == IS_METHOD_TIS) x = np_minimum(x, cut);
+                tmax = fmax(tmax, (x - lse) + (-v));
+            }
+            tmax = block_max<IS_NT>(tmax, red);
+            double st = 0.0;
+            for (int s = tid; s < S; s += IS_NT) {
+                const double v = lwraw(s);
+                double x = v - mx;
+                if (METHOD == IS_METHOD_TIS) x = np_minimum(x, cut);
+                st += exp(((x - lse) + (-v)) - tmax);
+            }
+            st = block_sum<IS_NT>(st, red);
+            if (tid == 0) {
+                p.elpd[row] = log(st) + tmax;
+                p.ess[row] = ess;
+                p.lppd[row] = log(sl) + ((-mn) - p.log_S);  // utils.py:352-357 with b_inv = S
+            }
+        }
+        __syncthreads();  // every read of the staged row is done before the next bulk load lands
+    }
+    if (MODE == IS_MODE_LOO && p.counters) {
+        if (c_nan) atomicAdd(&p.counters[0], (unsigned long long)c_nan);
+        if (c_pinf) atomicAdd(&p.counters[1], (unsigned long long)c_pinf);
+        if (c_ninf) atomicAdd(&p.counters[2], (unsigned long long)c_ninf);
+    }
+}
+
+// ===================================================================================== e_loo
+// ---- top-L selection ---------------------------------------------------------------------------
+// The caller's lane owns the elements first, first + stride, ... < n of buf.  Extracts the L largest keys
+// of the warp's elements in descending order into out[0..L) (padded with -inf when the warp owns fewer).
+// Ties are ordered by index, so duplicates are extracted one by one.  NEG selects on -buf[s].
+template <bool NEG>
+__device__ __forceinline__ void warp_top(const double* buf, int n, int first, int stride, int L,
+                                         double* out, int lane) {
+    constexpr int NONE = 0x7fffffff;
+    double lastv = inf_f64();
+    int lasti = -1;
+    double bestv;
+    int besti;
+    auto rescan = [&]() {
+        bestv = -inf_f64();
+        besti = NONE;
+        for (int s = first; s < n; s += stride) {
+            const double v = NEG ? -buf[s] : buf[s];
+            const bool eligible = (v < lastv) || (v == lastv && s > lasti);
+            if (eligible && (besti == NONE || v > bestv)) {
+                bestv = v;
+                besti = s;
+            }
+        }
+    };
+    rescan();
+    for (int k = 0; k < L; ++k) {
+        double wv = bestv;
+        int wi = besti;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(FULL, wv, o);
+            const int oi = __shfl_xor_sync(FULL, wi, o);
+            const bool take = (oi != NONE) && (wi == NONE || ov > wv || (ov == wv && oi < wi));
+            if (take) {
+                wv = ov;
+                wi = oi;
+            }
+        }
+        if (lane == 0) out[k] = (wi == NONE) ? -inf_f64() : wv;
+        if (wi != NONE && wi == besti) {
+            lastv = wv;
+            lasti = wi;
+            rescan();
+        }
+    }
+}
+
+// ---- generalised Pareto fit, literal -------------------------------------------------------------
+// pyloo/psis.py:181-208 evaluated operation by operation on ary[0..n) IN THE ORDER GIVEN, by one warp.
+// k_hat (e_loo.py:357,377,383) hands it descending tails whose last element is 0, so 1/ary[-1] is inf, the
+// whole profile is NaN, every grid weight is dropped, b_post = 0 and the result is 5/(n+10); running the
+// same arithmetic (IEEE division, NaN-propagating log1p/exp) reproduces that without special cases.
+// bs, ls: shared scratch of 64 doubles each (m_est = 30 + floor(sqrt(n)) <= 41 for n <= 128).
+__device__ __forceinline__ double gpdfit_literal_warp(const double* ary, int n, double* bs, double* ls,
+                                                      int lane) {
+    const int m = 30 + (int)sqrt((double)n);
+    int q = (int)((double)n / 4.0 + 0.5) - 1;
+    if (q < 0) q += n;
+    const double aq = ary[q], an = ary[n - 1];
+    for (int j = lane; j < m; j += 32) {
+        double b = 1.0 - sqrt((double)m / ((double)(j + 1) - 0.5));
+        b /= 3.0 * aq;
+        b += 1.0 / an;
+        double acc = 0.0;
+        for (int i = 0; i < n; ++i) acc += log1p(-b * ary[i]);
+        const double k = acc / (double)n;
+        bs[j] = b;
+        ls[j] = (double)n * (log(-(b / k)) - k - 1.0);
+    }
+    __syncwarp();
+    double w[2];
+    bool keep[2];
+    double wsum = 0.0;
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+        const int j = lane + 32 * jj;
+        w[jj] = 0.0;
+        keep[jj] = false;
+        if (j < m) {
+            double d = 0.0;
+            for (int l = 0; l < m; ++l) d += exp(ls[l] - ls[j]);
+            w[jj] = 1.0 / d;
+            keep[jj] = (w[jj] >= 10.0 * 2.220446049250313e-16);
+            if (keep[jj]) wsum += w[jj];
+        }
+    }
+    wsum = warp_sum(wsum);
+    double bp = 0.0;
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj)
+        if (keep[jj]) bp += bs[lane + 32 * jj] * (w[jj] / wsum);
+    const double b_post = warp_sum(bp);
+    double acc = 0.0;
+    for (int i = lane; i < n; i += 32) acc += log1p(-b_post * ary[i]);
+    const double k_post = warp_sum(acc) / (double)n;
+    __syncwarp();
+    return ((double)n * k_post + 5.0) / ((double)n + 10.0);
+}
+
+struct ElooSmem {
+    int row_words;  // padded S
+    int n_rows_staged;
+    __host__ __device__ static size_t bytes(int S, int n_staged) {
+        const size_t spad = (size_t)((S + 1) & ~1);
+        // red + staged rows + candidates (3 tails x 8 warps x L) + tails (3 x L) + gpd scratch (3 x 128)
+        return sizeof(double) * (IS_RED_WORDS + spad * n_staged + 3 * IS_NW * ELOO_MAX_TAIL +
+                                 3 * ELOO_MAX_TAIL + 3 * 128 + 8);
+    }
+};
+
+template <bool STAGED>
+__global__ void __launch_bounds__(IS_NT) eloo_row_kernel(const ElooParams p) {
+    extern __shared__ __align__(16) unsigned char is_smem[];
+    double* red = reinterpret_cast<double*>(is_smem);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(red + 128);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, S = p.S;
+    const int spad = (S + 1) & ~1;
+    const bool has_x = (p.x != nullptr) && (p.type != ELOO_NONE);
+    const bool lr_same = (p.lr == p.lw) && (p.lr_stride == p.lw_stride);
+    double* sm = red + IS_RED_WORDS;
+    double *bx = nullptr, *blw = nullptr, *blr = nullptr;
+    if (STAGED) {
+        blw = sm; sm += spad;
+        if (!lr_same) { blr = sm; sm += spad; } else blr = blw;
+        if (has_x) { bx = sm; sm += spad; }
+    }
+    double* cand = sm;                               // [3][IS_NW][L]
+    double* tails = cand + 3 * IS_NW * ELOO_MAX_TAIL;  // [3][L]
+    double* gpd = tails + 3 * ELOO_MAX_TAIL;           // [3][128]
+    double* res = gpd + 3 * 128;                       // [3] khat per tail
+    if (STAGED && p.bulk && tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    uint32_t parity = 0;
+    const int L = p.tail_len;
+    const int n_tail = (L < S) ? L : S;
+
+    for (long long row = blockIdx.x; row < p.n_rows; row += gridDim.x) {
+        const double* gx = has_x ? p.x + row * p.x_stride : nullptr;
+        const double* glw = p.lw + row * p.lw_stride;
+        const double* glr = p.lr + row * p.lr_stride;
+        if (STAGED) {
+            double* dsts[3];
+            const double* srcs[3];
+            int na = 0;
+            dsts[na] = blw; srcs[na++] = glw;
+            if (!lr_same) { dsts[na] = blr; srcs[na++] = glr; }
+            if (has_x) { dsts[na] = bx; srcs[na++] = gx; }
+            stage_rows<true>(dsts, srcs, na, S, p.bulk, bar, parity);
+        }
+        const double* X = STAGED ? bx : gx;
+        const double* LW = STAGED ? blw : glw;
+        const double* LR = STAGED ? blr : glr;
+        double* HR = STAGED ? bx : p.scratch + (long long)blockIdx.x * spad;  // h * r, in place when staged
+
+        // ---- pass 1: maxima and the degeneracy tests on h = x (mean) or x^2 (variance, sd; e_loo.py:234-239)
+        // for k_hat (e_loo.py:359-365) and on x for the weighted variance (e_loo.py:520)
+        const bool sq = (p.type != ELOO_MEAN);
+        const double x0 = has_x ? X[0] : 0.0;
+        const double h0 = sq ? x0 * x0 : x0;
+        double lwmax = -inf_f64(), lrmax = -inf_f64(), nemin = inf_f64(), nemax = -inf_f64();
+        // 1 NaN in lw, 2 NaN in lr, 4 h not finite, 8 h not all close to h[0], 16 some h != h[0],
+        // 32 x not all close to x[0]
+        int flags = 0;
+        for (int s = tid; s < S; s += IS_NT) {
+            const double a = LW[s], b = LR[s];
+            flags |= (a != a) ? 1 : 0;
+            flags |= (b != b) ? 2 : 0;
+            lwmax = fmax(lwmax, a);
+            lrmax = fmax(lrmax, b);
+            if (has_x) {
+                const double xv = X[s];
+                const double hv = sq ? xv * xv : xv;
+                if (!is_finite(hv)) flags |= 4;
+                if (!np_isclose(hv, h0)) flags |= 8;
+                if (!np_isclose(xv, x0)) flags |= 32;
+                if (hv != h0) {
+                    flags |= 16;
+                    nemin = fmin(nemin, hv);
+                    nemax = fmax(nemax, hv);
+                }
+            }
+        }
+        lwmax = block_max<IS_NT>(lwmax, red);
+        lrmax = block_max<IS_NT>(lrmax, red);
+        if (has_x) {
+            nemin = block_min<IS_NT>(nemin, red);
+            nemax = block_max<IS_NT>(nemax, red);
+        }
+        flags = block_or(flags, red);
+        if (flags & 1) lwmax = nan_f64();
+        if (flags & 2) lrmax = nan_f64();
+        const bool x_close = has_x && !(flags & 32);
+        const bool h_close = has_x && !(flags & 8);
+        const bool h_two = has_x && (flags & 16) && (nemin == nemax);  // len(np.unique(h)) == 2
+        const bool h_bad = has_x && (flags & 4);
+        const bool need_hr = has_x && !h_close && !h_two && !h_bad && is_finite(lrmax);
+
+        // ---- pass 2: weighted sums (e_loo.py:429-463) and h * r (e_loo.py:368)
+        double se = 0.0, sex = 0.0, sexx = 0.0, see = 0.0;
+        if (has_x) {
+            for (int s = tid; s < S; s += IS_NT) {
+                const double xv = X[s];
+                const double e = exp(LW[s] - lwmax);
+                se += e;
+                sex += e * xv;
+                sexx += e * (xv * xv);
+                see += e * e;
+                if (need_hr) HR[s] = (sq ? xv * xv : xv) * exp(LR[s] - lrmax);
+            }
+            se = block_sum<IS_NT>(se, red);
+            sex = block_sum<IS_NT>(sex, red);
+            if (p.type != ELOO_MEAN) {
+                sexx = block_sum<IS_NT>(sexx, red);
+                see = block_sum<IS_NT>(see, red);
+            }
+        }
+        __syncthreads();  // HR complete
+
+        // ---- k_hat: tails of r and of h * r (e_loo.py:350-390)
+        const bool r_ok = is_finite(lrmax);
+        if (r_ok) warp_top<false>(LR, S, tid, IS_NT, n_tail, cand + (0 * IS_NW + warp) * ELOO_MAX_TAIL, lane);
+        if (need_hr) {
+            warp_top<true>(HR, S, tid, IS_NT, n_tail, cand + (1 * IS_NW + warp) * ELOO_MAX_TAIL, lane);
+            warp_top<false>(HR, S, tid, IS_NT, n_tail, cand + (2 * IS_NW + warp) * ELOO_MAX_TAIL, lane);
+        }
+        __syncthreads();
+        if (warp < 3 && ((warp == 0 && r_ok) || (warp > 0 && need_hr))) {
+            double* tl = tails + warp * ELOO_MAX_TAIL;
+            // the candidates of warp w sit at [w * ELOO_MAX_TAIL, w * ELOO_MAX_TAIL + n_tail): compact view by index map
+            // (select over all IS_NW * ELOO_MAX_TAIL slots; unused slots were never written, so mask them)
+            {
+                constexpr int NONE = 0x7fffffff;
+                const double* cb = cand + warp * IS_NW * ELOO_MAX_TAIL;
+                double lastv = inf_f64();
+                int lasti = -1;
+                double bestv;
+                int besti;
+                auto rescan = [&]() {
+                    bestv = -inf_f64();
+                    besti = NONE;
+                    for (int c = lane; c < IS_NW * n_tail; c += 32) {
+                        const int s = (c / n_tail) * ELOO_MAX_TAIL + (c % n_tail);
+                        const double v = cb[s];
+                        const bool eligible = (v < lastv) || (v == lastv && s > lasti);
+                        if (eligible && (besti == NONE || v > bestv)) {
+                            bestv = v;
+                            besti = s;
+                        }
+                    }
+                };
+                rescan();
+                for (int k = 0; k < n_tail; ++k) {
+                    double wv = bestv;
+                    int wi = besti;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const double ov = __shfl_xor_sync(FULL, wv, o);
+                        const int oi = __shfl_xor_sync(FULL, wi, o);
+                        const bool take = (oi != NONE) && (wi == NONE || ov > wv || (ov == wv && oi < wi));
+                        if (take) {
+                            wv = ov;
+                            wi = oi;
+                        }
+                    }
+                    if (lane == 0) tl[k] = wv;
+                    if (wi != NONE && wi == besti) {
+                        lastv = wv;
+                        lasti = wi;
+                        rescan();
+                    }
+                }
+            }
+            __syncwarp();
+            // tail values in the reference's order, then its degeneracy test and the fit argument
+            // warp 0: sorted_r descending (e_loo.py:351); warp 1: left tail ascending (:370); warp 2: right
+            // tail descending (:371)
+            const double first = (warp == 0) ? exp(tl[0] - lrmax) : (warp == 1 ? -tl[0] : tl[0]);
+            __syncwarp();
+            int far = 0;
+            for (int i = lane; i < n_tail; i += 32) {
+                double v = tl[i];
+                v = (warp == 0) ? exp(v - lrmax) : (warp == 1 ? -v : v);
+                if (!np_isclose(v, first)) far = 1;
+                tl[i] = v;
+            }
+            far = __any_sync(FULL, far);
+            __syncwarp();
+            double kh;
+            if (n_tail < 5 || !far) {
+                kh = (warp == 0) ? inf_f64() : -inf_f64();  // e_loo.py:353-354, :373-374, :379-380
+            } else {
+                const double cutoff = tl[n_tail - 1];
+                __syncwarp();
+                for (int i = lane; i < n_tail; i += 32) {
+                    const double d = tl[i] - cutoff;
+                    tl[i] = (warp == 1) ? -d : d;  // e_loo.py:357, :377, :383
+                }
+                __syncwarp();
+                kh = gpdfit_literal_warp(tl, n_tail, gpd + warp * 128, gpd + warp * 128 + 64, lane);
+            }
+            if (lane == 0) res[warp] = kh;
+        }
+        __syncthreads();
+
+        if (tid == 0) {
+            // np.max propagates NaN: r is all-NaN, every fit returns NaN (e_loo.py:387-388).  A +inf maximum
+            // leaves r = 0 on every finite draw: the r tail is all-close => +inf.
+            double khat_r = r_ok ? res[0] : ((lrmax == inf_f64()) ? inf_f64() : nan_f64());
+            double khat = khat_r;
+            if (need_hr) {
+                const double khat_hr = py_max(res[1], res[2]);
+                khat = (khat_hr != khat_hr && khat_r != khat_r) ? nan_f64() : py_max(khat_hr, khat_r);
+            }
+            p.khat[row] = khat;
+            if (has_x) {
+                const double mean = sex / se;
+                double val = mean;
+                if (p.type != ELOO_MEAN) {
+                    const double wss = see / (se * se);
+                    if (x_close) val = 0.0;                       // e_loo.py:520-521
+                    else if (np_isclose(wss, 1.0)) val = 0.0;     // e_loo.py:523-525
+                    else {
+                        const double var = (sexx / se - mean * mean) / (1.0 - wss);
+                        val = (0.0 > var) ? 0.0 : var;            // max(var, 0.0)
+                    }
+                    if (p.type == ELOO_SD) val = sqrt(val);
+                }
+                p.value[row] = val;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ===================================================================================== host side
+static size_t is_smem_bytes(int S) { return sizeof(double) * (IS_RED_WORDS + (size_t)((S + 1) & ~1)); }
+constexpr size_t SMEM_LIMIT = 227 * 1024;
+
+template <typename K>
+static cudaError_t plan_kernel(K kern, size_t smem, long long n_rows, int* info) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int occ = 0, dev = 0, sms = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, IS_NT, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) return cudaErrorInvalidConfiguration;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long cap = (long long)sms * occ;
+    info[1] = (int)(n_rows < cap ? (n_rows > 0 ? n_rows : 1) : cap);
+    info[2] = (int)smem;
+    info[3] = occ;
+    return cudaSuccess;
+}
+
+template <int METHOD, int MODE>
+static cudaError_t is_plan_t(int S, long long n_rows, int* info) {
+    const size_t staged = is_smem_bytes(S);
+    if (staged <= SMEM_LIMIT) {
+        info[0] = 1;
+        return plan_kernel(is_row_kernel<METHOD, MODE, true>, staged, n_rows, info);
+    }
+    info[0] = 0;
+    return plan_kernel(is_row_kernel<METHOD, MODE, false>, sizeof(double) * IS_RED_WORDS, n_rows, info);
+}
+
+cudaError_t is_plan(int method, int mode, int S, long long n_rows, int* info) {
+    if (method == IS_METHOD_SIS)
+        return mode == IS_MODE_WEIGHTS ? is_plan_t<IS_METHOD_SIS, IS_MODE_WEIGHTS>(S, n_rows, info)
+                                       : is_plan_t<IS_METHOD_SIS, IS_MODE_LOO>(S, n_rows, info);
+    return mode == IS_MODE_WEIGHTS ? is_plan_t<IS_METHOD_TIS, IS_MODE_WEIGHTS>(S, n_rows, info)
+                                   : is_plan_t<IS_METHOD_TIS, IS_MODE_LOO>(S, n_rows, info);
+}
+
+template <int METHOD, int MODE>
+static cudaError_t is_launch_t(const IsParams& p, cudaStream_t st) {
+    int info[4];
+    cudaError_t e = is_plan_t<METHOD, MODE>(p.S, p.n_rows, info);
+    if (e != cudaSuccess) return e;
+    if (info[0]) is_row_kernel<METHOD, MODE, true><<<info[1], IS_NT, info[2], st>>>(p);
+    else is_row_kernel<METHOD, MODE, false><<<info[1], IS_NT, info[2], st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t is_launch(int method, int mode, const IsParams& p, cudaStream_t st) {
+    if (method == IS_METHOD_SIS)
+        return mode == IS_MODE_WEIGHTS ? is_launch_t<IS_METHOD_SIS, IS_MODE_WEIGHTS>(p, st)
+                                       : is_launch_t<IS_METHOD_SIS, IS_MODE_LOO>(p, st);
+    return mode == IS_MODE_WEIGHTS ? is_launch_t<IS_METHOD_TIS, IS_MODE_WEIGHTS>(p, st)
+                                   : is_launch_t<IS_METHOD_TIS, IS_MODE_LOO>(p, st);
+}
+
+cudaError_t eloo_plan(int S, long long n_rows, bool lr_same, bool has_x, int* info) {
+    const int n_staged = 1 + (lr_same ? 0 : 1) + (has_x ? 1 : 0);
+    const size_t staged = ElooSmem::bytes(S, n_staged);
+    if (staged <= SMEM_LIMIT) {
+        info[0] = 1;
+        return plan_kernel(eloo_row_kernel<true>, staged, n_rows, info);
+    }
+    info[0] = 0;
+    return plan_kernel(eloo_row_kernel<false>, ElooSmem::bytes(0, 0), n_rows, info);
+}
+
+cudaError_t eloo_launch(const ElooParams& p, cudaStream_t st) {
+    int info[4];
+    const bool lr_same = (p.lr == p.lw) && (p.lr_stride == p.lw_stride);
+    const bool has_x = (p.x != nullptr) && (p.type != ELOO_NONE);
+    cudaError_t e = eloo_plan(p.S, p.n_rows, lr_same, has_x, info);
+    if (e != cudaSuccess) return e;
+    if (info[0]) eloo_row_kernel<true><<<info[1], IS_NT, info[2], st>>>(p);
+    else eloo_row_kernel<false><<<info[1], IS_NT, info[2], st>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace b2l

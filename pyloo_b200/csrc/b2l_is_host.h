@@ -1,0 +1,55 @@
+// Host-side interface between the C-ABI translation unit and b2l_is.cu (SIS / TIS importance weights and
+// the e_loo weighted expectations: the consumers either side of psislw).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace b2l {
+
+constexpr int IS_METHOD_SIS = 1;  // pyloo/sis.py:86-106
+constexpr int IS_METHOD_TIS = 2;  // pyloo/tis.py:91-120
+constexpr int IS_MODE_WEIGHTS = 0;  // write the normalised log weights + ess (compute_importance_weights)
+constexpr int IS_MODE_LOO = 1;      // input is the log-likelihood; write elpd_i, ess_i, lppd_i (pyloo/loo.py:286-337)
+
+struct IsParams {
+    const double* in;  // rows of S doubles, element stride 1
+    long long in_stride;
+    double* out;  // weights mode: rows of S doubles
+    long long out_stride;
+    double* ess;                  // N
+    double* elpd;                 // loo mode: N
+    double* lppd;                 // loo mode: N
+    unsigned long long* counters; // loo mode, nullable: NaN / +inf / -inf inputs
+    long long n_rows;
+    int S;
+    int bulk;      // rows may be staged with 1-D bulk TMA (S even, 16 B aligned base and stride)
+    double log_S;  // np.log(n_samples), computed by the host like the reference does
+};
+
+constexpr int ELOO_MEAN = 0, ELOO_VARIANCE = 1, ELOO_SD = 2, ELOO_NONE = 3;
+constexpr int ELOO_MAX_TAIL = 128;
+
+struct ElooParams {
+    const double* x;  // nullable (type NONE): h(theta) rows
+    long long x_stride;
+    const double* lw;  // log weights rows (any normalisation)
+    long long lw_stride;
+    const double* lr;  // raw log ratios rows; == lw when the caller has none
+    long long lr_stride;
+    double* value;    // N (unused for type NONE)
+    double* khat;     // N
+    double* scratch;  // unstaged mode: one row of S doubles per CTA for h * r
+    long long n_rows;
+    int S;
+    int type;
+    int tail_len;
+    int bulk;
+};
+
+// Launch planners + launchers.  `*_info`: [0] staged in shared memory, [1] grid, [2] dynamic smem bytes,
+// [3] CTAs per SM.  The e_loo launcher needs `scratch` only when info[0] == 0.
+cudaError_t is_plan(int method, int mode, int S, long long n_rows, int* info);
+cudaError_t is_launch(int method, int mode, const IsParams& p, cudaStream_t st);
+cudaError_t eloo_plan(int S, long long n_rows, bool lr_same, bool has_x, int* info);
+cudaError_t eloo_launch(const ElooParams& p, cudaStream_t st);
+
+}  // namespace b2l

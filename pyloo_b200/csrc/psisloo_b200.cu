@@ -14,6 +14,7 @@
 #include "../../include/psisloo_b200.h"
 #include "b2l_row_kernel.cuh"
 #include "b2l_split_host.h"
+#include "b2l_is_host.h"
 
 using namespace b2l;
 
@@ -742,6 +743,113 @@ extern "C" int b2l_stats_merge(const double* shards, int32_t n_shards, double* m
     out[B2L_ST_N] = e.n; out[B2L_ST_ELPD_MEAN] = e.mean; out[B2L_ST_ELPD_M2] = e.m2;
     out[B2L_ST_WAIC_MEAN] = w.mean; out[B2L_ST_WAIC_M2] = w.m2;
     memcpy(merged, out, sizeof(out));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ SIS / TIS / e_loo
+static bool bulk_ok(long long S, const void* base, long long stride) {
+    return (S % 2 == 0) && aligned16(base) && (stride % 2 == 0) && (S * 8 < (1ll << 20));
+}
+static long long is_panel_obs(long long S, long long N) {
+    long long p = 148ll * 32;
+    while (p > 148 && p * S * 8 > (1ll << 29)) p /= 2;
+    return std::min(p, std::max<long long>(N, 1));
+}
+
+extern "C" int b2l_islw_dev_f64(const double* lw, int64_t S, int64_t N, int64_t stride_n, int32_t method,
+                                double* lw_out, int64_t ostride_n, double* ess_out, void* stream) {
+    if (!lw || !lw_out || !ess_out || N < 0 || S < 1) return fail(B2L_E_INVALID, "null pointer or bad size");
+    if (method != B2L_IS_SIS && method != B2L_IS_TIS) return fail(B2L_E_INVALID, "method must be B2L_IS_SIS or B2L_IS_TIS");
+    if (S > INT32_MAX) return fail(B2L_E_UNSUPPORTED, "S too large");
+    if (N == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    IsParams p;
+    memset(&p, 0, sizeof(p));
+    p.in = lw; p.in_stride = stride_n; p.out = lw_out; p.out_stride = ostride_n; p.ess = ess_out;
+    p.n_rows = N; p.S = (int)S; p.bulk = bulk_ok(S, lw, stride_n); p.log_S = std::log((double)S);
+    ProfScope prof(B2L_PROF_IS, st);
+    CK(is_launch(method, IS_MODE_WEIGHTS, p, st));
+    return 0;
+}
+
+extern "C" int b2l_is_workspace_bytes(int64_t S, int64_t N, int32_t layout_obs_fastest, size_t* out_bytes) {
+    if (!out_bytes || S < 1 || N < 0) return fail(B2L_E_INVALID, "bad arguments");
+    *out_bytes = layout_obs_fastest ? align_up((size_t)is_panel_obs(S, N) * (size_t)S * 8, 256) : 0;
+    return 0;
+}
+
+extern "C" int b2l_loo_is_dev_f64(const double* ll, int64_t S, int64_t N, int64_t stride_s, int64_t stride_n,
+                                  int32_t method, double* elpd_i, double* ess_i, double* lppd_i,
+                                  unsigned long long* counters, void* ws, size_t ws_bytes, void* stream) {
+    if (!ll || !elpd_i || !ess_i || !lppd_i || N < 0 || S < 1) return fail(B2L_E_INVALID, "null pointer or bad size");
+    if (method != B2L_IS_SIS && method != B2L_IS_TIS) return fail(B2L_E_INVALID, "method must be B2L_IS_SIS or B2L_IS_TIS");
+    if (S > INT32_MAX) return fail(B2L_E_UNSUPPORTED, "S too large");
+    if (N == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    IsParams p;
+    memset(&p, 0, sizeof(p));
+    p.S = (int)S; p.log_S = std::log((double)S); p.counters = counters;
+    if (stride_s == 1 || S == 1) {
+        p.in = ll; p.in_stride = stride_n; p.n_rows = N; p.bulk = bulk_ok(S, ll, stride_n);
+        p.elpd = elpd_i; p.ess = ess_i; p.lppd = lppd_i;
+        ProfScope prof(B2L_PROF_IS, st);
+        CK(is_launch(method, IS_MODE_LOO, p, st));
+        return 0;
+    }
+    if (stride_n != 1 && N != 1) return fail(B2L_E_INVALID, "one of (stride_s, stride_n) must be 1");
+    const long long P = is_panel_obs(S, N);
+    const size_t need = align_up((size_t)P * (size_t)S * 8, 256);
+    if (!ws || ws_bytes < need) return fail(B2L_E_WORKSPACE, "workspace too small: need %zu bytes", need);
+    double* panel = reinterpret_cast<double*>(ws);
+    for (long long i0 = 0; i0 < N; i0 += P) {
+        const long long np = std::min<long long>(P, N - i0);
+        int rc = launch_transpose(ll + i0, stride_s, panel, S, S, np, st);  // (S x np) -> (np x S)
+        if (rc) return rc;
+        p.in = panel; p.in_stride = S; p.n_rows = np; p.bulk = bulk_ok(S, panel, S);
+        p.elpd = elpd_i + i0; p.ess = ess_i + i0; p.lppd = lppd_i + i0;
+        ProfScope prof(B2L_PROF_IS, st);
+        CK(is_launch(method, IS_MODE_LOO, p, st));
+    }
+    return 0;
+}
+
+extern "C" int b2l_eloo_workspace_bytes(int64_t S, int64_t N, int32_t has_lr, int32_t type, size_t* out_bytes) {
+    if (!out_bytes || S < 1 || N < 0 || S > INT32_MAX) return fail(B2L_E_INVALID, "bad arguments");
+    int info[4] = {0, 0, 0, 0};
+    CK(eloo_plan((int)S, std::max<long long>(N, 1), !has_lr, type != B2L_ELOO_NONE, info));
+    *out_bytes = info[0] ? 0 : align_up((size_t)info[1] * (size_t)((S + 1) & ~1ll) * 8, 256);
+    return 0;
+}
+
+extern "C" int b2l_eloo_dev_f64(const double* x, int64_t x_stride_n, const double* lw, int64_t lw_stride_n,
+                                const double* lr, int64_t lr_stride_n, int64_t S, int64_t N, int32_t type,
+                                int32_t tail_len, double* value_out, double* khat_out, void* ws,
+                                size_t ws_bytes, void* stream) {
+    if (!lw || !khat_out || N < 0 || S < 1) return fail(B2L_E_INVALID, "null pointer or bad size");
+    if (type < B2L_ELOO_MEAN || type > B2L_ELOO_NONE) return fail(B2L_E_INVALID, "bad expectation type %d", type);
+    if (type != B2L_ELOO_NONE && (!x || !value_out)) return fail(B2L_E_INVALID, "x and value_out are required");
+    if (tail_len < 5) return fail(B2L_E_INVALID, "tail_len must be at least 5");  // e_loo.py:295-296
+    if (tail_len > ELOO_MAX_TAIL) return fail(B2L_E_UNSUPPORTED, "tail_len > %d", ELOO_MAX_TAIL);
+    if (S > INT32_MAX) return fail(B2L_E_UNSUPPORTED, "S too large");
+    if (N == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    ElooParams p;
+    memset(&p, 0, sizeof(p));
+    p.x = (type == B2L_ELOO_NONE) ? nullptr : x; p.x_stride = x_stride_n;
+    p.lw = lw; p.lw_stride = lw_stride_n;
+    p.lr = lr ? lr : lw; p.lr_stride = lr ? lr_stride_n : lw_stride_n;
+    p.value = value_out; p.khat = khat_out; p.n_rows = N; p.S = (int)S; p.type = type; p.tail_len = tail_len;
+    p.bulk = bulk_ok(S, lw, lw_stride_n) && bulk_ok(S, p.lr, p.lr_stride) && (!p.x || bulk_ok(S, p.x, x_stride_n));
+    int info[4] = {0, 0, 0, 0};
+    const bool lr_same = (p.lr == p.lw) && (p.lr_stride == p.lw_stride);
+    CK(eloo_plan((int)S, N, lr_same, p.x != nullptr, info));
+    if (!info[0]) {
+        const size_t need = align_up((size_t)info[1] * (size_t)((S + 1) & ~1ll) * 8, 256);
+        if (!ws || ws_bytes < need) return fail(B2L_E_WORKSPACE, "workspace too small: need %zu bytes", need);
+        p.scratch = reinterpret_cast<double*>(ws);
+    }
+    ProfScope prof(B2L_PROF_ELOO, st);
+    CK(eloo_launch(p, st));
     return 0;
 }
 

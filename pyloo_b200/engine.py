@@ -300,3 +300,175 @@ def row_launch_info(S: int, M: int, mode: str = "psislw") -> dict:
     _native.check(lib.b2l_row_launch_info(S, M, 0 if mode == "psislw" else 1, *[ctypes.byref(v) for v in vals]))
     keys = ("grid", "block", "smem_bytes", "ctas_per_sm", "nbuf")
     return {k: int(v.value) for k, v in zip(keys, vals)}
+
+
+# --------------------------------------------------------------------------------- SIS / TIS / e_loo
+_IS_METHODS = {"sis": _native.IS_SIS, "tis": _native.IS_TIS}
+_CHUNK_BYTES = 1 << 30  # host arrays are staged through the GPU in slabs of about this size
+
+
+def _method_code(method) -> int:
+    name = getattr(method, "value", method)
+    try:
+        return _IS_METHODS[str(name).lower()]
+    except KeyError:
+        raise ValueError(f"method must be 'sis' or 'tis' on this entry point, not {name!r}") from None
+
+
+def islw_cuda(lw, method, *, out=None):
+    """SIS / TIS normalised log weights of a device-resident float64 ``(N, S)`` tensor with contiguous
+    rows (pyloo/sis.py:86-106, pyloo/tis.py:91-120).  Asynchronous.  Returns ``(lw_out, ess)``."""
+    torch = _torch()
+    lib = _native.load()
+    if lw.dtype != torch.float64 or lw.dim() != 2 or not lw.is_cuda:
+        raise ValueError("expected a 2-D float64 CUDA tensor")
+    N, S = lw.shape
+    if S > 1 and lw.stride(1) != 1:
+        lw = lw.contiguous()
+    if out is None:
+        out = torch.empty((N, S), dtype=torch.float64, device=lw.device)
+    ess = torch.empty(N, dtype=torch.float64, device=lw.device)
+    with torch.cuda.device(lw.device):
+        rc = lib.b2l_islw_dev_f64(lw.data_ptr(), S, N, lw.stride(0), _method_code(method), out.data_ptr(),
+                                  out.stride(0), ess.data_ptr(), _stream_ptr(torch, lw.device))
+    _native.check(rc)
+    return out, ess
+
+
+def loo_is_cuda(ll_sn, method, *, counters=None, workspace=None):
+    """Pointwise LOO with SIS / TIS weights on a device-resident float64 ``(S, N)`` log-likelihood
+    (obs-fastest ArviZ layout or a transposed row-contiguous view).  Asynchronous.
+    Returns dict of device tensors ``elpd_i, ess_i, lppd_i, counters``."""
+    torch = _torch()
+    lib = _native.load()
+    if ll_sn.dtype != torch.float64 or ll_sn.dim() != 2 or not ll_sn.is_cuda:
+        raise ValueError("expected a 2-D float64 CUDA tensor")
+    S, N = ll_sn.shape
+    ss, sn = ll_sn.stride()
+    if not (ss == 1 or sn == 1 or N == 1 or S == 1):
+        ll_sn = ll_sn.contiguous()
+        ss, sn = ll_sn.stride()
+    dev = ll_sn.device
+    outs = [torch.empty(N, dtype=torch.float64, device=dev) for _ in range(3)]
+    if counters is None:
+        counters = torch.zeros(4, dtype=torch.int64, device=dev)
+    if workspace is None:
+        need = ctypes.c_size_t(0)
+        _native.check(lib.b2l_is_workspace_bytes(S, N, 0 if (ss == 1 or S == 1) else 1, ctypes.byref(need)))
+        workspace = torch.empty(max(int(need.value), 256), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.b2l_loo_is_dev_f64(ll_sn.data_ptr(), S, N, ss, sn, _method_code(method),
+                                    *[o.data_ptr() for o in outs], counters.data_ptr(), workspace.data_ptr(),
+                                    workspace.numel(), _stream_ptr(torch, dev))
+    _native.check(rc)
+    return {"elpd_i": outs[0], "ess_i": outs[1], "lppd_i": outs[2], "counters": counters, "n_samples": S}
+
+
+def eloo_cuda(x, lw, lr=None, kind: str = "mean", tail_len: int = 20, *, workspace=None):
+    """Weighted expectation of ``x`` under log weights ``lw`` with the function-specific Pareto k
+    (pyloo/e_loo.py:429-463, :328-390) for device-resident float64 ``(N, S)`` tensors with contiguous rows.
+    ``kind``: ``mean`` / ``variance`` / ``sd`` / ``none`` (k of the ratios only; ``x`` may be None).
+    Asynchronous.  Returns ``(value or None, khat)``."""
+    torch = _torch()
+    lib = _native.load()
+    code = _native.ELOO_TYPES[kind]
+
+    def rows(t):
+        if t is None:
+            return None
+        if t.dtype != torch.float64 or t.dim() != 2 or not t.is_cuda:
+            raise ValueError("expected 2-D float64 CUDA tensors")
+        return t if (t.shape[1] == 1 or t.stride(1) == 1) else t.contiguous()
+
+    x, lw, lr = rows(x if code != 3 else None), rows(lw), rows(lr)
+    N, S = lw.shape
+    for t in (x, lr):
+        if t is not None and tuple(t.shape) != (N, S):
+            raise ValueError("x, log_weights and log_ratios must have the same shape")
+    dev = lw.device
+    value = torch.empty(N, dtype=torch.float64, device=dev) if code != 3 else None
+    khat = torch.empty(N, dtype=torch.float64, device=dev)
+    if workspace is None:
+        need = ctypes.c_size_t(0)
+        _native.check(lib.b2l_eloo_workspace_bytes(S, N, 0 if lr is None else 1, code, ctypes.byref(need)))
+        workspace = torch.empty(max(int(need.value), 256), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.b2l_eloo_dev_f64(x.data_ptr() if x is not None else None, x.stride(0) if x is not None else 0,
+                                  lw.data_ptr(), lw.stride(0), lr.data_ptr() if lr is not None else None,
+                                  lr.stride(0) if lr is not None else 0, S, N, code, int(tail_len),
+                                  value.data_ptr() if value is not None else None, khat.data_ptr(),
+                                  workspace.data_ptr(), workspace.numel(), _stream_ptr(torch, dev))
+    _native.check(rc)
+    return value, khat
+
+
+def _slabs(N: int, row_bytes: int):
+    step = max(1, min(N, _CHUNK_BYTES // max(row_bytes, 1)))
+    for i0 in range(0, N, step):
+        yield i0, min(N, i0 + step)
+
+
+def _dev(device):
+    torch = _torch()
+    return torch.device("cuda", current_device() if device is None else int(device))
+
+
+def islw_host(lw_ns: np.ndarray, method, *, device=None):
+    """SIS / TIS on a HOST ``(N, S)`` array.  Returns ``(lw_out (N, S), ess (N,))``; input untouched."""
+    torch = _torch()
+    a = np.asarray(lw_ns, dtype=np.float64)
+    if a.ndim != 2:
+        raise ValueError("expected a 2-D array")
+    N, S = a.shape
+    out = np.empty((N, S), dtype=np.float64)
+    ess = np.empty(N, dtype=np.float64)
+    dev = _dev(device)
+    for i0, i1 in _slabs(N, 16 * S):
+        d_in = torch.from_numpy(np.ascontiguousarray(a[i0:i1])).to(dev)
+        d_out, d_ess = islw_cuda(d_in, method)
+        out[i0:i1] = d_out.cpu().numpy()
+        ess[i0:i1] = d_ess.cpu().numpy()
+    return out, ess
+
+
+def loo_is_host(ll_sn: np.ndarray, method, *, device=None):
+    """Pointwise SIS / TIS LOO on a HOST sample-major ``(S, N)`` log-likelihood.
+    Returns ``dict(elpd_i, ess_i, lppd_i, n_nan_in)`` of NumPy arrays (log scale)."""
+    torch = _torch()
+    a = _as_strided_f64_2d(ll_sn)
+    S, N = a.shape
+    res = {k: np.empty(N, dtype=np.float64) for k in ("elpd_i", "ess_i", "lppd_i")}
+    dev = _dev(device)
+    counters = torch.zeros(4, dtype=torch.int64, device=dev)
+    for i0, i1 in _slabs(N, 8 * S):
+        d_in = torch.from_numpy(np.ascontiguousarray(a[:, i0:i1])).to(dev)
+        r = loo_is_cuda(d_in, method, counters=counters)
+        for k in res:
+            res[k][i0:i1] = r[k].cpu().numpy()
+    res["n_nan_in"] = int(counters[0].item())
+    res["n_samples"] = S
+    return res
+
+
+def eloo_host(x_ns, lw_ns, lr_ns=None, kind: str = "mean", tail_len: int = 20, *, device=None):
+    """Weighted expectation + Pareto k on HOST ``(N, S)`` arrays.  Returns ``(value or None, khat)``."""
+    torch = _torch()
+    lw = np.asarray(lw_ns, dtype=np.float64)
+    if lw.ndim != 2:
+        raise ValueError("expected 2-D arrays")
+    N, S = lw.shape
+    x = None if (x_ns is None or kind == "none") else np.asarray(x_ns, dtype=np.float64)
+    lr = None if lr_ns is None else np.asarray(lr_ns, dtype=np.float64)
+    value = np.empty(N, dtype=np.float64) if x is not None else None
+    khat = np.empty(N, dtype=np.float64)
+    dev = _dev(device)
+
+    def up(arr, i0, i1):
+        return None if arr is None else torch.from_numpy(np.ascontiguousarray(arr[i0:i1])).to(dev)
+
+    for i0, i1 in _slabs(N, 24 * S):
+        v, k = eloo_cuda(up(x, i0, i1), up(lw, i0, i1), up(lr, i0, i1), kind, tail_len)
+        if value is not None:
+            value[i0:i1] = v.cpu().numpy()
+        khat[i0:i1] = k.cpu().numpy()
+    return value, khat

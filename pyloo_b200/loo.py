@@ -1,8 +1,8 @@
 """``loo`` -- PSIS-LOO-CV with the reference's signature and ELPDData output.
 
-Drop-in for the PSIS branch of ``pyloo.loo`` (reference: pyloo/loo.py:20-513).  What the reference
-does with five full-size NumPy temporaries and three per-observation Python loops
-(loo.py:286-289, :319-324, :329-337) is one fused GPU pass here; totals and standard errors come
+Drop-in for ``pyloo.loo`` with ``method`` in ``psis`` / ``sis`` / ``tis`` (reference: pyloo/loo.py:20-513).
+What the reference does with five full-size NumPy temporaries and three per-observation Python loops
+(loo.py:286-289, :319-324, :329-337) is one fused GPU pass here; for PSIS totals and standard errors come
 from the device-side statistics record (loo.py:326-342).
 """
 
@@ -35,9 +35,9 @@ def loo(data, pointwise=None, var_name=None, reff=None, scale=None, method="psis
         jacobian=None, mixture=False, **kwargs):
     """Pareto-smoothed importance sampling leave-one-out cross-validation (PSIS-LOO-CV).
 
-    Same parameters, errors, warnings and ``ELPDData`` rows as ``pyloo.loo`` for ``method="psis"``.
-    ``moment_match``, ``mixture`` and the SIS / TIS methods are outside the accelerated path and
-    raise ``NotImplementedError``.
+    Same parameters, errors, warnings and ``ELPDData`` rows as ``pyloo.loo`` for ``method`` in
+    ``"psis"`` / ``"sis"`` / ``"tis"``.  ``moment_match`` and ``mixture`` are outside the accelerated path
+    and raise ``NotImplementedError``.
     """
     idata = to_inference_data(data)
     log_lik = get_log_likelihood(idata, var_name=var_name)
@@ -64,8 +64,9 @@ def loo(data, pointwise=None, var_name=None, reff=None, scale=None, method="psis
     except ValueError:
         valid = ", ".join(m.value for m in ISMethod)
         raise ValueError(f"Invalid method '{method}'. Must be one of: {valid}")
-    if method != ISMethod.PSIS:
-        raise NotImplementedError(f"method={method.value!r}: only PSIS is built on the B200 path")
+    if method != ISMethod.PSIS:  # loo.py:235-244
+        warnings.warn(f"Using {method.value.upper()} for LOO computation. Note that PSIS is the recommended "
+                      "method as it is typically more efficient and reliable.", UserWarning, stacklevel=2)
     if mixture:
         raise NotImplementedError("mixture=True (Mix-IS-LOO) is outside the B200 hot path")
     if moment_match:
@@ -73,6 +74,10 @@ def loo(data, pointwise=None, var_name=None, reff=None, scale=None, method="psis
             raise ValueError("Moment matching requires pointwise LOO results. "
                              "Please set pointwise=True when using moment_match=True.")
         raise NotImplementedError("moment_match=True is outside the B200 hot path")
+
+    if method != ISMethod.PSIS:
+        return _loo_is(log_lik, ll_sn, obs_dims, obs_shape, method, sv, scale, pointwise, jacobian,
+                       n_samples, n_data_points)
 
     res = engine.loo_host(ll_sn, reff)
     st = res["stats"]
@@ -118,6 +123,10 @@ def loo(data, pointwise=None, var_name=None, reff=None, scale=None, method="psis
              ("pareto_k", k_da), ("good_k", good_k), ("subsample_size", n_data_points)]  # loo.py:599-624, :400-410
     result = ELPDData(data=[v for _, v in rows], index=[k for k, _ in rows])
 
+    return _apply_jacobian(result, jacobian, lppd, sv, n_data_points)
+
+
+def _apply_jacobian(result, jacobian, lppd, sv, n_data_points):
     if jacobian is not None:  # loo.py:414-439 (host-only add)
         adj = np.asarray(jacobian)
         if adj.shape != result["loo_i"].shape:
@@ -134,3 +143,44 @@ def loo(data, pointwise=None, var_name=None, reff=None, scale=None, method="psis
         result["looic"] = -2 * total
         result["looic_se"] = 2 * total_se
     return result
+
+
+def _loo_is(log_lik, ll_sn, obs_dims, obs_shape, method, sv, scale, pointwise, jacobian, n_samples,
+            n_data_points):
+    """SIS / TIS branch (loo.py:286-289, :305-342): the pointwise pass runs on the GPU, the totals are the
+    reference's NumPy reductions over the N pointwise values."""
+    res = engine.loo_is_host(ll_sn, method.value)
+    if res["n_nan_in"] > 0:  # loo.py:218-227
+        warnings.warn("NaN values detected in log-likelihood. These will be ignored in the LOO calculation.",
+                      UserWarning, stacklevel=3)
+    warn_mg = False
+    min_ess = np.min(res["ess_i"])
+    if min_ess < n_samples * 0.1:  # loo.py:306-317
+        warnings.warn(f"Low effective sample size detected (minimum ESS: {min_ess:.1f}). This indicates that "
+                      "the importance sampling approximation may be unreliable. Consider using PSIS which "
+                      "is more robust to such cases.", UserWarning, stacklevel=3)
+        warn_mg = True
+    loo_i = sv * res["elpd_i"]
+    loo_lppd = loo_i.sum()                                   # loo.py:326
+    loo_lppd_se = (n_data_points * np.var(loo_i)) ** 0.5     # loo.py:327
+    lppd = np.sum(res["lppd_i"])                             # loo.py:329-337
+    p_loo = lppd - loo_lppd / sv                             # loo.py:339
+    p_loo_se = np.sqrt(np.sum(np.var(loo_i)))                # loo.py:340
+    looic = -2 * loo_lppd
+    looic_se = 2 * loo_lppd_se
+    rows = [("elpd_loo", loo_lppd), ("se", loo_lppd_se), ("p_loo", p_loo), ("p_loo_se", p_loo_se),
+            ("n_samples", n_samples), ("n_data_points", n_data_points), ("warning", warn_mg)]
+    if not pointwise:
+        rows += [("scale", scale), ("looic", looic), ("looic_se", looic_se),
+                 ("subsample_size", n_data_points)]  # no good_k row outside PSIS (loo.py:360-365)
+        return ELPDData(data=[v for _, v in rows], index=[k for k, _ in rows])
+    loo_i = loo_i.reshape(obs_shape)
+    if np.allclose(loo_i, loo_i.flat[0]):  # loo.py:377-382
+        warnings.warn("The point-wise LOO is the same with the sum LOO, please double check the Observed RV "
+                      "in your model to make sure it returns element-wise logp.", stacklevel=3)
+    loo_i_da = wrap_like(log_lik, loo_i, obs_dims, "loo_i")
+    ess_da = wrap_like(log_lik, res["ess_i"].reshape(obs_shape), obs_dims, "ess")
+    rows += [("loo_i", loo_i_da), ("scale", scale), ("looic", looic), ("looic_se", looic_se),
+             ("ess", ess_da), ("subsample_size", n_data_points)]  # loo.py:400-410
+    result = ELPDData(data=[v for _, v in rows], index=[k for k, _ in rows])
+    return _apply_jacobian(result, jacobian, lppd, sv, n_data_points)

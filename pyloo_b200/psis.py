@@ -32,20 +32,35 @@ def _split_sample_axis(log_weights):
     return np.asarray(log_weights), None
 
 
-def _psislw_values(vals: np.ndarray, reff: float):
-    """ndarray ``(..., S)`` -> ``(lw (..., S), k (...))`` on the GPU."""
+def _batch_values(vals: np.ndarray, run):
+    """ndarray ``(..., S)`` -> ``(lw (..., S), diagnostic (...))`` through ``run((N, S)) -> (lw, diag)``."""
     if vals.ndim < 1:
         raise ValueError("log_weights must have at least one dimension")
     obs_shape = vals.shape[:-1]
     S = vals.shape[-1]
     in_dtype = vals.dtype
     mat = vals if vals.ndim == 2 else vals.reshape(-1, S)
-    lw, k = engine.psislw_host(mat, reff)
+    lw, k = run(mat)
     lw = lw.reshape(*obs_shape, S)
     k = k.reshape(obs_shape)  # 0-d ndarray for 1-D input (pyloo/psis.py:92, test_psis.py:57)
     if in_dtype.kind == "f" and in_dtype != np.float64:
         lw = lw.astype(in_dtype)  # computed in FP64 regardless of the input dtype (SURVEY App. D)
     return lw, k
+
+
+def _psislw_values(vals: np.ndarray, reff: float):
+    """ndarray ``(..., S)`` -> ``(lw (..., S), k (...))`` on the GPU."""
+    return _batch_values(vals, lambda mat: engine.psislw_host(mat, reff))
+
+
+def _wrap_outputs(log_weights, obs_dims, lw, diag, diag_name):
+    """ndarray in -> ndarrays out; DataArray in -> DataArrays named ``log_weights`` / ``diag_name``
+    (pyloo/psis.py:107-110, pyloo/sis.py:79-83, pyloo/tis.py:84-88)."""
+    if obs_dims is None:
+        return lw, diag
+    lw_da = wrap_like(log_weights, lw, (*obs_dims, SAMPLE_DIM if SAMPLE_DIM in log_weights.dims
+                                         else log_weights.dims[-1]), "log_weights")
+    return lw_da, wrap_like(log_weights, diag, obs_dims, diag_name)
 
 
 def psislw(log_weights, reff: float = 1.0):
@@ -68,9 +83,4 @@ def psislw(log_weights, reff: float = 1.0):
     """
     vals, obs_dims = _split_sample_axis(log_weights)
     lw, k = _psislw_values(vals, reff)
-    if obs_dims is None:
-        return lw, k
-    lw_da = wrap_like(log_weights, lw, (*obs_dims, SAMPLE_DIM if SAMPLE_DIM in log_weights.dims
-                                         else log_weights.dims[-1]), "log_weights")
-    k_da = wrap_like(log_weights, k, obs_dims, "pareto_shape")  # pyloo/psis.py:107-110
-    return lw_da, k_da
+    return _wrap_outputs(log_weights, obs_dims, lw, k, "pareto_shape")  # pyloo/psis.py:107-110

@@ -1,0 +1,213 @@
+"""GPU parity tests for the callers either side of psislw: SIS / TIS weights,
+``loo(method="sis"|"tis")`` and ``e_loo`` -- the CUDA kernels (through the C ABI) against the golden vectors
+of the real reference (tests/golden/is_eloo.npz) and against the CPU oracle on seeded inputs.
+
+Tolerance: 1e-10 relative (BASELINE.json) on log weights, ess, elpd_i, lppd_i, weighted moments; Pareto k of
+``k_hat`` to 1e-12; identical NaN / inf patterns."""
+
+import warnings
+
+import numpy as np
+import pytest
+
+from b2l_testutil import golden
+
+pytestmark = pytest.mark.gpu
+
+import pyloo_b200 as pl
+from pyloo_b200 import engine
+from pyloo_b200.data import LiteDataArray, from_dict
+from oracle import is_oracle as iso
+
+RTOL = 1e-10
+
+
+def close(a, b, rtol=RTOL, atol=0.0):
+    np.testing.assert_allclose(np.asarray(a), np.asarray(b), rtol=rtol, atol=atol, equal_nan=True)
+
+
+# ------------------------------------------------------------------------------------ SIS / TIS
+@pytest.mark.parametrize("tag", ["n4000", "wide", "t15", "odd", "edge", "const"])
+@pytest.mark.parametrize("method", ["sis", "tis"])
+def test_islw_against_reference_vectors(tag, method):
+    g = golden("is_eloo.npz")
+    x = g[f"{tag}_x"]
+    keep = x.copy()
+    with np.errstate(all="ignore"):
+        lw, ess = engine.islw_host(x, method)
+    assert np.array_equal(x, keep, equal_nan=True)
+    close(lw, g[f"{tag}_{method}_lw"], atol=1e-12)
+    close(ess, g[f"{tag}_{method}_ess"])
+
+
+@pytest.mark.parametrize("S", [1, 2, 7, 33, 255, 256, 257, 1000, 4001, 30000])
+@pytest.mark.parametrize("method", ["sis", "tis"])
+def test_islw_shapes_against_oracle(S, method):
+    # odd S and unaligned rows take the plain staging loop; S = 30000 does not fit shared memory and runs
+    # straight from global memory
+    rng = np.random.default_rng(S)
+    x = rng.normal(size=(5, S)) * 3.0
+    lw, ess = engine.islw_host(x, method)
+    ref_lw, ref_ess = iso.islw(x, method)
+    close(lw, ref_lw, atol=1e-12)
+    close(ess, ref_ess)
+
+
+@pytest.mark.parametrize("method", ["sis", "tis"])
+def test_islw_many_rows_and_batch_invariance(method):
+    rng = np.random.default_rng(5)
+    x = rng.standard_t(3, size=(3000, 512))
+    lw, ess = engine.islw_host(x, method)
+    idx = rng.choice(3000, size=40, replace=False)
+    ref_lw, ref_ess = iso.islw(x[idx], method)
+    close(lw[idx], ref_lw, atol=1e-12)
+    close(ess[idx], ref_ess)
+    lw1, ess1 = engine.islw_host(x[idx], method)            # same rows, different batch: bit-identical
+    assert np.array_equal(lw1, lw[idx]) and np.array_equal(ess1, ess[idx])
+
+
+def test_compute_importance_weights_dispatch_and_names():
+    rng = np.random.default_rng(2)
+    x = rng.normal(size=(6, 400))
+    for method, fn in (("sis", pl.sislw), ("tis", pl.tislw)):
+        lw, ess = pl.compute_importance_weights(x, method=method)
+        ref_lw, ref_ess = iso.islw(x, method)
+        close(lw, ref_lw, atol=1e-12)
+        close(ess, ref_ess)
+        lw2, ess2 = fn(x)
+        assert np.array_equal(lw, lw2) and np.array_equal(ess, ess2)
+        da = LiteDataArray(x.T.copy(), ("__sample__", "obs"))          # sample axis first
+        lw_da, ess_da = pl.compute_importance_weights(da, method=method.upper())
+        assert lw_da.name == "log_weights" and ess_da.name == "ess"     # base.py:168-173
+        assert lw_da.dims == ("obs", "__sample__") and ess_da.dims == ("obs",)
+        close(lw_da.values, ref_lw, atol=1e-12)
+    one, ess0 = pl.sislw(x[0])
+    assert one.shape == (400,) and ess0.shape == ()
+    with pytest.raises(ValueError, match="Invalid method"):
+        pl.compute_importance_weights(x, method="nope")
+
+
+@pytest.mark.parametrize("method", ["sis", "tis"])
+def test_loo_is_pointwise_against_reference_vectors(method):
+    g = golden("is_eloo.npz")
+    res = engine.loo_is_host(g["loo_ll_sn"], method)                     # obs-fastest (S, N) layout
+    close(res["elpd_i"], g[f"loo_{method}_elpd_i"])
+    close(res["ess_i"], g[f"loo_{method}_ess_i"])
+    close(res["lppd_i"], g["loo_lppd_i"])
+    assert res["n_nan_in"] == 1
+    rows = np.ascontiguousarray(g["loo_ll_sn"].T)                         # row-contiguous (N, S) view
+    res2 = engine.loo_is_host(rows.T, method)
+    for key in ("elpd_i", "ess_i", "lppd_i"):
+        assert np.array_equal(res[key], res2[key], equal_nan=True)
+
+
+@pytest.mark.parametrize("method", ["sis", "tis"])
+def test_loo_method_api(method):
+    rng = np.random.default_rng(11)
+    ll = -1.0 + 0.7 * rng.normal(size=(4, 250, 9))
+    idata = from_dict(posterior={"mu": rng.normal(size=(4, 250))}, log_likelihood={"y": ll},
+                      dims={"y": ["obs"]})
+    with pytest.warns(UserWarning, match=f"Using {method.upper()} for LOO computation"):
+        res = pl.loo(idata, pointwise=True, method=method)
+    ref = iso.loo_is_summary(ll.reshape(-1, 9), method)
+    for key in ("elpd_loo", "se", "p_loo", "p_loo_se", "looic", "looic_se"):
+        close(res[key], ref[key])
+    close(res["loo_i"].values, ref["elpd_i"])
+    close(res["ess"].values, ref["ess_i"])
+    assert "pareto_k" not in res and "good_k" not in res                # loo.py:400-410
+    assert bool(res["warning"]) == ref["warning"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        dev = pl.loo(idata, method=method, scale="deviance")
+    close(dev["elpd_loo"], -2 * ref["elpd_loo"])
+    assert list(dev.index[-4:]) == ["scale", "looic", "looic_se", "subsample_size"]
+
+
+def test_loo_is_low_ess_warning():
+    rng = np.random.default_rng(3)
+    ll = 6.0 * rng.normal(size=(2, 300, 4))                              # wild ratios: ESS collapses
+    idata = from_dict(posterior={"mu": rng.normal(size=(2, 300))}, log_likelihood={"y": ll})
+    with pytest.warns(UserWarning, match="Low effective sample size detected"):
+        res = pl.loo(idata, method="sis")
+    assert res["warning"]
+
+
+# ------------------------------------------------------------------------------------ e_loo
+def test_eloo_against_reference_vectors():
+    g = golden("is_eloo.npz")
+    x, lw, lr = g["eloo_x"], g["eloo_lw"], g["eloo_lr"]
+    with np.errstate(all="ignore"):
+        v, k = engine.eloo_host(x, lw, lr, "mean")
+        close(v, g["eloo_mean"], atol=1e-13)
+        close(k, g["eloo_k_mean"], 1e-12)
+        v, k = engine.eloo_host(x, lw, lr, "variance")
+        close(v, g["eloo_var"], 1e-9)
+        close(k, g["eloo_k_var"], 1e-12)
+        v, _ = engine.eloo_host(x, lw, lr, "sd")
+        close(v, np.sqrt(g["eloo_var"]), 1e-9)
+        v, k = engine.eloo_host(None, lw, lr, "none")
+        assert v is None
+        close(k, g["eloo_k_none"], 1e-12)
+        for tl, key in ((20, "short_k"), (7, "short_k7")):
+            _, k = engine.eloo_host(g["short_x"], g["short_lr"], None, "mean", tl)
+            close(k, g[key], 1e-12)
+
+
+@pytest.mark.parametrize("S,N", [(64, 40), (1001, 17), (4000, 700), (12000, 9)])
+def test_eloo_against_oracle(S, N):
+    # S = 1001: odd rows, plain staging; S = 12000 with separate ratios: three rows exceed shared memory, the
+    # kernel reads global memory and keeps h * r in the workspace
+    rng = np.random.default_rng(S + N)
+    x = rng.normal(size=(N, S)) + rng.normal(size=(N, 1))
+    lr = rng.standard_t(4, size=(N, S))
+    lw, _ = iso.islw(lr, "tis")
+    x[0] = np.round(x[0])                                                 # heavy ties in h
+    lr[1] = np.round(lr[1], 1)                                            # heavy ties in the ratios
+    sub = slice(0, min(N, 25))
+    for kind in ("mean", "variance", "sd"):
+        v, k = engine.eloo_host(x, lw, lr, kind)
+        ref = iso.e_loo_arrays(x[sub], lw[sub], lr[sub], kind)
+        close(v[sub], ref["value"], 1e-9, atol=1e-13)
+        close(k[sub], ref["pareto_k"], 1e-12)
+    v, k = engine.eloo_host(x, lw, None, "mean")                          # ratios default to the weights
+    ref = iso.e_loo_arrays(x[sub], lw[sub], None, "mean")
+    close(v[sub], ref["value"], 1e-9, atol=1e-13)
+    close(k[sub], ref["pareto_k"], 1e-12)
+
+
+def test_eloo_api_and_diagnostics():
+    rng = np.random.default_rng(8)
+    ll = -1.0 + 0.5 * rng.normal(size=(4, 300, 6))
+    yrep = rng.normal(size=(4, 300, 6)) * 2 + 1
+    idata = from_dict(posterior={"mu": rng.normal(size=(4, 300))}, log_likelihood={"y": ll},
+                      posterior_predictive={"y": yrep}, dims={"y": ["obs"]})
+    llda = idata.log_likelihood["y"].stack(__sample__=("chain", "draw"))
+    lw, _ = pl.psislw(-llda)
+    res = pl.e_loo(idata, var_name="y", log_weights=lw, log_ratios=-llda, type="mean")
+    x = yrep.reshape(-1, 6).T
+    ref = iso.e_loo_arrays(x, np.asarray(lw.values), -ll.reshape(-1, 6).T, "mean")
+    assert res.value.dims == ("obs",) and res.pareto_k.dims == ("obs",)
+    close(res.value.values, ref["value"], 1e-9)
+    close(res.pareto_k.values, ref["pareto_k"], 1e-12)
+    close(res.min_ss.values, ref["min_ss"])
+    close(res.khat_threshold.values, ref["khat_threshold"])
+    close(res.convergence_rate.values, ref["convergence_rate"])
+    sd = pl.e_loo(idata, log_weights=lw, type="sd")                       # ratios default to the weights
+    close(sd.value.values, iso.e_loo_arrays(x, np.asarray(lw.values), None, "sd")["value"], 1e-9)
+    w = LiteDataArray(np.exp(np.asarray(lw.values)), lw.dims)
+    byw = pl.e_loo(idata, weights=w, type="mean")                          # e_loo.py:199-200
+    close(byw.value.values, ref["value"], 1e-9)
+    with pytest.raises(ValueError, match="type must be"):
+        pl.e_loo(idata, log_weights=lw, type="median")
+    with pytest.raises(ValueError, match="Either weights or log_weights"):
+        pl.e_loo(idata)
+    with pytest.raises(ValueError, match="probs must be provided"):
+        pl.e_loo(idata, log_weights=lw, type="quantile")
+    with pytest.raises(ValueError, match="does not have a nope group"):
+        pl.e_loo(idata, group="nope", log_weights=lw)
+    k1 = pl.k_hat(x[0], -ll.reshape(-1, 6).T[0])
+    close(k1, ref["pareto_k"][0], 1e-12)
+    kd = pl.compute_pareto_k(LiteDataArray(x, ("obs", "__sample__")), -llda)
+    close(kd.values, ref["pareto_k"], 1e-12)
+    with pytest.raises(ValueError, match="tail_len must be at least 5"):
+        pl.compute_pareto_k(x[0], x[0], tail_len=3)
