@@ -242,6 +242,30 @@ __device__ __forceinline__ void warp_top(const double* buf, int n, int first, in
     }
 }
 
+// 32 doubles (one per lane, no NaN) sorted descending across the warp: bitonic network on shuffles
+__device__ __forceinline__ double warp_sort_desc(double v, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const double o = __shfl_xor_sync(FULL, v, j);
+            const bool keep_max = (((lane & k) == 0) == ((lane & j) == 0));
+            v = keep_max ? fmax(v, o) : fmin(v, o);
+        }
+    }
+    return v;
+}
+// number of entries of the descending list d[0..32) that are > v (strict) or >= v
+__device__ __forceinline__ int count_above(const double* d, double v, bool or_equal) {
+    int lo = 0, hi = 32;  // first index whose entry is NOT above v
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const bool above = or_equal ? (d[mid] >= v) : (d[mid] > v);
+        if (above) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
 // ---- generalised Pareto fit, literal -------------------------------------------------------------
 // pyloo/psis.py:181-208 evaluated operation by operation on ary[0..n) IN THE ORDER GIVEN, by one warp.
 // k_hat (e_loo.py:357,377,383) hands it descending tails whose last element is 0, so 1/ary[-1] is inf, the
@@ -254,6 +278,16 @@ __device__ __forceinline__ double gpdfit_literal_warp(const double* ary, int n, 
     int q = (int)((double)n / 4.0 + 0.5) - 1;
     if (q < 0) q += n;
     const double aq = ary[q], an = ary[n - 1];
+    {
+        // Shortcut, exactly equivalent to the literal evaluation below: with ary[n-1] == +-0 and every entry
+        // finite, 1/ary[n-1] is +-inf, every b_j is +-inf or NaN, the i = n-1 term of every profile mean is
+        // log1p(-(+-inf) * 0) = NaN, so all grid weights are NaN and dropped, b_post = 0 (empty sum),
+        // k_post = mean(log1p(-0 * ary)) = -0 and the estimate is (n * -0 + 5) / (n + 10).  This is the only
+        // case k_hat produces (the cutoff is an element of the tail), so the loops below never run for it.
+        int fin = 1;
+        for (int i = lane; i < n; i += 32) fin &= is_finite(ary[i]) ? 1 : 0;
+        if (__all_sync(FULL, fin) && an == 0.0) return ((double)n * -0.0 + 5.0) / ((double)n + 10.0);
+    }
     for (int j = lane; j < m; j += 32) {
         double b = 1.0 - sqrt((double)m / ((double)(j + 1) - 0.5));
         b /= 3.0 * aq;
@@ -294,14 +328,17 @@ __device__ __forceinline__ double gpdfit_literal_warp(const double* ary, int n, 
     return ((double)n * k_post + 5.0) / ((double)n + 10.0);
 }
 
+constexpr int ELOO_FAST_CAP = 128;  // candidates above the sampled threshold handled without the slow path
+
 struct ElooSmem {
     int row_words;  // padded S
     int n_rows_staged;
     __host__ __device__ static size_t bytes(int S, int n_staged) {
         const size_t spad = (size_t)((S + 1) & ~1);
         // red + staged rows + candidates (3 tails x 8 warps x L) + tails (3 x L) + gpd scratch (3 x 128)
+        // + thread maxima (3 x 256) + fast-path candidates (3 x 128) + thresholds / counters (8)
         return sizeof(double) * (IS_RED_WORDS + spad * n_staged + 3 * IS_NW * ELOO_MAX_TAIL +
-                                 3 * ELOO_MAX_TAIL + 3 * 128 + 8);
+                                 3 * ELOO_MAX_TAIL + 3 * 128 + 8 + 3 * IS_NT + 3 * ELOO_FAST_CAP + 8);
     }
 };
 
@@ -324,7 +361,11 @@ __global__ void __launch_bounds__(IS_NT) eloo_row_kernel(const ElooParams p) {
     double* cand = sm;                               // [3][IS_NW][L]
     double* tails = cand + 3 * IS_NW * ELOO_MAX_TAIL;  // [3][L]
     double* gpd = tails + 3 * ELOO_MAX_TAIL;           // [3][128]
-    double* res = gpd + 3 * 128;                       // [3] khat per tail
+    double* res = gpd + 3 * 128;                       // [3] khat per tail (8 words reserved)
+    double* tmax = res + 8;                            // [3][IS_NT] thread-local maxima, sorted per warp
+    double* fcand = tmax + 3 * IS_NT;                  // [3][ELOO_FAST_CAP]
+    double* thr = fcand + 3 * ELOO_FAST_CAP;           // [3] thresholds
+    int* cnt = reinterpret_cast<int*>(thr + 4);        // [3] candidate counts
     if (STAGED && p.bulk && tid == 0) {
         mbar_init(bar, 1);
         fence_mbar_init();
@@ -380,6 +421,7 @@ __global__ void __launch_bounds__(IS_NT) eloo_row_kernel(const ElooParams p) {
                 }
             }
         }
+        const double m_r = lrmax;  // this thread's largest log ratio
         lwmax = block_max<IS_NT>(lwmax, red);
         lrmax = block_max<IS_NT>(lrmax, red);
         if (has_x) {
@@ -397,7 +439,9 @@ __global__ void __launch_bounds__(IS_NT) eloo_row_kernel(const ElooParams p) {
 
         // ---- pass 2: weighted sums (e_loo.py:429-463) and h * r (e_loo.py:368)
         double se = 0.0, sex = 0.0, sexx = 0.0, see = 0.0;
+        double m_hi = -inf_f64(), m_lo = -inf_f64();  // this thread's largest h*r and largest -(h*r)
         if (has_x) {
+            const bool same = (LR == LW);
             for (int s = tid; s < S; s += IS_NT) {
                 const double xv = X[s];
                 const double e = exp(LW[s] - lwmax);
@@ -405,7 +449,12 @@ __global__ void __launch_bounds__(IS_NT) eloo_row_kernel(const ElooParams p) {
                 sex += e * xv;
                 sexx += e * (xv * xv);
                 see += e * e;
-                if (need_hr) HR[s] = (sq ? xv * xv : xv) * exp(LR[s] - lrmax);
+                if (need_hr) {
+                    const double hr = (sq ? xv * xv : xv) * (same ? e : exp(LR[s] - lrmax));
+                    HR[s] = hr;
+                    m_hi = fmax(m_hi, hr);
+                    m_lo = fmax(m_lo, -hr);
+                }
             }
             se = block_sum<IS_NT>(se, red);
             sex = block_sum<IS_NT>(sex, red);
@@ -417,18 +466,80 @@ __global__ void __launch_bounds__(IS_NT) eloo_row_kernel(const ElooParams p) {
         __syncthreads();  // HR complete
 
         // ---- k_hat: tails of r and of h * r (e_loo.py:350-390)
+        // Top-n_tail selection.  Fast path: the n_tail-th largest of the 256 thread-local maxima is a lower
+        // bound of the n_tail-th largest element, so everything >= it is a candidate (n_tail .. a few more on
+        // ordinary rows); candidates are ranked by counting.  Rows with many ties at the threshold overflow the
+        // candidate list and take the exact extraction (warp_top) instead.
         const bool r_ok = is_finite(lrmax);
-        if (r_ok) warp_top<false>(LR, S, tid, IS_NT, n_tail, cand + (0 * IS_NW + warp) * ELOO_MAX_TAIL, lane);
-        if (need_hr) {
-            warp_top<true>(HR, S, tid, IS_NT, n_tail, cand + (1 * IS_NW + warp) * ELOO_MAX_TAIL, lane);
-            warp_top<false>(HR, S, tid, IS_NT, n_tail, cand + (2 * IS_NW + warp) * ELOO_MAX_TAIL, lane);
+        const bool want[3] = {r_ok, need_hr, need_hr};
+        {
+            const double keys[3] = {m_r, m_lo, m_hi};
+#pragma unroll
+            for (int t = 0; t < 3; ++t)
+                if (want[t]) tmax[t * IS_NT + tid] = warp_sort_desc(keys[t], lane);
+            if (tid < 3) cnt[tid] = 0;
         }
         __syncthreads();
-        if (warp < 3 && ((warp == 0 && r_ok) || (warp > 0 && need_hr))) {
+        {
+            const int K = n_tail < IS_NT ? n_tail : IS_NT;
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                if (!want[t]) continue;
+                const double v = tmax[t * IS_NT + tid];
+                int rank = lane;
+                for (int w = 0; w < IS_NW; ++w)
+                    if (w != warp) rank += count_above(tmax + t * IS_NT + w * 32, v, w < warp);
+                if (rank == K - 1) thr[t] = v;
+            }
+        }
+        __syncthreads();
+        {
+            const double t0 = thr[0], t1 = thr[1], t2 = thr[2];
+            for (int s = tid; s < S; s += IS_NT) {
+                if (want[0]) {
+                    const double v = LR[s];
+                    if (v >= t0) {
+                        const int pos = atomicAdd(&cnt[0], 1);
+                        if (pos < ELOO_FAST_CAP) fcand[pos] = v;
+                    }
+                }
+                if (want[1]) {
+                    const double v = HR[s];
+                    if (-v >= t1) {
+                        const int pos = atomicAdd(&cnt[1], 1);
+                        if (pos < ELOO_FAST_CAP) fcand[ELOO_FAST_CAP + pos] = -v;
+                    }
+                    if (v >= t2) {
+                        const int pos = atomicAdd(&cnt[2], 1);
+                        if (pos < ELOO_FAST_CAP) fcand[2 * ELOO_FAST_CAP + pos] = v;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        const bool slow[3] = {want[0] && cnt[0] > ELOO_FAST_CAP, want[1] && cnt[1] > ELOO_FAST_CAP,
+                              want[2] && cnt[2] > ELOO_FAST_CAP};
+        if (slow[0]) warp_top<false>(LR, S, tid, IS_NT, n_tail, cand + (0 * IS_NW + warp) * ELOO_MAX_TAIL, lane);
+        if (slow[1]) warp_top<true>(HR, S, tid, IS_NT, n_tail, cand + (1 * IS_NW + warp) * ELOO_MAX_TAIL, lane);
+        if (slow[2]) warp_top<false>(HR, S, tid, IS_NT, n_tail, cand + (2 * IS_NW + warp) * ELOO_MAX_TAIL, lane);
+        if (slow[0] || slow[1] || slow[2]) __syncthreads();
+        if (warp < 3 && want[warp]) {
             double* tl = tails + warp * ELOO_MAX_TAIL;
-            // the candidates of warp w sit at [w * ELOO_MAX_TAIL, w * ELOO_MAX_TAIL + n_tail): compact view by index map
-            // (select over all IS_NW * ELOO_MAX_TAIL slots; unused slots were never written, so mask them)
-            {
+            if (!slow[warp]) {
+                // rank the candidates by counting (ties by slot): the n_tail largest land in tl, descending
+                const double* fc = fcand + warp * ELOO_FAST_CAP;
+                const int c = cnt[warp];
+                for (int i = lane; i < c; i += 32) {
+                    const double v = fc[i];
+                    int rank = 0;
+                    for (int j = 0; j < c; ++j) {
+                        const double o = fc[j];
+                        rank += (o > v || (o == v && j < i)) ? 1 : 0;
+                    }
+                    if (rank < n_tail) tl[rank] = v;
+                }
+            } else {
+                // merge the per-warp extractions: candidates of warp w sit at [w * ELOO_MAX_TAIL, + n_tail)
                 constexpr int NONE = 0x7fffffff;
                 const double* cb = cand + warp * IS_NW * ELOO_MAX_TAIL;
                 double lastv = inf_f64();

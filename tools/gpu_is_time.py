@@ -3,7 +3,10 @@
     python tools/gpu_is_time.py [S] [N]
 """
 import json
+import os
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import torch
 
