@@ -242,6 +242,50 @@ __device__ __forceinline__ void warp_top(const double* buf, int n, int first, in
     }
 }
 
+// Merge the per-warp descending lists cb[w * ELOO_MAX_TAIL + 0..n_tail), w < IS_NW, written by warp_top into
+// the n_tail largest overall (descending) in tl.  One warp.
+__device__ __forceinline__ void merge_warp_lists(const double* cb, int n_tail, double* tl, int lane) {
+    constexpr int NONE = 0x7fffffff;
+    double lastv = inf_f64();
+    int lasti = -1;
+    double bestv;
+    int besti;
+    auto rescan = [&]() {
+        bestv = -inf_f64();
+        besti = NONE;
+        for (int c = lane; c < IS_NW * n_tail; c += 32) {
+            const int s = (c / n_tail) * ELOO_MAX_TAIL + (c % n_tail);
+            const double v = cb[s];
+            const bool eligible = (v < lastv) || (v == lastv && s > lasti);
+            if (eligible && (besti == NONE || v > bestv)) {
+                bestv = v;
+                besti = s;
+            }
+        }
+    };
+    rescan();
+    for (int k = 0; k < n_tail; ++k) {
+        double wv = bestv;
+        int wi = besti;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(FULL, wv, o);
+            const int oi = __shfl_xor_sync(FULL, wi, o);
+            const bool take = (oi != NONE) && (wi == NONE || ov > wv || (ov == wv && oi < wi));
+            if (take) {
+                wv = ov;
+                wi = oi;
+            }
+        }
+        if (lane == 0) tl[k] = wv;
+        if (wi != NONE && wi == besti) {
+            lastv = wv;
+            lasti = wi;
+            rescan();
+        }
+    }
+}
+
 // 32 doubles (one per lane, no NaN) sorted descending across the warp: bitonic network on shuffles
 __device__ __forceinline__ double warp_sort_desc(double v, int lane) {
 #pragma unroll
@@ -329,16 +373,18 @@ __device__ __forceinline__ double gpdfit_literal_warp(const double* ary, int n, 
 }
 
 constexpr int ELOO_FAST_CAP = 128;  // candidates above the sampled threshold handled without the slow path
+constexpr int ELOO_AREA_WORDS = IS_NW * ELOO_MAX_TAIL;  // 1024 >= 3 * IS_NT and >= 3 * 128
+static_assert(ELOO_AREA_WORDS >= 3 * IS_NT && ELOO_AREA_WORDS >= 3 * 128, "scratch area too small");
 
 struct ElooSmem {
     int row_words;  // padded S
     int n_rows_staged;
     __host__ __device__ static size_t bytes(int S, int n_staged) {
         const size_t spad = (size_t)((S + 1) & ~1);
-        // red + staged rows + candidates (3 tails x 8 warps x L) + tails (3 x L) + gpd scratch (3 x 128)
-        // + thread maxima (3 x 256) + fast-path candidates (3 x 128) + thresholds / counters (8)
-        return sizeof(double) * (IS_RED_WORDS + spad * n_staged + 3 * IS_NW * ELOO_MAX_TAIL +
-                                 3 * ELOO_MAX_TAIL + 3 * 128 + 8 + 3 * IS_NT + 3 * ELOO_FAST_CAP + 8);
+        // red + staged rows + scratch area (union: thread maxima 3 x 256 | exact-extraction lists 8 warps x L |
+        // fit scratch 3 x 128) + tails (3 x L) + fast-path candidates (3 x 128) + results / thresholds / counters
+        return sizeof(double) * (IS_RED_WORDS + spad * n_staged + ELOO_AREA_WORDS + 3 * ELOO_MAX_TAIL +
+                                 3 * ELOO_FAST_CAP + 16);
     }
 };
 
@@ -358,14 +404,14 @@ __global__ void __launch_bounds__(IS_NT) eloo_row_kernel(const ElooParams p) {
         if (!lr_same) { blr = sm; sm += spad; } else blr = blw;
         if (has_x) { bx = sm; sm += spad; }
     }
-    double* cand = sm;                               // [3][IS_NW][L]
-    double* tails = cand + 3 * IS_NW * ELOO_MAX_TAIL;  // [3][L]
-    double* gpd = tails + 3 * ELOO_MAX_TAIL;           // [3][128]
-    double* res = gpd + 3 * 128;                       // [3] khat per tail (8 words reserved)
-    double* tmax = res + 8;                            // [3][IS_NT] thread-local maxima, sorted per warp
-    double* fcand = tmax + 3 * IS_NT;                  // [3][ELOO_FAST_CAP]
-    double* thr = fcand + 3 * ELOO_FAST_CAP;           // [3] thresholds
-    int* cnt = reinterpret_cast<int*>(thr + 4);        // [3] candidate counts
+    double* area = sm;                        // union, see ElooSmem::bytes
+    double* tmax = area;                      // [3][IS_NT] thread-local maxima, sorted per warp
+    double* gpd = area;                       // [3][128] literal-fit scratch (after the selection)
+    double* tails = area + ELOO_AREA_WORDS;   // [3][L]
+    double* fcand = tails + 3 * ELOO_MAX_TAIL;  // [3][ELOO_FAST_CAP]
+    double* res = fcand + 3 * ELOO_FAST_CAP;  // [3] khat per tail
+    double* thr = res + 4;                    // [3] thresholds
+    int* cnt = reinterpret_cast<int*>(thr + 4);  // [3] candidate counts
     if (STAGED && p.bulk && tid == 0) {
         mbar_init(bar, 1);
         fence_mbar_init();
@@ -519,68 +565,35 @@ __global__ void __launch_bounds__(IS_NT) eloo_row_kernel(const ElooParams p) {
         __syncthreads();
         const bool slow[3] = {want[0] && cnt[0] > ELOO_FAST_CAP, want[1] && cnt[1] > ELOO_FAST_CAP,
                               want[2] && cnt[2] > ELOO_FAST_CAP};
-        if (slow[0]) warp_top<false>(LR, S, tid, IS_NT, n_tail, cand + (0 * IS_NW + warp) * ELOO_MAX_TAIL, lane);
-        if (slow[1]) warp_top<true>(HR, S, tid, IS_NT, n_tail, cand + (1 * IS_NW + warp) * ELOO_MAX_TAIL, lane);
-        if (slow[2]) warp_top<false>(HR, S, tid, IS_NT, n_tail, cand + (2 * IS_NW + warp) * ELOO_MAX_TAIL, lane);
-        if (slow[0] || slow[1] || slow[2]) __syncthreads();
+        if (warp < 3 && want[warp] && !slow[warp]) {
+            // rank the candidates by counting (ties by slot): the n_tail largest land in the tail, descending
+            double* tl = tails + warp * ELOO_MAX_TAIL;
+            const double* fc = fcand + warp * ELOO_FAST_CAP;
+            const int c = cnt[warp];
+            for (int i = lane; i < c; i += 32) {
+                const double v = fc[i];
+                int rank = 0;
+                for (int j = 0; j < c; ++j) {
+                    const double o = fc[j];
+                    rank += (o > v || (o == v && j < i)) ? 1 : 0;
+                }
+                if (rank < n_tail) tl[rank] = v;
+            }
+        }
+        // exact extraction for the tails that overflowed, one at a time through the shared scratch area
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            if (!slow[t]) continue;  // block-uniform
+            __syncthreads();
+            if (t == 0) warp_top<false>(LR, S, tid, IS_NT, n_tail, area + warp * ELOO_MAX_TAIL, lane);
+            else if (t == 1) warp_top<true>(HR, S, tid, IS_NT, n_tail, area + warp * ELOO_MAX_TAIL, lane);
+            else warp_top<false>(HR, S, tid, IS_NT, n_tail, area + warp * ELOO_MAX_TAIL, lane);
+            __syncthreads();
+            if (warp == 0) merge_warp_lists(area, n_tail, tails + t * ELOO_MAX_TAIL, lane);
+        }
+        __syncthreads();  // tails complete; the scratch area is free for the fit
         if (warp < 3 && want[warp]) {
             double* tl = tails + warp * ELOO_MAX_TAIL;
-            if (!slow[warp]) {
-                // rank the candidates by counting (ties by slot): the n_tail largest land in tl, descending
-                const double* fc = fcand + warp * ELOO_FAST_CAP;
-                const int c = cnt[warp];
-                for (int i = lane; i < c; i += 32) {
-                    const double v = fc[i];
-                    int rank = 0;
-                    for (int j = 0; j < c; ++j) {
-                        const double o = fc[j];
-                        rank += (o > v || (o == v && j < i)) ? 1 : 0;
-                    }
-                    if (rank < n_tail) tl[rank] = v;
-                }
-            } else {
-                // merge the per-warp extractions: candidates of warp w sit at [w * ELOO_MAX_TAIL, + n_tail)
-                constexpr int NONE = 0x7fffffff;
-                const double* cb = cand + warp * IS_NW * ELOO_MAX_TAIL;
-                double lastv = inf_f64();
-                int lasti = -1;
-                double bestv;
-                int besti;
-                auto rescan = [&]() {
-                    bestv = -inf_f64();
-                    besti = NONE;
-                    for (int c = lane; c < IS_NW * n_tail; c += 32) {
-                        const int s = (c / n_tail) * ELOO_MAX_TAIL + (c % n_tail);
-                        const double v = cb[s];
-                        const bool eligible = (v < lastv) || (v == lastv && s > lasti);
-                        if (eligible && (besti == NONE || v > bestv)) {
-                            bestv = v;
-                            besti = s;
-                        }
-                    }
-                };
-                rescan();
-                for (int k = 0; k < n_tail; ++k) {
-                    double wv = bestv;
-                    int wi = besti;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const double ov = __shfl_xor_sync(FULL, wv, o);
-                        const int oi = __shfl_xor_sync(FULL, wi, o);
-                        const bool take = (oi != NONE) && (wi == NONE || ov > wv || (ov == wv && oi < wi));
-                        if (take) {
-                            wv = ov;
-                            wi = oi;
-                        }
-                    }
-                    if (lane == 0) tl[k] = wv;
-                    if (wi != NONE && wi == besti) {
-                        lastv = wv;
-                        lasti = wi;
-                        rescan();
-                    }
-                }
-            }
             __syncwarp();
             // tail values in the reference's order, then its degeneracy test and the fit argument
             // warp 0: sorted_r descending (e_loo.py:351); warp 1: left tail ascending (:370); warp 2: right

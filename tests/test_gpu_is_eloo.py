@@ -175,6 +175,29 @@ def test_eloo_against_oracle(S, N):
     close(k[sub], ref["pareto_k"], 1e-12)
 
 
+def test_eloo_tie_heavy_rows_take_the_exact_extraction():
+    # hundreds of ties at the selection threshold overflow the candidate list of the fast path
+    rng = np.random.default_rng(21)
+    N, S = 12, 4000
+    x = rng.normal(size=(N, S))
+    lr = rng.normal(size=(N, S))
+    lr[0, :600] = 5.0                          # 600 equal maxima: ratio tail all close -> k = inf
+    lr[1, :10] = np.linspace(6.0, 7.0, 10)     # 10 distinct values, then 400 ties at the 11th..20th place
+    lr[1, 10:410] = 5.5
+    x[2, ::2] = 0.0                            # half of h is exactly 0: left tail of x^2 * r is all zeros
+    x[3] = np.abs(x[3])
+    x[3, :900] = 0.0                           # non-negative h with 900 zeros: left tail of h * r all zeros
+    x[4, :300] = 50.0                          # 300 equal large h, ratios tied too: right tail ties
+    lr[4, :300] = 1.0
+    lw, _ = iso.islw(lr, "sis")
+    for kind in ("mean", "variance"):
+        v, k = engine.eloo_host(x, lw, lr, kind)
+        ref = iso.e_loo_arrays(x, lw, lr, kind)
+        close(v, ref["value"], 1e-9, atol=1e-13)
+        close(k, ref["pareto_k"], 1e-12)
+    assert np.isinf(ref["pareto_k"][0])
+
+
 def test_eloo_api_and_diagnostics():
     rng = np.random.default_rng(8)
     ll = -1.0 + 0.5 * rng.normal(size=(4, 300, 6))
