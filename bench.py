@@ -283,7 +283,7 @@ def main():
     kernel_names = {"stream": "psis_stream_kernel<256,16,PSISLW> (row pass + fused apply of the previous batch)",
                     "tail": "psis_tail_kernel<8,PSISLW>", "apply": "psis_apply_kernel",
                     "row": "psis_row_kernel<256,PSISLW> (hand-over rows)", "transpose": "transpose_f64_kernel",
-                    "stats": "stats kernels"}
+                    "stats": "stats kernels", "is": "is_row_kernel", "eloo": "eloo_row_kernel"}
     tot_ms = sum(ms for ms, _ in prof.values()) or 1.0
     kernels = {k: {"name": kernel_names[k], "ms_per_step": ms / prof_steps, "launches_per_step": cnt / prof_steps,
                    "share": ms / tot_ms}
@@ -345,6 +345,36 @@ def main():
                "elpd_loo": merged.elpd_sum, "n_total": merged.n, "collective": "all_gather(32 f64)" if world > 1 else None}
         del ll
 
+    # ---- the callers either side of psislw: SIS / TIS weights and e_loo on a 2-round slab
+    next_rows = None
+    if not args.skip_loo:
+        n_nx = min(N, 148 * 64 * 2)
+        xs, outs = x[:n_nx], out[:n_nx]
+        hs = torch.randn(n_nx, S, dtype=torch.float64, device=dev, generator=gen)
+        lw_tis, _ = engine.islw_cuda(xs, "tis")
+
+        def timed(fn, nbytes):
+            for _ in range(3):
+                fn()
+            barrier()
+            ev0.record()
+            for _ in range(args.steps):
+                fn()
+            ev1.record()
+            barrier()
+            ms = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+            gbs = n_nx * nbytes / (ms * 1e-3) / 1e9
+            return {"value": world * n_nx / (ms * 1e-3), "unit": "obs/s", "ms_per_step": ms,
+                    "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak}}
+
+        next_rows = {
+            "workload": f"S={S} x N={n_nx} per GPU, device resident, 606 MB per array (larger than L2)",
+            "sislw": timed(lambda: engine.islw_cuda(xs, "sis", out=outs), 16 * S + 8),
+            "tislw": timed(lambda: engine.islw_cuda(xs, "tis", out=outs), 16 * S + 8),
+            "e_loo_mean": timed(lambda: engine.eloo_cuda(hs, lw_tis, xs, "mean"), 24 * S + 16),
+        }
+        del hs, lw_tis
+
     # ---- end to end through the host-buffer C-ABI entry (pinned host memory both ways)
     e2e = None
     if not args.skip_e2e:
@@ -381,7 +411,7 @@ def main():
                        "parallelism": f"obs-sharded x{world}, no data-path collective"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(round(launches_per_step * args.steps)), "clocks": clocks,
-            "loo": loo,
+            "loo": loo, "next_rows": next_rows,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -656,6 +656,139 @@ __global__ void __launch_bounds__(IS_NT) eloo_row_kernel(const ElooParams p) {
     }
 }
 
+// ===================================================================================== e_loo quantiles
+// pyloo/e_loo.py:466-515 + _weighted_quantile :534-554 for a batch: per observation the draws are sorted
+// (bitonic network in shared memory on (x, draw index), NaN last like np.argsort), the normalised weights are
+// accumulated in sorted order and every requested probability is located by binary search in the cumulative
+// weights and interpolated linearly.  Rows whose weights are all close to the first one take np.quantile's
+// linear rule instead (:536-537).
+__device__ __forceinline__ bool key_greater(double a, int ia, double b, int ib, int S) {
+    const bool pa = (ia >= S), pb = (ib >= S);  // padding sorts after everything, NaN included
+    if (pa != pb) return pa;
+    const bool an = (a != a), bn = (b != b);
+    if (an != bn) return an;
+    if (an) return ia > ib;
+    return (a > b) || (a == b && ia > ib);
+}
+
+__global__ void __launch_bounds__(IS_NT) eloo_quantile_kernel(const QuantParams p) {
+    extern __shared__ __align__(16) unsigned char is_smem[];
+    double* red = reinterpret_cast<double*>(is_smem);
+    double* keys = red + IS_RED_WORDS;   // [P2] sorted draws
+    double* cs = keys + p.P2;            // [P2] cumulative weights in sorted order
+    double* part = cs + p.P2;            // [IS_NT] scan partials
+    int* idx = reinterpret_cast<int*>(part + IS_NT);  // [P2]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, S = p.S, P2 = p.P2;
+
+    for (long long row = blockIdx.x; row < p.n_rows; row += gridDim.x) {
+        const double* gx = p.x + row * p.x_stride;
+        const double* glw = p.lw + row * p.lw_stride;
+        // ---- normaliser of the weights (e_loo.py:557-559) and the sort input
+        double lwmax = -inf_f64();
+        int bad = 0;
+        for (int s = tid; s < P2; s += IS_NT) {
+            keys[s] = (s < S) ? gx[s] : inf_f64();
+            idx[s] = s;
+            if (s < S) {
+                const double a = glw[s];
+                bad |= (a != a);
+                lwmax = fmax(lwmax, a);
+            }
+        }
+        lwmax = block_max<IS_NT>(lwmax, red);
+        if (block_or(bad, red)) lwmax = nan_f64();
+        double se = 0.0;
+        for (int s = tid; s < S; s += IS_NT) se += exp(glw[s] - lwmax);
+        se = block_sum<IS_NT>(se, red);
+        const double lse = log(se) + lwmax;
+        const double w0 = exp(glw[0] - lse);
+        int far = 0;
+        for (int s = tid; s < S; s += IS_NT) far |= np_isclose(exp(glw[s] - lse), w0) ? 0 : 1;
+        const bool uniform = !block_or(far, red);  // np.allclose(w, w[0]) (:536)
+
+        // ---- bitonic sort of (x, index), ascending, NaN last
+        for (int k = 2; k <= P2; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < (P2 >> 1); t += IS_NT) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const int l = i | j;
+                    const double ka = keys[i], kb = keys[l];
+                    const int ia = idx[i], ib = idx[l];
+                    const bool up = ((i & k) == 0);
+                    if (key_greater(ka, ia, kb, ib, S) == up) {
+                        keys[i] = kb; keys[l] = ka;
+                        idx[i] = ib; idx[l] = ia;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+
+        if (!uniform) {
+            // ---- cumulative weights in sorted order: per-thread chunk sums, block scan, then the offsets
+            const int C = P2 / IS_NT;
+            double run = 0.0;
+            for (int i = tid * C; i < (tid + 1) * C; ++i) {
+                const int s = idx[i];
+                run += (s < S) ? exp(glw[s] - lse) : 0.0;
+                cs[i] = run;
+            }
+            double incl = run;  // inclusive scan of the chunk totals across the block
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double v = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (lane == 31) part[warp] = incl;
+            __syncthreads();
+            double base = 0.0;
+            for (int w = 0; w < warp; ++w) base += part[w];
+            const double excl = base + (incl - run);
+            for (int i = tid * C; i < (tid + 1) * C; ++i) cs[i] += excl;
+            __syncthreads();
+        }
+        if (tid < p.n_probs) {
+            const double q = p.probs[tid];
+            double val;
+            if (uniform) {
+                // np.quantile(x, q), method "linear": virtual index n*q + (alpha + q*(1 - alpha - beta)) - 1 with
+                // alpha = beta = 1, evaluated in that order; lerp as numpy's _lerp
+                const double n = (double)S;
+                const double virt = n * q + (1.0 + q * (1.0 - 1.0 - 1.0)) - 1.0;
+                double lo = floor(virt);
+                const double g = virt - lo;
+                int il = (int)lo, ih = il + 1;
+                if (il < 0) il = 0;
+                if (ih > S - 1) ih = S - 1;
+                if (il > S - 1) il = S - 1;
+                const double a = keys[il], b = keys[ih];
+                const double d = b - a;
+                val = a + d * g;
+                if (g >= 0.5) val = b - d * (1.0 - g);
+                if (d == 0.0) val = a;
+                if (keys[S - 1] != keys[S - 1]) val = nan_f64();  // NaN in the data poisons np.quantile
+            } else {
+                const double total = cs[P2 - 1];
+                // first sorted position whose normalised cumulative weight reaches q (:542-544)
+                int lo = 0, hi = S;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (cs[mid] / total >= q) hi = mid; else lo = mid + 1;
+                }
+                if (lo >= S) val = keys[S - 1];      // :545-546
+                else if (lo == 0) val = keys[0];     // :549-550
+                else {
+                    const double w1 = cs[lo - 1] / total, w2 = cs[lo] / total;
+                    const double x1 = keys[lo - 1];
+                    val = x1 + (keys[lo] - x1) * (q - w1) / (w2 - w1);  // :552-554
+                }
+            }
+            p.out[row * p.n_probs + tid] = val;
+        }
+        __syncthreads();
+    }
+}
+
 // ===================================================================================== host side
 static size_t is_smem_bytes(int S) { return sizeof(double) * (IS_RED_WORDS + (size_t)((S + 1) & ~1)); }
 constexpr size_t SMEM_LIMIT = 227 * 1024;
@@ -733,6 +866,18 @@ cudaError_t eloo_launch(const ElooParams& p, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     if (info[0]) eloo_row_kernel<true><<<info[1], IS_NT, info[2], st>>>(p);
     else eloo_row_kernel<false><<<info[1], IS_NT, info[2], st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t eloo_quantile_launch(QuantParams p, cudaStream_t st) {
+    int p2 = IS_NT;
+    while (p2 < p.S) p2 <<= 1;
+    p.P2 = p2;
+    const size_t smem = sizeof(double) * (IS_RED_WORDS + 2 * (size_t)p2 + IS_NT) + sizeof(int) * (size_t)p2;
+    int info[4];
+    cudaError_t e = plan_kernel(eloo_quantile_kernel, smem, p.n_rows, info);
+    if (e != cudaSuccess) return e;
+    eloo_quantile_kernel<<<info[1], IS_NT, info[2], st>>>(p);
     return cudaGetLastError();
 }
 

@@ -45,11 +45,28 @@ struct ElooParams {
     int bulk;
 };
 
+constexpr int ELOO_MAX_PROBS = 32;
+constexpr int ELOO_QUANT_MAX_S = 8192;  // sort buffer: 20 B per (padded) draw in shared memory
+
+struct QuantParams {
+    const double* x;  // draws, rows of S doubles
+    long long x_stride;
+    const double* lw;  // log weights rows (any normalisation)
+    long long lw_stride;
+    double* out;  // N x n_probs
+    long long n_rows;
+    int S;
+    int P2;  // S padded to a power of two (>= 256)
+    int n_probs;
+    double probs[ELOO_MAX_PROBS];
+};
+
 // Launch planners + launchers.  `*_info`: [0] staged in shared memory, [1] grid, [2] dynamic smem bytes,
 // [3] CTAs per SM.  The e_loo launcher needs `scratch` only when info[0] == 0.
 cudaError_t is_plan(int method, int mode, int S, long long n_rows, int* info);
 cudaError_t is_launch(int method, int mode, const IsParams& p, cudaStream_t st);
 cudaError_t eloo_plan(int S, long long n_rows, bool lr_same, bool has_x, int* info);
 cudaError_t eloo_launch(const ElooParams& p, cudaStream_t st);
+cudaError_t eloo_quantile_launch(QuantParams p, cudaStream_t st);  // fills p.P2
 
 }  // namespace b2l

@@ -853,6 +853,27 @@ extern "C" int b2l_eloo_dev_f64(const double* x, int64_t x_stride_n, const doubl
     return 0;
 }
 
+extern "C" int b2l_eloo_quantile_dev_f64(const double* x, int64_t x_stride_n, const double* lw,
+                                         int64_t lw_stride_n, int64_t S, int64_t N, const double* probs,
+                                         int32_t n_probs, double* value_out, void* stream) {
+    if (!x || !lw || !probs || !value_out || N < 0 || S < 1) return fail(B2L_E_INVALID, "null pointer or bad size");
+    if (n_probs < 1 || n_probs > ELOO_MAX_PROBS) return fail(B2L_E_INVALID, "n_probs must be in 1..%d", ELOO_MAX_PROBS);
+    if (S > ELOO_QUANT_MAX_S)
+        return fail(B2L_E_UNSUPPORTED, "weighted quantiles sort each row in shared memory: S <= %d", ELOO_QUANT_MAX_S);
+    for (int i = 0; i < n_probs; ++i)
+        if (!(probs[i] > 0.0 && probs[i] < 1.0)) return fail(B2L_E_INVALID, "probs must be between 0 and 1");  // e_loo.py:161-162
+    if (N == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    QuantParams p;
+    memset(&p, 0, sizeof(p));
+    p.x = x; p.x_stride = x_stride_n; p.lw = lw; p.lw_stride = lw_stride_n; p.out = value_out;
+    p.n_rows = N; p.S = (int)S; p.n_probs = n_probs;
+    for (int i = 0; i < n_probs; ++i) p.probs[i] = probs[i];
+    ProfScope prof(B2L_PROF_ELOO, st);
+    CK(eloo_quantile_launch(p, st));
+    return 0;
+}
+
 extern "C" int b2l_handover_reasons(uint64_t* out16, int32_t reset) {
     if (!out16) return fail(B2L_E_INVALID, "null pointer");
     unsigned long long a[HO_REASONS], b[HO_REASONS];

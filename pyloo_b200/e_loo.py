@@ -136,8 +136,8 @@ def e_loo(data, var_name=None, group="posterior_predictive", weights=None, log_w
           log_ratios=None, type="mean", probs=None) -> ExpectationResult:  # noqa: A002 (reference signature)
     """Weighted mean / variance / sd of posterior(-predictive) draws under importance weights.
 
-    Same parameters and errors as ``pyloo.e_loo`` (e_loo.py:56-263).  ``type="quantile"`` is not built yet
-    and raises ``NotImplementedError`` (it needs a full per-observation sort; listed as next in DESIGN.md).
+    Same parameters and errors as ``pyloo.e_loo`` (e_loo.py:56-263).  ``type="quantile"`` returns a trailing
+    ``quantile`` dimension of ``len(probs)`` (e_loo.py:509-515) and supports up to 8192 draws per observation.
     """
     if type not in ["mean", "variance", "sd", "quantile"]:
         raise ValueError("type must be 'mean', 'variance', 'sd' or 'quantile'")
@@ -184,21 +184,22 @@ def e_loo(data, var_name=None, group="posterior_predictive", weights=None, log_w
         lrv, _ = _sample_last(log_ratios, "log_ratios")
         lr2 = _as_rows(lrv, obs_shape, S, "log_ratios")
 
-    if type == "quantile":
-        raise NotImplementedError("e_loo(type='quantile') is not built on the B200 path yet")
-    value, k = engine.eloo_host(x2, lw2, lr2, type, 20)
-
-    k = k.reshape(obs_shape)
-    value = value.reshape(obs_shape)
     template = x_data if is_dataarray_like(x_data) else None
+    if type == "quantile":  # e_loo.py:226-227, :232-233: h is None, k comes from the ratios alone
+        value = engine.eloo_quantile_host(x2, lw2, probs_array).reshape(*obs_shape, len(probs_array))
+        _, k = engine.eloo_host(None, lw2 if lr2 is None else lr2, None, "none", 20)
+    else:
+        value, k = engine.eloo_host(x2, lw2, lr2, type, 20)
+        value = value.reshape(obs_shape)
+    k = k.reshape(obs_shape)
 
-    def wrap(arr, name):
+    def wrap(arr, name, extra_dims=()):
         if template is None:
             return arr if arr.ndim else arr[()]
-        return wrap_like(template, arr, obs_dims, name)
+        return wrap_like(template, arr, (*obs_dims, *extra_dims), name)
 
     return ExpectationResult(
-        value=wrap(value, getattr(x_data, "name", None)),
+        value=wrap(value, getattr(x_data, "name", None), ("quantile",) if type == "quantile" else ()),
         pareto_k=wrap(k, "pareto_k"),
         min_ss=wrap(np.asarray(_pareto_min_ss(k)), "min_ss"),                          # e_loo.py:248
         khat_threshold=wrap(np.full(obs_shape, _pareto_khat_threshold(S)), "khat_threshold"),  # :249

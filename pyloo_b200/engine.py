@@ -402,6 +402,45 @@ def eloo_cuda(x, lw, lr=None, kind: str = "mean", tail_len: int = 20, *, workspa
     return value, khat
 
 
+def eloo_quantile_cuda(x, lw, probs):
+    """Weighted quantiles (pyloo/e_loo.py:466-554) of device-resident float64 ``(N, S)`` tensors with
+    contiguous rows; ``probs`` is a host sequence in (0, 1).  Asynchronous.  Returns an ``(N, len(probs))`` tensor."""
+    torch = _torch()
+    lib = _native.load()
+    for t in (x, lw):
+        if t.dtype != torch.float64 or t.dim() != 2 or not t.is_cuda:
+            raise ValueError("expected 2-D float64 CUDA tensors")
+    if x.shape != lw.shape:
+        raise ValueError("x and log_weights must have the same shape")
+    x = x if (x.shape[1] == 1 or x.stride(1) == 1) else x.contiguous()
+    lw = lw if (lw.shape[1] == 1 or lw.stride(1) == 1) else lw.contiguous()
+    N, S = x.shape
+    pr = np.ascontiguousarray(np.atleast_1d(np.asarray(probs, dtype=np.float64)))
+    out = torch.empty((N, pr.size), dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.b2l_eloo_quantile_dev_f64(x.data_ptr(), x.stride(0), lw.data_ptr(), lw.stride(0), S, N,
+                                           pr.ctypes.data, int(pr.size), out.data_ptr(),
+                                           _stream_ptr(torch, x.device))
+    _native.check(rc)
+    return out
+
+
+def eloo_quantile_host(x_ns, lw_ns, probs, *, device=None):
+    """Weighted quantiles on HOST ``(N, S)`` arrays.  Returns an ``(N, len(probs))`` array."""
+    torch = _torch()
+    x = np.asarray(x_ns, dtype=np.float64)
+    lw = np.asarray(lw_ns, dtype=np.float64)
+    N, S = lw.shape
+    pr = np.atleast_1d(np.asarray(probs, dtype=np.float64))
+    out = np.empty((N, pr.size), dtype=np.float64)
+    dev = _dev(device)
+    for i0, i1 in _slabs(N, 16 * S):
+        d_x = torch.from_numpy(np.ascontiguousarray(x[i0:i1])).to(dev)
+        d_lw = torch.from_numpy(np.ascontiguousarray(lw[i0:i1])).to(dev)
+        out[i0:i1] = eloo_quantile_cuda(d_x, d_lw, pr).cpu().numpy()
+    return out
+
+
 def _slabs(N: int, row_bytes: int):
     step = max(1, min(N, _CHUNK_BYTES // max(row_bytes, 1)))
     for i0 in range(0, N, step):

@@ -198,6 +198,47 @@ def test_eloo_tie_heavy_rows_take_the_exact_extraction():
     assert np.isinf(ref["pareto_k"][0])
 
 
+def test_eloo_quantiles_against_reference_vectors():
+    g = golden("is_eloo.npz")
+    with np.errstate(all="ignore"):
+        q = engine.eloo_quantile_host(g["eloo_x"], g["eloo_lw"], g["eloo_probs"])
+    # rows: 3 constant draws, 5 NaN / 6 inf in the draws, 7 uniform weights (np.quantile rule)
+    close(q, g["eloo_quant"], 1e-10, atol=1e-13)
+
+
+@pytest.mark.parametrize("S", [5, 256, 300, 1000, 4000, 8192])
+def test_eloo_quantiles_against_oracle(S):
+    rng = np.random.default_rng(S)
+    N = 9
+    x = rng.normal(size=(N, S)) * 3 + 1
+    lw = rng.standard_t(3, size=(N, S))
+    lw[1] = 0.7                                              # uniform weights: np.quantile's linear rule
+    lw[2, : S // 2] = -800.0                                 # half of the weights underflow to 0
+    probs = [0.001, 0.1, 0.5, 0.9, 0.999]
+    q = engine.eloo_quantile_host(x, lw, probs)
+    ref = iso.e_loo_arrays(x, lw, None, "quantile", probs=probs)["value"]
+    close(q, ref, 1e-9, atol=1e-12)
+    assert np.all(np.diff(q, axis=1) >= 0)                    # monotone in the probability
+
+
+def test_eloo_quantile_api_and_limits():
+    rng = np.random.default_rng(4)
+    x = LiteDataArray(rng.normal(size=(5, 3, 600)), ("a", "b", "__sample__"), name="y")
+    lw = LiteDataArray(rng.normal(size=(5, 3, 600)), ("a", "b", "__sample__"))
+    res = pl.e_loo(x, log_weights=lw, type="quantile", probs=[0.25, 0.75])
+    assert res.value.dims == ("a", "b", "quantile") and res.value.shape == (5, 3, 2)
+    ref = iso.e_loo_arrays(x.values.reshape(15, 600), lw.values.reshape(15, 600), None, "quantile",
+                           probs=[0.25, 0.75])
+    close(res.value.values.reshape(15, 2), ref["value"], 1e-9, atol=1e-12)
+    close(res.pareto_k.values.ravel(), ref["pareto_k"], 1e-12)      # h is None: ratio tail only
+    one = pl.e_loo(x, log_weights=lw, type="quantile", probs=0.5)
+    assert one.value.shape == (5, 3, 1)
+    with pytest.raises(ValueError, match="probs must be between 0 and 1"):
+        pl.e_loo(x, log_weights=lw, type="quantile", probs=[0.5, 1.0])
+    with pytest.raises(NotImplementedError, match="S <= 8192"):
+        engine.eloo_quantile_host(np.zeros((1, 9000)), np.zeros((1, 9000)), [0.5])
+
+
 def test_eloo_api_and_diagnostics():
     rng = np.random.default_rng(8)
     ll = -1.0 + 0.5 * rng.normal(size=(4, 300, 6))

@@ -49,6 +49,7 @@ for name, fn, bytes_per_obs in (
     ("e_loo mean (lw + lr)", lambda: engine.eloo_cuda(x, lw, lr, "mean"), 24 * S + 16),
     ("e_loo sd (lw + lr)", lambda: engine.eloo_cuda(x, lw, lr, "sd"), 24 * S + 16),
     ("e_loo k only", lambda: engine.eloo_cuda(None, lw, lr, "none"), 16 * S + 8),
+    ("e_loo quantiles x3", lambda: engine.eloo_quantile_cuda(x, lw, [0.05, 0.5, 0.95]), 16 * S + 24),
 ):
     ms = timeit(fn)
     gbs = bytes_per_obs * N / ms / 1e6
