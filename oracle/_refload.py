@@ -36,7 +36,7 @@ def load_reference_modules(names=("utils", "psis")):
     NumPy-only numerics of ``sis``, ``tis`` and ``e_loo`` (their xarray drivers are not callable)."""
     if not reference_available():
         raise RuntimeError(f"reference tree not found under {REFERENCE_ROOT}")
-    keys = ["xarray", "arviz", "pyloo"] + [f"pyloo.{n}" for n in names]
+    keys = ["xarray", "arviz", "arviz.data", "pyloo"] + [f"pyloo.{n}" for n in names]
     saved = {k: sys.modules.get(k) for k in keys}
     try:
         class _DataArray:  # placeholder type for isinstance checks only
@@ -51,7 +51,11 @@ def load_reference_modules(names=("utils", "psis")):
         if "xarray" not in sys.modules:
             sys.modules["xarray"] = _stub("xarray", DataArray=_DataArray, apply_ufunc=_apply_ufunc)
         if "arviz" not in sys.modules:
-            sys.modules["arviz"] = _stub("arviz", InferenceData=_InferenceData)
+            az = _stub("arviz", InferenceData=_InferenceData)
+            az.__path__ = []  # a package, so that ``from arviz.data import InferenceData`` resolves
+            az.data = _stub("arviz.data", InferenceData=_InferenceData)
+            sys.modules["arviz"] = az
+            sys.modules["arviz.data"] = az.data
         pkg = types.ModuleType("pyloo")
         pkg.__path__ = [os.path.join(REFERENCE_ROOT, "pyloo")]
         sys.modules["pyloo"] = pkg

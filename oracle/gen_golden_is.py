@@ -27,7 +27,8 @@ GOLDEN = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
 
 def main():
-    mods = _refload.load_reference_modules(("utils", "psis", "sis", "tis", "e_loo"))
+    mods = _refload.load_reference_modules(("utils", "psis", "sis", "tis", "e_loo", "rcparams",
+                                            "loo_predictive_metric", "loo_score"))
     utils, sis, tis, eloo = mods["utils"], mods["sis"], mods["tis"], mods["e_loo"]
     rng = np.random.default_rng(20261019)
     out = {}
@@ -105,6 +106,22 @@ def main():
     out["diag_min_ss"] = np.array([eloo._pareto_min_ss(k) for k in ks])
     out["diag_rate"] = np.array([eloo._pareto_convergence_rate(k, S) for k in ks])
     out["diag_thr"] = np.array([eloo._pareto_khat_threshold(S)])
+
+    # metric and score formulas of the e_loo consumers (pyloo/loo_predictive_metric.py:234-356,
+    # pyloo/loo_score.py:326-346)
+    lpm, lsc = mods["loo_predictive_metric"], mods["loo_score"]
+    yv = rng.normal(size=40)
+    yh = yv + 0.3 * rng.normal(size=40)
+    yb = (rng.random(40) < 0.4).astype(float)
+    ph = np.clip(0.5 + 0.4 * (yb - 0.5) + 0.3 * rng.normal(size=40), 0, 1)
+    out.update(metric_y=yv, metric_yhat=yh, metric_yb=yb, metric_phat=ph)
+    for name, fn, a, b in (("mae", lpm._mae, yv, yh), ("mse", lpm._mse, yv, yh), ("rmse", lpm._rmse, yv, yh),
+                           ("acc", lpm._accuracy, yb, ph), ("balanced_acc", lpm._balanced_accuracy, yb, ph)):
+        r = fn(a, b)
+        out[f"metric_{name}"] = np.array([r["estimate"], r["se"]])
+    exx, exy = rng.random(12) + 0.5, rng.random(12) + 0.2
+    out.update(crps_exx=exx, crps_exy=exy, crps_plain=lsc._crps(exx, exy, scale=False),
+               crps_scaled=lsc._crps(exx, exy, scale=True))
 
     np.savez_compressed(os.path.join(GOLDEN, "is_eloo.npz"), **out)
     print("written", os.path.join(GOLDEN, "is_eloo.npz"),

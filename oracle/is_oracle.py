@@ -26,10 +26,12 @@ from __future__ import annotations
 import numpy as np
 
 from .psis_oracle import gpdfit, logsumexp_row
+from .psis_oracle import psislw as _psislw_oracle
 
 __all__ = ["sislw_row", "tislw_row", "islw", "loo_is_pointwise", "loo_is_summary", "k_hat",
            "weighted_mean", "weighted_variance", "weighted_quantile", "e_loo_arrays", "pareto_min_ss",
-           "pareto_khat_threshold", "pareto_convergence_rate"]
+           "pareto_khat_threshold", "pareto_convergence_rate", "predictive_metric",
+           "loo_predictive_metric_arrays", "crps", "loo_score_arrays"]
 
 
 # ------------------------------------------------------------------------------- SIS / TIS
@@ -220,3 +222,63 @@ def e_loo_arrays(x_ns, lw_ns, lr_ns=None, kind: str = "mean", probs=None, tail_l
     return {"value": value, "pareto_k": k, "min_ss": np.array([pareto_min_ss(v) for v in k]),
             "khat_threshold": np.full(N, pareto_khat_threshold(S)),
             "convergence_rate": np.array([pareto_convergence_rate(v, S) for v in k])}
+
+
+# ------------------------------------------------------------------------------- consumers of e_loo
+def predictive_metric(y, yhat, metric: str) -> dict:
+    """pyloo/loo_predictive_metric.py:234-356 (``_mae``, ``_mse``, ``_rmse``, ``_accuracy``,
+    ``_balanced_accuracy``)."""
+    y = np.asarray(y)
+    yhat = np.asarray(yhat)
+    n = len(y)
+    if metric in ("mae", "mse", "rmse"):
+        e = np.abs(y - yhat) if metric == "mae" else (y - yhat) ** 2
+        est, se = np.mean(e), np.std(e, ddof=1) / np.sqrt(n)
+        if metric == "rmse":                                  # :291-298
+            return {"estimate": np.sqrt(est), "se": np.sqrt(se**2 / est / 4)}
+        return {"estimate": est, "se": se}
+    pred = (yhat > 0.5).astype(int)
+    if metric == "acc":                                       # :319-326
+        est = np.mean((pred == y).astype(int))
+        return {"estimate": est, "se": np.sqrt(est * (1 - est) / n)}
+    mask = y == 0                                             # :347-356
+    tn = np.mean(pred[mask] == y[mask])
+    tp = np.mean(pred[~mask] == y[~mask])
+    return {"estimate": (tp + tn) / 2, "se": np.sqrt((tp * (1 - tp) + tn * (1 - tn)) / 4 / n)}
+
+
+def loo_predictive_metric_arrays(x_ns, ll_ns, y, metric: str, reff: float = 1.0) -> dict:
+    """pyloo/loo_predictive_metric.py:208-231 on ``(N, S)`` arrays: PSIS weights of ``-ll``, weighted mean of
+    the predictive draws, metric against ``y``."""
+    ll = np.asarray(ll_ns, dtype=np.float64)
+    lw, _ = _psislw_oracle(-ll, reff)
+    pred = e_loo_arrays(x_ns, lw, -ll, "mean")["value"]
+    return predictive_metric(np.asarray(y).flatten(), pred, metric)
+
+
+def crps(exx, exy, scale: bool = False):
+    """pyloo/loo_score.py:343-346."""
+    if scale:
+        return -exy / exx - 0.5 * np.log(exx)
+    return 0.5 * exx - exy
+
+
+def loo_score_arrays(x_ns, x2_ns, ll_ns, y, permutations: int = 1, reff: float = 1.0, scale: bool = False):
+    """pyloo/loo_score.py:219-246 and :304-323 on ``(N, S)`` arrays (``y`` of length N).  Draws the shuffles
+    from NumPy's global generator like the reference (:306)."""
+    x = np.asarray(x_ns, dtype=np.float64)
+    x2 = np.asarray(x2_ns, dtype=np.float64)
+    ll = np.asarray(ll_ns, dtype=np.float64)
+    S = x.shape[-1]
+    exx = 0
+    for _ in range(permutations):
+        shuffle = np.random.permutation(S)                     # :306
+        joint = -ll - ll[:, shuffle]                           # :308-311
+        lw, _ = _psislw_oracle(joint, reff)                    # :312
+        exx = exx + e_loo_arrays(np.abs(x - x2[:, shuffle]), lw, joint, "mean")["value"]  # :314-321
+    exx = exx / permutations                                   # :225
+    lw, k = _psislw_oracle(-ll, reff)                          # :227
+    exy = e_loo_arrays(np.abs(x - np.asarray(y, dtype=np.float64).reshape(-1, 1)), lw, -ll, "mean")["value"]
+    pw = crps(exx, exy, scale)
+    return {"pointwise": pw, "estimate": float(pw.mean()), "se": float(pw.std() / np.sqrt(pw.size)),
+            "pareto_k": k}

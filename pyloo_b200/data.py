@@ -143,12 +143,15 @@ def from_dict(posterior=None, log_likelihood=None, dims=None, **other):
     pyloo/tests/helpers.py:64-84)."""
     dims = dims or {}
 
-    def group(block):
+    def group(block, sampled=True):
         out = {}
         for var, arr in block.items():
             arr = np.asarray(arr)
-            extra = dims.get(var) or [f"{var}_dim_{i}" for i in range(arr.ndim - 2)]
-            out[var] = LiteDataArray(arr, ("chain", "draw", *extra), name=var)
+            if sampled:
+                extra = dims.get(var) or [f"{var}_dim_{i}" for i in range(arr.ndim - 2)]
+                out[var] = LiteDataArray(arr, ("chain", "draw", *extra), name=var)
+            else:  # observed_data / constant_data carry no chain / draw dimensions
+                out[var] = LiteDataArray(arr, dims.get(var) or [f"{var}_dim_{i}" for i in range(arr.ndim)], name=var)
         return LiteDataset(out)
 
     groups = {}
@@ -158,7 +161,7 @@ def from_dict(posterior=None, log_likelihood=None, dims=None, **other):
         groups["log_likelihood"] = group(log_likelihood)
     for name, block in other.items():
         if isinstance(block, dict):
-            groups[name] = group(block)
+            groups[name] = group(block, sampled=name not in ("observed_data", "constant_data"))
     return InferenceDataLite(**groups)
 
 

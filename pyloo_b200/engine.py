@@ -511,3 +511,34 @@ def eloo_host(x_ns, lw_ns, lr_ns=None, kind: str = "mean", tail_len: int = 20, *
             value[i0:i1] = v.cpu().numpy()
         khat[i0:i1] = k.cpu().numpy()
     return value, khat
+
+
+def psis_expectation_host(x_ns, lr_ns, reff: float = 1.0, kind: str = "mean", tail_len: int = 20, *, device=None):
+    """PSIS weights of the raw log ratios ``lr_ns`` chained with the weighted expectation of ``x_ns`` under
+    them, both ``(N, S)`` HOST arrays -- what ``loo_predictive_metric`` and ``loo_score`` do through
+    ``psislw`` + ``e_loo`` (pyloo/loo_predictive_metric.py:208-218, pyloo/loo_score.py:227-237, :311-321).
+    The smoothed ``(N, S)`` weights never leave the device.
+    Returns ``(value (N,), khat (N,), pareto_k (N,))``."""
+    torch = _torch()
+    lr = np.asarray(lr_ns, dtype=np.float64)
+    x = np.asarray(x_ns, dtype=np.float64)
+    if lr.ndim != 2 or x.shape != lr.shape:
+        raise ValueError("x and log ratios must be 2-D arrays of the same shape")
+    N, S = lr.shape
+    M = tail_length(S, reff)
+    _check_tail(S, M)
+    value, khat, pk = (np.empty(N, dtype=np.float64) for _ in range(3))
+    dev = _dev(device)
+    ws = lw = None
+    for i0, i1 in _slabs(N, 40 * S):
+        d_lr = torch.from_numpy(np.ascontiguousarray(lr[i0:i1])).to(dev)
+        d_x = torch.from_numpy(np.ascontiguousarray(x[i0:i1])).to(dev)
+        if ws is None:
+            ws = workspace_for(S, i1 - i0, reff, False, dev)
+            lw = torch.empty((i1 - i0, S), dtype=torch.float64, device=dev)
+        d_lw, d_k = psislw_cuda(d_lr, reff, out=lw[: i1 - i0], workspace=ws)
+        d_v, d_kh = eloo_cuda(d_x, d_lw, d_lr, kind, tail_len)
+        value[i0:i1] = d_v.cpu().numpy()
+        khat[i0:i1] = d_kh.cpu().numpy()
+        pk[i0:i1] = d_k.cpu().numpy()
+    return value, khat, pk

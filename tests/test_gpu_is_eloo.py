@@ -275,3 +275,68 @@ def test_eloo_api_and_diagnostics():
     close(kd.values, ref["pareto_k"], 1e-12)
     with pytest.raises(ValueError, match="tail_len must be at least 5"):
         pl.compute_pareto_k(x[0], x[0], tail_len=3)
+
+
+# ------------------------------------------------------------------------------------ consumers of e_loo
+def _predictive_model(seed=5, chains=4, draws=300, n_obs=12):
+    rng = np.random.default_rng(seed)
+    ll = -1.0 + 0.6 * rng.normal(size=(chains, draws, n_obs))
+    yrep = rng.normal(size=(chains, draws, n_obs)) + np.linspace(-1, 1, n_obs)
+    yrep2 = yrep + 0.1 * rng.normal(size=yrep.shape)
+    y = rng.normal(size=n_obs) + np.linspace(-1, 1, n_obs)
+    idata = from_dict(posterior={"mu": rng.normal(size=(chains, draws))}, log_likelihood={"y": ll},
+                      posterior_predictive={"y": yrep, "y2": yrep2}, observed_data={"y": y},
+                      dims={"y": ["obs"], "y2": ["obs"]})
+    rows = lambda a: a.reshape(-1, n_obs).T  # noqa: E731  (N, S) with stack(chain, draw) order
+    return idata, rows(ll), rows(yrep), rows(yrep2), y
+
+
+@pytest.mark.parametrize("metric", ["mae", "mse", "rmse"])
+def test_loo_predictive_metric(metric):
+    idata, ll, yrep, _, y = _predictive_model()
+    res = pl.loo_predictive_metric(idata, y, var_name="y", metric=metric, r_eff=0.8)
+    ref = iso.loo_predictive_metric_arrays(yrep, ll, y, metric, 0.8)
+    close(res["estimate"], ref["estimate"], 1e-9)
+    close(res["se"], ref["se"], 1e-9)
+
+
+def test_loo_predictive_metric_binary_and_errors():
+    rng = np.random.default_rng(9)
+    ll = -0.7 + 0.3 * rng.normal(size=(2, 400, 30))
+    prob = np.clip(rng.random(size=(2, 400, 30)), 0.01, 0.99)
+    yb = (rng.random(30) < 0.5).astype(float)
+    idata = from_dict(posterior={"mu": rng.normal(size=(2, 400))}, log_likelihood={"y": ll},
+                      posterior_predictive={"y": prob}, dims={"y": ["obs"]})
+    for metric in ("acc", "balanced_acc"):
+        res = pl.loo_predictive_metric(idata, yb, metric=metric)
+        ref = iso.loo_predictive_metric_arrays(prob.reshape(-1, 30).T, ll.reshape(-1, 30).T, yb, metric)
+        close([res["estimate"], res["se"]], [ref["estimate"], ref["se"]], 1e-9)
+    with pytest.raises(ValueError, match="Invalid metric"):
+        pl.loo_predictive_metric(idata, yb, metric="f1")
+    with pytest.raises(ValueError, match=r"Length of y \(3\) must match"):
+        pl.loo_predictive_metric(idata, yb[:3])
+    with pytest.raises(ValueError, match="does not have a nope group"):
+        pl.loo_predictive_metric(idata, yb, group="nope")
+
+
+@pytest.mark.parametrize("scale", [False, True])
+def test_loo_score(scale):
+    idata, ll, yrep, yrep2, y = _predictive_model(seed=6)
+    # The shuffles come from NumPy's global stream.  Seed 131: neither permutation has a 2-cycle.  A 2-cycle
+    # (s <-> s') makes joint[s] == joint[s'] exactly; if that tie falls in the PSIS tail, which of the two draws
+    # receives which smoothed value follows np.argsort's unspecified order among equal keys in the reference
+    # (draw-index order here), and |x - x2| differs between the two draws.
+    np.random.seed(131)
+    res = pl.loo_score(idata, x_var="y", x2_var="y2", y_var="y", permutations=2, reff=1.0, scale=scale,
+                       pointwise=True)
+    np.random.seed(131)
+    ref = iso.loo_score_arrays(yrep, yrep2, ll, y, permutations=2, reff=1.0, scale=scale)
+    close(res.pointwise, ref["pointwise"], 1e-8)
+    close(res.estimates["Estimate"][0], ref["estimate"], 1e-8)
+    close(res.estimates["SE"][0], ref["se"], 1e-8)
+    close(res.pareto_k.values, ref["pareto_k"])
+    assert res.good_k == pytest.approx(min(1 - 1 / np.log10(1200), 0.7)) and res.warning in (True, False)
+    plain = pl.loo_score(idata, x_var="y", x2_var="y2", y_var="y", reff=1.0)
+    assert plain.pareto_k is None and plain.pointwise.shape == (12,)
+    with pytest.raises(ValueError, match="Variable 'zz' not found"):
+        pl.loo_score(idata, x_var="zz", y_var="y")

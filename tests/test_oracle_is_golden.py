@@ -84,6 +84,38 @@ def test_pareto_diagnostics():
     _close(iso.pareto_khat_threshold(4000), g["diag_thr"][0])
 
 
+def test_metric_and_score_formulas():
+    g = golden("is_eloo.npz")
+    for name in ("mae", "mse", "rmse"):
+        r = iso.predictive_metric(g["metric_y"], g["metric_yhat"], name)
+        _close([r["estimate"], r["se"]], g[f"metric_{name}"])
+    for name in ("acc", "balanced_acc"):
+        r = iso.predictive_metric(g["metric_yb"], g["metric_phat"], name)
+        _close([r["estimate"], r["se"]], g[f"metric_{name}"])
+    _close(iso.crps(g["crps_exx"], g["crps_exy"]), g["crps_plain"])
+    _close(iso.crps(g["crps_exx"], g["crps_exy"], scale=True), g["crps_scaled"])
+
+
+def test_product_metric_formulas_match_reference_vectors():
+    # host-side formulas of the product (no GPU needed): pyloo_b200.loo_predictive_metric / loo_score
+    import importlib
+
+    lpm = importlib.import_module("pyloo_b200.loo_predictive_metric")  # the package re-exports the functions
+    lsc = importlib.import_module("pyloo_b200.loo_score")
+
+    g = golden("is_eloo.npz")
+    for name, fn, a, b in (("mae", lpm._mae, "metric_y", "metric_yhat"), ("mse", lpm._mse, "metric_y", "metric_yhat"),
+                           ("rmse", lpm._rmse, "metric_y", "metric_yhat"),
+                           ("acc", lpm._accuracy, "metric_yb", "metric_phat"),
+                           ("balanced_acc", lpm._balanced_accuracy, "metric_yb", "metric_phat")):
+        r = fn(g[a], g[b])
+        _close([r["estimate"], r["se"]], g[f"metric_{name}"])
+    _close(lsc._crps(g["crps_exx"], g["crps_exy"]), g["crps_plain"])
+    _close(lsc._crps(g["crps_exx"], g["crps_exy"], scale=True), g["crps_scaled"])
+    with pytest.raises(ValueError, match="y must contain values between 0 and 1"):
+        lpm._accuracy(np.array([0.0, 2.0]), np.array([0.1, 0.9]))
+
+
 @pytest.mark.skipif(not _refload.reference_available(), reason="reference tree not present")
 def test_restatement_against_live_reference():
     mods = _refload.load_reference_modules(("utils", "psis", "sis", "tis", "e_loo"))
