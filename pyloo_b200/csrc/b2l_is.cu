@@ -69,7 +69,10 @@ __device__ __forceinline__ const double* stage_rows(double* const* dst, const do
 }
 
 // ===================================================================================== SIS / TIS
-template <int METHOD, int MODE, bool STAGED>
+// EPT > 0 (TIS, S <= IS_NT * EPT): the exp of every draw is kept in EPT registers per thread, so the sum over
+// the truncated row reuses it (exp(min(x, cut) - m) == min(exp(x) * exp(-m), exp(cut - m)) up to rounding)
+// instead of evaluating a second exp per draw.
+template <int METHOD, int MODE, bool STAGED, int EPT = 0>
 __global__ void __launch_bounds__(IS_NT) is_row_kernel(const IsParams p) {
     extern __shared__ __align__(16) unsigned char is_smem[];
     double* red = reinterpret_cast<double*>(is_smem);
@@ -122,12 +125,26 @@ __global__ void __launch_bounds__(IS_NT) is_row_kernel(const IsParams p) {
 
         // ---- pass 2: first logsumexp (max of x is 0 by construction)
         double s1 = 0.0, s2 = 0.0, sl = 0.0;
-        for (int s = tid; s < S; s += IS_NT) {
-            const double v = lwraw(s);
-            const double e = exp(v - mx);
-            s1 += e;
-            s2 += e * e;
-            if (MODE == IS_MODE_LOO) sl += exp(mn - v);  // exp(ll - max ll)
+        double ecache[EPT > 0 ? EPT : 1];
+        if (EPT > 0) {
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) {
+                const int s = tid + i * IS_NT;
+                const double v = (s < S) ? lwraw(s) : -inf_f64();
+                const double e = (s < S) ? exp(v - mx) : 0.0;
+                ecache[i] = e;
+                s1 += e;
+                if (MODE == IS_MODE_LOO && s < S) sl += exp(mn - v);
+            }
+        } else {
+#pragma unroll 4
+            for (int s = tid; s < S; s += IS_NT) {
+                const double v = lwraw(s);
+                const double e = exp(v - mx);
+                s1 += e;
+                s2 += e * e;
+                if (MODE == IS_MODE_LOO) sl += exp(mn - v);  // exp(ll - max ll)
+            }
         }
         s1 = block_sum<IS_NT>(s1, red);
         if (MODE == IS_MODE_LOO) sl = block_sum<IS_NT>(sl, red);
@@ -141,10 +158,21 @@ __global__ void __launch_bounds__(IS_NT) is_row_kernel(const IsParams p) {
             cut = log_z + 0.5 * p.log_S;             // tis.py:114
             const double mx2 = np_minimum(0.0, cut); // max of the truncated row
             double t1 = 0.0, t2 = 0.0;
-            for (int s = tid; s < S; s += IS_NT) {
-                const double a = exp(np_minimum(lwraw(s) - mx, cut) - mx2);
-                t1 += a;
-                t2 += a * a;
+            if (EPT > 0) {
+                const double up = exp(-mx2), ecut = exp(cut - mx2);
+#pragma unroll
+                for (int i = 0; i < EPT; ++i) {
+                    const double a = np_minimum(ecache[i] * up, ecut);  // 0 for the slots past S
+                    t1 += a;
+                    t2 += a * a;
+                }
+            } else {
+#pragma unroll 4
+                for (int s = tid; s < S; s += IS_NT) {
+                    const double a = exp(np_minimum(lwraw(s) - mx, cut) - mx2);
+                    t1 += a;
+                    t2 += a * a;
+                }
             }
             t1 = block_sum<IS_NT>(t1, red);
             t2 = block_sum<IS_NT>(t2, red);
@@ -155,6 +183,7 @@ __global__ void __launch_bounds__(IS_NT) is_row_kernel(const IsParams p) {
         // ---- output
         if (MODE == IS_MODE_WEIGHTS) {
             double* dst = p.out + row * p.out_stride;
+#pragma unroll 4
             for (int s = tid; s < S; s += IS_NT) {
                 double x = lwraw(s) - mx;
                 if (METHOD == IS_METHOD_TIS) x = np_minimum(x, cut);
@@ -164,6 +193,7 @@ __global__ void __launch_bounds__(IS_NT) is_row_kernel(const IsParams p) {
         } else {
             // elpd_i = logsumexp(lw + ll)  (loo.py:289, :319-324)
             double tmax = -inf_f64();
+#pragma unroll 4
             for (int s = tid; s < S; s += IS_NT) {
                 const double v = lwraw(s);
                 double x = v - mx;
@@ -172,6 +202,7 @@ __global__ void __launch_bounds__(IS_NT) is_row_kernel(const IsParams p) {
             }
             tmax = block_max<IS_NT>(tmax, red);
             double st = 0.0;
+#pragma unroll 4
             for (int s = tid; s < S; s += IS_NT) {
                 const double v = lwraw(s);
                 double x = v - mx;
@@ -284,30 +315,6 @@ __device__ __forceinline__ void merge_warp_lists(const double* cb, int n_tail, d
             rescan();
         }
     }
-}
-
-// 32 doubles (one per lane, no NaN) sorted descending across the warp: bitonic network on shuffles
-__device__ __forceinline__ double warp_sort_desc(double v, int lane) {
-#pragma unroll
-    for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            const double o = __shfl_xor_sync(FULL, v, j);
-            const bool keep_max = (((lane & k) == 0) == ((lane & j) == 0));
-            v = keep_max ? fmax(v, o) : fmin(v, o);
-        }
-    }
-    return v;
-}
-// number of entries of the descending list d[0..32) that are > v (strict) or >= v
-__device__ __forceinline__ int count_above(const double* d, double v, bool or_equal) {
-    int lo = 0, hi = 32;  // first index whose entry is NOT above v
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        const bool above = or_equal ? (d[mid] >= v) : (d[mid] > v);
-        if (above) lo = mid + 1; else hi = mid;
-    }
-    return lo;
 }
 
 // ---- generalised Pareto fit, literal -------------------------------------------------------------
@@ -488,6 +495,7 @@ __global__ void __launch_bounds__(IS_NT) eloo_row_kernel(const ElooParams p) {
         double m_hi = -inf_f64(), m_lo = -inf_f64();  // this thread's largest h*r and largest -(h*r)
         if (has_x) {
             const bool same = (LR == LW);
+#pragma unroll 4
             for (int s = tid; s < S; s += IS_NT) {
                 const double xv = X[s];
                 const double e = exp(LW[s] - lwmax);
@@ -512,31 +520,35 @@ __global__ void __launch_bounds__(IS_NT) eloo_row_kernel(const ElooParams p) {
         __syncthreads();  // HR complete
 
         // ---- k_hat: tails of r and of h * r (e_loo.py:350-390)
-        // Top-n_tail selection.  Fast path: the n_tail-th largest of the 256 thread-local maxima is a lower
-        // bound of the n_tail-th largest element, so everything >= it is a candidate (n_tail .. a few more on
-        // ordinary rows); candidates are ranked by counting.  Rows with many ties at the threshold overflow the
-        // candidate list and take the exact extraction (warp_top) instead.
+        // Top-n_tail selection.  Fast path: every warp finds the c-th largest of its 32 thread-local maxima
+        // (c = ceil(n_tail / 8)); the smallest of those 8 values has at least 8c >= n_tail distinct elements
+        // at or above it, so it is a lower bound of the n_tail-th largest element and everything >= it is a
+        // candidate (a few dozen on ordinary rows); candidates are ranked by counting.  Rows with many ties at
+        // the threshold overflow the candidate list and take the exact extraction (warp_top) instead.
         const bool r_ok = is_finite(lrmax);
         const bool want[3] = {r_ok, need_hr, need_hr};
         {
+            const int c = (n_tail + IS_NW - 1) / IS_NW;
             const double keys[3] = {m_r, m_lo, m_hi};
-#pragma unroll
-            for (int t = 0; t < 3; ++t)
-                if (want[t]) tmax[t * IS_NT + tid] = warp_sort_desc(keys[t], lane);
-            if (tid < 3) cnt[tid] = 0;
-        }
-        __syncthreads();
-        {
-            const int K = n_tail < IS_NT ? n_tail : IS_NT;
 #pragma unroll
             for (int t = 0; t < 3; ++t) {
                 if (!want[t]) continue;
-                const double v = tmax[t * IS_NT + tid];
-                int rank = lane;
-                for (int w = 0; w < IS_NW; ++w)
-                    if (w != warp) rank += count_above(tmax + t * IS_NT + w * 32, v, w < warp);
-                if (rank == K - 1) thr[t] = v;
+                double mine = keys[t], cth = -inf_f64();
+                for (int k = 0; k < c; ++k) {  // c rounds: take the warp maximum out, one lane at a time
+                    cth = warp_max(mine);
+                    const unsigned holders = __ballot_sync(FULL, mine == cth);
+                    if (lane == __ffs(holders) - 1) mine = -inf_f64();
+                    if (cth == -inf_f64()) break;  // fewer than c lanes own elements (warp-uniform)
+                }
+                if (lane == 0) tmax[t * IS_NW + warp] = cth;
             }
+            if (tid < 3) cnt[tid] = 0;
+        }
+        __syncthreads();
+        if (tid < 3 && want[tid]) {
+            double t = tmax[tid * IS_NW];
+            for (int w = 1; w < IS_NW; ++w) t = fmin(t, tmax[tid * IS_NW + w]);
+            thr[tid] = t;
         }
         __syncthreads();
         {
@@ -810,9 +822,15 @@ static cudaError_t plan_kernel(K kern, size_t smem, long long n_rows, int* info)
     return cudaSuccess;
 }
 
+constexpr int TIS_EPT = 16;
 template <int METHOD, int MODE>
 static cudaError_t is_plan_t(int S, long long n_rows, int* info) {
     const size_t staged = is_smem_bytes(S);
+    if (METHOD == IS_METHOD_TIS && S <= IS_NT * TIS_EPT) {
+        info[0] = 2;
+        return plan_kernel(is_row_kernel<METHOD, MODE, true, (METHOD == IS_METHOD_TIS ? TIS_EPT : 0)>, staged, n_rows,
+                           info);
+    }
     if (staged <= SMEM_LIMIT) {
         info[0] = 1;
         return plan_kernel(is_row_kernel<METHOD, MODE, true>, staged, n_rows, info);
@@ -834,7 +852,9 @@ static cudaError_t is_launch_t(const IsParams& p, cudaStream_t st) {
     int info[4];
     cudaError_t e = is_plan_t<METHOD, MODE>(p.S, p.n_rows, info);
     if (e != cudaSuccess) return e;
-    if (info[0]) is_row_kernel<METHOD, MODE, true><<<info[1], IS_NT, info[2], st>>>(p);
+    if (info[0] == 2)
+        is_row_kernel<METHOD, MODE, true, (METHOD == IS_METHOD_TIS ? TIS_EPT : 0)><<<info[1], IS_NT, info[2], st>>>(p);
+    else if (info[0]) is_row_kernel<METHOD, MODE, true><<<info[1], IS_NT, info[2], st>>>(p);
     else is_row_kernel<METHOD, MODE, false><<<info[1], IS_NT, info[2], st>>>(p);
     return cudaGetLastError();
 }

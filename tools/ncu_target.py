@@ -12,6 +12,15 @@ if mode == "psislw":
     out = torch.empty_like(x)
     for _ in range(4):
         engine.psislw_cuda(x, 0.9, out=out)
+elif mode in ("sis", "tis"):
+    out = torch.empty_like(x)
+    for _ in range(3):
+        engine.islw_cuda(x, mode, out=out)
+elif mode == "eloo":
+    lw, _ = engine.islw_cuda(x, "tis")
+    h = torch.randn(N, S, dtype=torch.float64, device="cuda")
+    for _ in range(3):
+        engine.eloo_cuda(h, lw, x, "mean")
 elif mode == "loo_rows":
     for _ in range(4):
         engine.loo_cuda(x.t(), 1.0)
