@@ -173,6 +173,16 @@ int b2l_eloo_quantile_dev_f64(const double* x, int64_t x_stride_n, const double*
                               int64_t S, int64_t N, const double* probs, int32_t n_probs,
                               double* value_out, void* stream);
 
+/* loo_group (leave-one-group-out): replaces the aggregation loop pyloo/loo_group.py:188-222.
+ *   out[g * out_stride_g + s] = sum over the observations i of group g of ll(s, i), NaN -> -1e10 first
+ * with the groups given in CSR form (device arrays): members[offsets[g] .. offsets[g+1]) are the observation
+ * indices of group g in ascending order.  The G x S result (rows contiguous) then goes through
+ * b2l_loo_dev_f64 / b2l_loo_is_dev_f64 with stride_s = 1 -- one "observation" per group.
+ * counters: nullable, counters[0] += NaN inputs.                                                       */
+int b2l_group_sum_dev_f64(const double* ll, int64_t S, int64_t N, int64_t stride_s, int64_t stride_n,
+                          const int32_t* members, const int32_t* offsets, int32_t G, double* out,
+                          int64_t out_stride_g, unsigned long long* counters, void* stream);
+
 /* Per-kernel device timing for benchmarks (no reference counterpart): with b2l_profile(1) every kernel
  * launch is bracketed by CUDA events on its stream; b2l_profile_read() synchronises them and returns
  * summed milliseconds and launch counts per kernel kind since the last read.  Not thread safe.    */

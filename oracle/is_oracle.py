@@ -26,12 +26,13 @@ from __future__ import annotations
 import numpy as np
 
 from .psis_oracle import gpdfit, logsumexp_row
+from .psis_oracle import loo_pointwise as _loo_pointwise_oracle
 from .psis_oracle import psislw as _psislw_oracle
 
 __all__ = ["sislw_row", "tislw_row", "islw", "loo_is_pointwise", "loo_is_summary", "k_hat",
            "weighted_mean", "weighted_variance", "weighted_quantile", "e_loo_arrays", "pareto_min_ss",
            "pareto_khat_threshold", "pareto_convergence_rate", "predictive_metric",
-           "loo_predictive_metric_arrays", "crps", "loo_score_arrays"]
+           "loo_predictive_metric_arrays", "crps", "loo_score_arrays", "loo_group_arrays"]
 
 
 # ------------------------------------------------------------------------------- SIS / TIS
@@ -282,3 +283,28 @@ def loo_score_arrays(x_ns, x2_ns, ll_ns, y, permutations: int = 1, reff: float =
     pw = crps(exx, exy, scale)
     return {"pointwise": pw, "estimate": float(pw.mean()), "se": float(pw.std() / np.sqrt(pw.size)),
             "pareto_k": k}
+
+
+def loo_group_arrays(ll_sn, group_ids, method: str = "psis", reff: float = 1.0, scale_value: float = 1.0):
+    """pyloo/loo_group.py:162-163 (sorted unique groups), :188-197 (NaN -> -1e10), :215-222 (per-group sums of
+    the stacked log-likelihood), :226-233 and :281-305 (the LOO pass per group), :283-303 (totals).
+    The per-group pass is the pinned single-observation oracle applied to the group sums."""
+    ll = np.asarray(ll_sn, dtype=np.float64).T           # (N, S) like .stack(__sample__=...)
+    ll = np.where(np.isnan(ll), -1e10, ll)
+    gid = np.asarray(group_ids)
+    groups = np.unique(gid)
+    sums = np.array([ll[gid == g].sum(axis=0) for g in groups])   # :216-222
+    if method == "psis":
+        pw = _loo_pointwise_oracle(sums.T, reff)
+        diag = pw["pareto_k"]
+    else:
+        pw = loo_is_pointwise(sums.T, method)
+        diag = pw["ess_i"]
+    logo_i = scale_value * pw["elpd_i"]
+    n = len(groups)
+    elpd = logo_i.sum()
+    se = (n * np.var(logo_i)) ** 0.5
+    lppd = pw["lppd_i"].sum()
+    return {"groups": groups, "group_sums": sums, "logo_i": logo_i, "diagnostic": diag, "elpd_logo": elpd, "se": se,
+            "p_logo": lppd - elpd / scale_value, "p_logo_se": np.sqrt(np.sum(np.var(logo_i))),
+            "logoic": -2 * elpd, "logoic_se": 2 * se}

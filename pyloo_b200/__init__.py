@@ -14,6 +14,7 @@ from .sis import sislw  # noqa: F401
 from .tis import tislw  # noqa: F401
 from .e_loo import ExpectationResult, compute_pareto_k, e_loo, k_hat  # noqa: F401
 from .loo import loo  # noqa: F401
+from .loo_group import loo_group  # noqa: F401
 from .loo_predictive_metric import loo_predictive_metric  # noqa: F401
 from .loo_score import LooScoreResult, loo_score  # noqa: F401
 from .waic import waic  # noqa: F401
@@ -24,6 +25,6 @@ __version__ = "0.1.0"
 
 __all__ = [
     "psislw", "sislw", "tislw", "e_loo", "ExpectationResult", "compute_pareto_k", "k_hat",
-    "compute_importance_weights", "ISMethod", "loo", "loo_predictive_metric", "loo_score", "LooScoreResult", "waic", "loo_compare", "ELPDData",
+    "compute_importance_weights", "ISMethod", "loo", "loo_group", "loo_predictive_metric", "loo_score", "LooScoreResult", "waic", "loo_compare", "ELPDData",
     "rcParams", "InferenceDataLite", "LiteDataArray", "from_dict",
 ]

@@ -801,6 +801,49 @@ __global__ void __launch_bounds__(IS_NT) eloo_quantile_kernel(const QuantParams 
     }
 }
 
+// ===================================================================================== group sums (LOGO)
+// One warp per (group, draw).  Observation-fastest input (ArviZ layout): lanes stride over the members, which
+// is coalesced when a group's observations are adjacent; row input: lanes take adjacent draws of one group and
+// loop over the members.  Partial sums are combined in a fixed order (deterministic).
+__global__ void __launch_bounds__(256) group_sum_kernel(const GroupSumParams p) {
+    const int lane = threadIdx.x & 31;
+    const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    unsigned c_nan = 0;
+    if (p.stride_n == 1 && p.stride_s != 1) {
+        const long long tasks = (long long)p.G * p.S;
+        for (long long t = warp_global; t < tasks; t += n_warps) {
+            const int g = (int)(t / p.S), s = (int)(t % p.S);
+            const int b = p.offsets[g], e = p.offsets[g + 1];
+            const double* col = p.ll + (long long)s * p.stride_s;
+            double acc = 0.0;
+            for (int m = b + lane; m < e; m += 32) {
+                double v = col[p.members[m]];
+                if (v != v) { v = -1e10; ++c_nan; }
+                acc += v;
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) p.out[(long long)g * p.out_stride + s] = acc;
+        }
+    } else {
+        const int tiles = (p.S + 31) / 32;
+        const long long tasks = (long long)p.G * tiles;
+        for (long long t = warp_global; t < tasks; t += n_warps) {
+            const int g = (int)(t / tiles), s = (int)(t % tiles) * 32 + lane;
+            if (s >= p.S) continue;
+            const int b = p.offsets[g], e = p.offsets[g + 1];
+            double acc = 0.0;
+            for (int m = b; m < e; ++m) {
+                double v = p.ll[(long long)s * p.stride_s + (long long)p.members[m] * p.stride_n];
+                if (v != v) { v = -1e10; ++c_nan; }
+                acc += v;
+            }
+            p.out[(long long)g * p.out_stride + s] = acc;
+        }
+    }
+    if (p.counters && c_nan) atomicAdd(&p.counters[0], (unsigned long long)c_nan);
+}
+
 // ===================================================================================== host side
 static size_t is_smem_bytes(int S) { return sizeof(double) * (IS_RED_WORDS + (size_t)((S + 1) & ~1)); }
 constexpr size_t SMEM_LIMIT = 227 * 1024;
@@ -898,6 +941,14 @@ cudaError_t eloo_quantile_launch(QuantParams p, cudaStream_t st) {
     cudaError_t e = plan_kernel(eloo_quantile_kernel, smem, p.n_rows, info);
     if (e != cudaSuccess) return e;
     eloo_quantile_kernel<<<info[1], IS_NT, info[2], st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t group_sum_launch(const GroupSumParams& p, cudaStream_t st) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    group_sum_kernel<<<sms * 8, 256, 0, st>>>(p);
     return cudaGetLastError();
 }
 

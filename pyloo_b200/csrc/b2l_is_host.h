@@ -61,6 +61,20 @@ struct QuantParams {
     double probs[ELOO_MAX_PROBS];
 };
 
+// Leave-one-group-out: out[g][s] = sum over the members i of group g (ascending i) of ll(s, i), NaN -> -1e10
+// (pyloo/loo_group.py:188-222).  members / offsets: CSR of the groups (device).  out: G rows of S doubles.
+struct GroupSumParams {
+    const double* ll;
+    long long stride_s, stride_n;  // element (s, i) at ll[s * stride_s + i * stride_n]
+    const int* members;            // [N] observation indices grouped by group, ascending inside a group
+    const int* offsets;            // [G + 1]
+    double* out;
+    long long out_stride;          // row stride of out (>= S)
+    unsigned long long* counters;  // nullable: [0] += NaN inputs
+    int S, G;
+};
+cudaError_t group_sum_launch(const GroupSumParams& p, cudaStream_t st);
+
 // Launch planners + launchers.  `*_info`: [0] staged in shared memory, [1] grid, [2] dynamic smem bytes,
 // [3] CTAs per SM.  The e_loo launcher needs `scratch` only when info[0] == 0.
 cudaError_t is_plan(int method, int mode, int S, long long n_rows, int* info);

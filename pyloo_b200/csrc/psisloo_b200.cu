@@ -874,6 +874,22 @@ extern "C" int b2l_eloo_quantile_dev_f64(const double* x, int64_t x_stride_n, co
     return 0;
 }
 
+extern "C" int b2l_group_sum_dev_f64(const double* ll, int64_t S, int64_t N, int64_t stride_s, int64_t stride_n,
+                                     const int32_t* members, const int32_t* offsets, int32_t G, double* out,
+                                     int64_t out_stride_g, unsigned long long* counters, void* stream) {
+    if (!ll || !members || !offsets || !out || S < 1 || N < 1 || G < 1) return fail(B2L_E_INVALID, "null pointer or bad size");
+    if (S > INT32_MAX || N > INT32_MAX) return fail(B2L_E_UNSUPPORTED, "S or N too large");
+    if (out_stride_g < S) return fail(B2L_E_INVALID, "out_stride_g < S");
+    cudaStream_t st = (cudaStream_t)stream;
+    GroupSumParams p;
+    memset(&p, 0, sizeof(p));
+    p.ll = ll; p.stride_s = stride_s; p.stride_n = stride_n; p.members = members; p.offsets = offsets;
+    p.out = out; p.out_stride = out_stride_g; p.counters = counters; p.S = (int)S; p.G = G;
+    ProfScope prof(B2L_PROF_IS, st);
+    CK(group_sum_launch(p, st));
+    return 0;
+}
+
 extern "C" int b2l_handover_reasons(uint64_t* out16, int32_t reset) {
     if (!out16) return fail(B2L_E_INVALID, "null pointer");
     unsigned long long a[HO_REASONS], b[HO_REASONS];

@@ -13,9 +13,11 @@ import numpy as np
 import pandas as pd
 
 _HEAD = "\nComputed from {n_samples} posterior samples and {n_points} observations log-likelihood matrix.\n"
+_HEAD_LOGO = "\nComputed from {n_samples} posterior samples and {n_groups} groups log-likelihood matrix.\n"
 _TABLE = {
     "loo": ("elpd_loo", "p_loo", "looic"),
     "waic": ("elpd_waic", "p_waic", None),
+    "logo": ("elpd_logo", "p_logo", "logoic"),  # pyloo/elpd.py:74-81, :165-222
 }
 _K_TABLE = (
     "\n------\n\nPareto k diagnostic values:\n"
@@ -50,6 +52,25 @@ class ELPDData(pd.Series):
     def __str__(self):
         kind = self._kind()
         est, pen, ic = _TABLE[kind]
+        if kind == "logo":
+            out = _HEAD_LOGO.format(n_samples=self["n_samples"], n_groups=self["n_groups"])
+            out += "\n         Estimate       SE\n"
+            out += f"{est}   {self[est]:<8.2f}    {self['se']:<.2f}\n"
+            out += f"{pen}       {self[pen]:<8.2f}    {self.get('p_logo_se', float('nan')):<.2f}\n"
+            out += f"{ic}      {self['logoic']:<8.2f}    {self['logoic_se']:<.2f}"
+            if self["warning"]:
+                out += _WARN
+            if "pareto_k" in self and self.get("good_k") is not None:
+                good_k = self["good_k"]
+                counts = _k_counts(self["pareto_k"], good_k)
+                if counts[1] == 0 and counts[2] == 0:
+                    out += (f"\n\nAll Pareto k estimates are good (k < {good_k:.1f})."
+                            "\nSee help('pareto-k-diagnostic') for details.")
+                else:
+                    pct = counts / np.sum(counts) * 100
+                    out += _K_TABLE.format(gk=good_k, c0=int(counts[0]), c1=int(counts[1]), c2=int(counts[2]),
+                                           p0=pct[0], p1=pct[1], p2=pct[2])
+            return out
         out = _HEAD.format(n_samples=self["n_samples"], n_points=self["n_data_points"])
         out += "\n         Estimate       SE\n"
         out += f"{est}   {self[est]:<8.2f}    {self['se']:<.2f}\n"
@@ -96,6 +117,10 @@ class ELPDData(pd.Series):
     @property
     def n_data_points(self):
         return self["n_data_points"]
+
+    @property
+    def n_groups(self):
+        return self["n_groups"]
 
     @property
     def warning(self):

@@ -542,3 +542,51 @@ def psis_expectation_host(x_ns, lr_ns, reff: float = 1.0, kind: str = "mean", ta
         khat[i0:i1] = d_kh.cpu().numpy()
         pk[i0:i1] = d_k.cpu().numpy()
     return value, khat, pk
+
+
+def group_loo_host(ll_sn, group_index, n_groups: int, reff: float = 1.0, method: str = "psis", *, device=None):
+    """Leave-one-group-out pointwise pass on a HOST sample-major ``(S, N)`` log-likelihood
+    (pyloo/loo_group.py:188-285): per-group sums of the log-likelihood on the device
+    (``b2l_group_sum_dev_f64``), then the ordinary LOO pass with one "observation" per group.
+    ``group_index``: int array of length N with values in ``[0, n_groups)``.
+    Returns the dict of :func:`loo_host` (PSIS) or :func:`loo_is_host` (SIS / TIS) over the groups."""
+    torch = _torch()
+    lib = _native.load()
+    a = np.asarray(ll_sn, dtype=np.float64)
+    if a.ndim != 2:
+        raise ValueError("expected a 2-D array")
+    S, N = a.shape
+    gidx = np.asarray(group_index, dtype=np.int64)
+    if gidx.shape != (N,) or gidx.min() < 0 or gidx.max() >= n_groups:
+        raise ValueError("group_index must hold one group number in [0, n_groups) per observation")
+    G = int(n_groups)
+    dev = _dev(device)
+    members = torch.from_numpy(np.argsort(gidx, kind="stable").astype(np.int32)).to(dev)
+    offsets = torch.from_numpy(np.concatenate([[0], np.cumsum(np.bincount(gidx, minlength=G))]).astype(np.int32)).to(dev)
+    sums = torch.empty((G, S), dtype=torch.float64, device=dev)
+    counters = torch.zeros(4, dtype=torch.int64, device=dev)
+    step = max(1, min(S, _CHUNK_BYTES // max(8 * N, 1)))
+    with torch.cuda.device(dev):
+        for s0 in range(0, S, step):
+            s1 = min(S, s0 + step)
+            slab = torch.from_numpy(np.ascontiguousarray(a[s0:s1])).to(dev)  # (s1 - s0, N), observations fastest
+            rc = lib.b2l_group_sum_dev_f64(slab.data_ptr(), s1 - s0, N, N, 1, members.data_ptr(), offsets.data_ptr(),
+                                           G, sums.data_ptr() + 8 * s0, S, counters.data_ptr(),
+                                           _stream_ptr(torch, dev))
+            _native.check(rc)
+            torch.cuda.current_stream(dev).synchronize()  # the slab is released before the next upload
+    n_nan = int(counters[0].item())
+    if _method_name(method) == "psis":
+        res = loo_cuda(sums.t(), reff)
+        st = StatsRecord(stats_cuda(res).cpu().numpy())
+        out = {k: res[k].cpu().numpy() for k in ("elpd_i", "pareto_k", "lppd_i")}
+        out.update(stats=st, good_k=good_k_threshold(S), n_samples=S, n_nan_in=n_nan)
+        return out
+    res = loo_is_cuda(sums.t(), method)
+    out = {k: res[k].cpu().numpy() for k in ("elpd_i", "ess_i", "lppd_i")}
+    out.update(n_samples=S, n_nan_in=n_nan)
+    return out
+
+
+def _method_name(method) -> str:
+    return str(getattr(method, "value", method)).lower()

@@ -340,3 +340,53 @@ def test_loo_score(scale):
     assert plain.pareto_k is None and plain.pointwise.shape == (12,)
     with pytest.raises(ValueError, match="Variable 'zz' not found"):
         pl.loo_score(idata, x_var="zz", y_var="y")
+
+
+# ------------------------------------------------------------------------------------ loo_group
+@pytest.mark.parametrize("method", ["psis", "sis", "tis"])
+def test_loo_group(method):
+    rng = np.random.default_rng(17)
+    n_obs, chains, draws = 60, 4, 250
+    ll = -1.0 + 0.25 * rng.normal(size=(chains, draws, n_obs))
+    ll[1, 7, 3] = np.nan
+    group_ids = rng.permutation(np.repeat(np.array(["a", "b", "c", "d", "e", "f", "g", "h", "i", "j"]), 6))
+    idata = from_dict(posterior={"mu": rng.normal(size=(chains, draws))}, log_likelihood={"y": ll},
+                      dims={"y": ["obs"]})
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        res = pl.loo_group(idata, group_ids, pointwise=True, reff=0.9, method=method)
+    msgs = " | ".join(str(w.message) for w in rec)
+    assert "NaN values detected in log-likelihood" in msgs
+    assert (f"Using {method.upper()} for LOGO computation" in msgs) == (method != "psis")
+    ref = iso.loo_group_arrays(ll.reshape(-1, n_obs), group_ids, method, 0.9)
+    for key in ("elpd_logo", "se", "p_logo", "p_logo_se", "logoic", "logoic_se"):
+        close(res[key], ref[key])
+    close(res["logo_i"].values, ref["logo_i"])
+    assert list(res["logo_i"].coords["group"]) == list(ref["groups"])
+    close(res["pareto_k" if method == "psis" else "ess"], ref["diagnostic"])
+    assert res["n_groups"] == 10 and res["n_samples"] == 1000
+    assert ("good_k" in res) == (method == "psis")
+    assert "elpd_logo" in str(res) and "10 groups log-likelihood matrix" in str(res)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        dev = pl.loo_group(idata, group_ids, reff=0.9, method=method, scale="deviance")
+    close(dev["elpd_logo"], -2 * ref["elpd_logo"])
+    assert list(dev.index[:7]) == ["elpd_logo", "se", "p_logo", "p_logo_se", "n_samples", "n_groups", "warning"]
+    with pytest.raises(ValueError, match="Length of group_ids"):
+        pl.loo_group(idata, group_ids[:5], reff=1.0)
+
+
+def test_loo_group_sums_row_layout_and_many_groups():
+    # engine level: contiguous integer groups of unequal size, (N, S)-row input viewed as (S, N)
+    rng = np.random.default_rng(23)
+    S, N = 2000, 700
+    rows = -0.5 + 0.05 * rng.normal(size=(N, S))
+    sizes = rng.integers(1, 12, size=200)
+    gid = np.repeat(np.arange(200), sizes)[:N]
+    gid = np.concatenate([gid, np.full(N - gid.size, 199)]) if gid.size < N else gid
+    G = int(gid.max()) + 1
+    res = engine.group_loo_host(rows.T, gid, G, 1.0, "psis")
+    ref = iso.loo_group_arrays(rows.T, gid, "psis", 1.0)
+    close(res["elpd_i"], ref["logo_i"])
+    close(res["pareto_k"], ref["diagnostic"])
+    close(res["stats"].elpd_sum, ref["elpd_logo"], 1e-11)
