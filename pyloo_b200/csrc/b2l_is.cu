@@ -273,9 +273,9 @@ __device__ __forceinline__ void warp_top(const double* buf, int n, int first, in
     }
 }
 
-// Merge the per-warp descending lists cb[w * ELOO_MAX_TAIL + 0..n_tail), w < IS_NW, written by warp_top into
-// the n_tail largest overall (descending) in tl.  One warp.
-__device__ __forceinline__ void merge_warp_lists(const double* cb, int n_tail, double* tl, int lane) {
+// Merge the per-warp descending lists cb[w * ld + 0..n_tail), w < IS_NW, written by warp_top into the n_tail
+// largest overall (descending) in tl.  One warp.
+__device__ __forceinline__ void merge_warp_lists(const double* cb, int ld, int n_tail, double* tl, int lane) {
     constexpr int NONE = 0x7fffffff;
     double lastv = inf_f64();
     int lasti = -1;
@@ -285,7 +285,7 @@ __device__ __forceinline__ void merge_warp_lists(const double* cb, int n_tail, d
         bestv = -inf_f64();
         besti = NONE;
         for (int c = lane; c < IS_NW * n_tail; c += 32) {
-            const int s = (c / n_tail) * ELOO_MAX_TAIL + (c % n_tail);
+            const int s = (c / n_tail) * ld + (c % n_tail);
             const double v = cb[s];
             const bool eligible = (v < lastv) || (v == lastv && s > lasti);
             if (eligible && (besti == NONE || v > bestv)) {
@@ -380,23 +380,25 @@ __device__ __forceinline__ double gpdfit_literal_warp(const double* ary, int n, 
 }
 
 constexpr int ELOO_FAST_CAP = 128;  // candidates above the sampled threshold handled without the slow path
-constexpr int ELOO_AREA_WORDS = IS_NW * ELOO_MAX_TAIL;  // 1024 >= 3 * IS_NT and >= 3 * 128
-static_assert(ELOO_AREA_WORDS >= 3 * IS_NT && ELOO_AREA_WORDS >= 3 * 128, "scratch area too small");
+// scratch area, a union over the phases of a row: the per-warp c-th maxima (3 x 8), the exact-extraction lists
+// (8 warps x tail_len) and the literal-fit scratch (3 x 128)
+__host__ __device__ inline int eloo_area_words(int tail_len) {
+    const int lists = IS_NW * tail_len;
+    return lists > 3 * 128 ? lists : 3 * 128;
+}
 
 struct ElooSmem {
-    int row_words;  // padded S
-    int n_rows_staged;
-    __host__ __device__ static size_t bytes(int S, int n_staged) {
+    __host__ __device__ static size_t bytes(int S, int n_staged, int tail_len) {
         const size_t spad = (size_t)((S + 1) & ~1);
-        // red + staged rows + scratch area (union: thread maxima 3 x 256 | exact-extraction lists 8 warps x L |
-        // fit scratch 3 x 128) + tails (3 x L) + fast-path candidates (3 x 128) + results / thresholds / counters
-        return sizeof(double) * (IS_RED_WORDS + spad * n_staged + ELOO_AREA_WORDS + 3 * ELOO_MAX_TAIL +
+        // red + staged rows + scratch area + tails (3 x tail_len) + fast-path candidates (3 x 128) + results /
+        // thresholds / counters
+        return sizeof(double) * (IS_RED_WORDS + spad * n_staged + eloo_area_words(tail_len) + 3 * tail_len +
                                  3 * ELOO_FAST_CAP + 16);
     }
 };
 
 template <bool STAGED>
-__global__ void __launch_bounds__(IS_NT) eloo_row_kernel(const ElooParams p) {
+__global__ void __launch_bounds__(IS_NT, 3) eloo_row_kernel(const ElooParams p) {
     extern __shared__ __align__(16) unsigned char is_smem[];
     double* red = reinterpret_cast<double*>(is_smem);
     uint64_t* bar = reinterpret_cast<uint64_t*>(red + 128);
@@ -407,15 +409,18 @@ __global__ void __launch_bounds__(IS_NT) eloo_row_kernel(const ElooParams p) {
     double* sm = red + IS_RED_WORDS;
     double *bx = nullptr, *blw = nullptr, *blr = nullptr;
     if (STAGED) {
-        blw = sm; sm += spad;
-        if (!lr_same) { blr = sm; sm += spad; } else blr = blw;
+        // the ratios are read three times and h * r overwrites x in place: those two rows are staged; log
+        // weights that are not also the ratios are read twice straight from global memory (second read: L2)
+        blr = sm; sm += spad;
+        blw = lr_same ? blr : nullptr;
         if (has_x) { bx = sm; sm += spad; }
     }
+    const int LP = p.tail_len;  // row pitch of the tail arrays
     double* area = sm;                        // union, see ElooSmem::bytes
     double* tmax = area;                      // [3][IS_NT] thread-local maxima, sorted per warp
     double* gpd = area;                       // [3][128] literal-fit scratch (after the selection)
-    double* tails = area + ELOO_AREA_WORDS;   // [3][L]
-    double* fcand = tails + 3 * ELOO_MAX_TAIL;  // [3][ELOO_FAST_CAP]
+    double* tails = area + eloo_area_words(LP);  // [3][L]
+    double* fcand = tails + 3 * LP;              // [3][ELOO_FAST_CAP]
     double* res = fcand + 3 * ELOO_FAST_CAP;  // [3] khat per tail
     double* thr = res + 4;                    // [3] thresholds
     int* cnt = reinterpret_cast<int*>(thr + 4);  // [3] candidate counts
@@ -436,13 +441,12 @@ __global__ void __launch_bounds__(IS_NT) eloo_row_kernel(const ElooParams p) {
             double* dsts[3];
             const double* srcs[3];
             int na = 0;
-            dsts[na] = blw; srcs[na++] = glw;
-            if (!lr_same) { dsts[na] = blr; srcs[na++] = glr; }
+            dsts[na] = blr; srcs[na++] = glr;
             if (has_x) { dsts[na] = bx; srcs[na++] = gx; }
             stage_rows<true>(dsts, srcs, na, S, p.bulk, bar, parity);
         }
         const double* X = STAGED ? bx : gx;
-        const double* LW = STAGED ? blw : glw;
+        const double* LW = (STAGED && lr_same) ? blw : glw;
         const double* LR = STAGED ? blr : glr;
         double* HR = STAGED ? bx : p.scratch + (long long)blockIdx.x * spad;  // h * r, in place when staged
 
@@ -579,7 +583,7 @@ __global__ void __launch_bounds__(IS_NT) eloo_row_kernel(const ElooParams p) {
                               want[2] && cnt[2] > ELOO_FAST_CAP};
         if (warp < 3 && want[warp] && !slow[warp]) {
             // rank the candidates by counting (ties by slot): the n_tail largest land in the tail, descending
-            double* tl = tails + warp * ELOO_MAX_TAIL;
+            double* tl = tails + warp * LP;
             const double* fc = fcand + warp * ELOO_FAST_CAP;
             const int c = cnt[warp];
             for (int i = lane; i < c; i += 32) {
@@ -597,15 +601,15 @@ __global__ void __launch_bounds__(IS_NT) eloo_row_kernel(const ElooParams p) {
         for (int t = 0; t < 3; ++t) {
             if (!slow[t]) continue;  // block-uniform
             __syncthreads();
-            if (t == 0) warp_top<false>(LR, S, tid, IS_NT, n_tail, area + warp * ELOO_MAX_TAIL, lane);
-            else if (t == 1) warp_top<true>(HR, S, tid, IS_NT, n_tail, area + warp * ELOO_MAX_TAIL, lane);
-            else warp_top<false>(HR, S, tid, IS_NT, n_tail, area + warp * ELOO_MAX_TAIL, lane);
+            if (t == 0) warp_top<false>(LR, S, tid, IS_NT, n_tail, area + warp * LP, lane);
+            else if (t == 1) warp_top<true>(HR, S, tid, IS_NT, n_tail, area + warp * LP, lane);
+            else warp_top<false>(HR, S, tid, IS_NT, n_tail, area + warp * LP, lane);
             __syncthreads();
-            if (warp == 0) merge_warp_lists(area, n_tail, tails + t * ELOO_MAX_TAIL, lane);
+            if (warp == 0) merge_warp_lists(area, LP, n_tail, tails + t * LP, lane);
         }
         __syncthreads();  // tails complete; the scratch area is free for the fit
         if (warp < 3 && want[warp]) {
-            double* tl = tails + warp * ELOO_MAX_TAIL;
+            double* tl = tails + warp * LP;
             __syncwarp();
             // tail values in the reference's order, then its degeneracy test and the fit argument
             // warp 0: sorted_r descending (e_loo.py:351); warp 1: left tail ascending (:370); warp 2: right
@@ -910,25 +914,27 @@ cudaError_t is_launch(int method, int mode, const IsParams& p, cudaStream_t st) 
                                    : is_launch_t<IS_METHOD_TIS, IS_MODE_LOO>(p, st);
 }
 
-cudaError_t eloo_plan(int S, long long n_rows, bool lr_same, bool has_x, int* info) {
-    const int n_staged = 1 + (lr_same ? 0 : 1) + (has_x ? 1 : 0);
-    const size_t staged = ElooSmem::bytes(S, n_staged);
+cudaError_t eloo_plan(int S, long long n_rows, bool has_x, int tail_len, int* info) {
+    const int n_staged = 1 + (has_x ? 1 : 0);
+    const size_t staged = ElooSmem::bytes(S, n_staged, tail_len);
     if (staged <= SMEM_LIMIT) {
         info[0] = 1;
         return plan_kernel(eloo_row_kernel<true>, staged, n_rows, info);
     }
     info[0] = 0;
-    return plan_kernel(eloo_row_kernel<false>, ElooSmem::bytes(0, 0), n_rows, info);
+    return plan_kernel(eloo_row_kernel<false>, ElooSmem::bytes(0, 0, tail_len), n_rows, info);
 }
 
 cudaError_t eloo_launch(const ElooParams& p, cudaStream_t st) {
     int info[4];
-    const bool lr_same = (p.lr == p.lw) && (p.lr_stride == p.lw_stride);
     const bool has_x = (p.x != nullptr) && (p.type != ELOO_NONE);
-    cudaError_t e = eloo_plan(p.S, p.n_rows, lr_same, has_x, info);
+    cudaError_t e = eloo_plan(p.S, p.n_rows, has_x, p.tail_len, info);
     if (e != cudaSuccess) return e;
     if (info[0]) eloo_row_kernel<true><<<info[1], IS_NT, info[2], st>>>(p);
-    else eloo_row_kernel<false><<<info[1], IS_NT, info[2], st>>>(p);
+    else {
+        const int grid = (p.grid_cap > 0 && p.grid_cap < info[1]) ? p.grid_cap : info[1];
+        eloo_row_kernel<false><<<grid, IS_NT, info[2], st>>>(p);
+    }
     return cudaGetLastError();
 }
 

@@ -43,6 +43,7 @@ struct ElooParams {
     int type;
     int tail_len;
     int bulk;
+    int grid_cap;  // unstaged mode: number of scratch rows the workspace holds (0 = no limit)
 };
 
 constexpr int ELOO_MAX_PROBS = 32;
@@ -79,7 +80,7 @@ cudaError_t group_sum_launch(const GroupSumParams& p, cudaStream_t st);
 // [3] CTAs per SM.  The e_loo launcher needs `scratch` only when info[0] == 0.
 cudaError_t is_plan(int method, int mode, int S, long long n_rows, int* info);
 cudaError_t is_launch(int method, int mode, const IsParams& p, cudaStream_t st);
-cudaError_t eloo_plan(int S, long long n_rows, bool lr_same, bool has_x, int* info);
+cudaError_t eloo_plan(int S, long long n_rows, bool has_x, int tail_len, int* info);
 cudaError_t eloo_launch(const ElooParams& p, cudaStream_t st);
 cudaError_t eloo_quantile_launch(QuantParams p, cudaStream_t st);  // fills p.P2
 

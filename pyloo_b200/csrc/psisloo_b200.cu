@@ -816,7 +816,8 @@ extern "C" int b2l_loo_is_dev_f64(const double* ll, int64_t S, int64_t N, int64_
 extern "C" int b2l_eloo_workspace_bytes(int64_t S, int64_t N, int32_t has_lr, int32_t type, size_t* out_bytes) {
     if (!out_bytes || S < 1 || N < 0 || S > INT32_MAX) return fail(B2L_E_INVALID, "bad arguments");
     int info[4] = {0, 0, 0, 0};
-    CK(eloo_plan((int)S, std::max<long long>(N, 1), !has_lr, type != B2L_ELOO_NONE, info));
+    (void)has_lr;
+    CK(eloo_plan((int)S, std::max<long long>(N, 1), type != B2L_ELOO_NONE, ELOO_MAX_TAIL, info));
     *out_bytes = info[0] ? 0 : align_up((size_t)info[1] * (size_t)((S + 1) & ~1ll) * 8, 256);
     return 0;
 }
@@ -839,14 +840,16 @@ extern "C" int b2l_eloo_dev_f64(const double* x, int64_t x_stride_n, const doubl
     p.lw = lw; p.lw_stride = lw_stride_n;
     p.lr = lr ? lr : lw; p.lr_stride = lr ? lr_stride_n : lw_stride_n;
     p.value = value_out; p.khat = khat_out; p.n_rows = N; p.S = (int)S; p.type = type; p.tail_len = tail_len;
-    p.bulk = bulk_ok(S, lw, lw_stride_n) && bulk_ok(S, p.lr, p.lr_stride) && (!p.x || bulk_ok(S, p.x, x_stride_n));
+    p.bulk = bulk_ok(S, p.lr, p.lr_stride) && (!p.x || bulk_ok(S, p.x, x_stride_n));  // the two staged rows
     int info[4] = {0, 0, 0, 0};
-    const bool lr_same = (p.lr == p.lw) && (p.lr_stride == p.lw_stride);
-    CK(eloo_plan((int)S, N, lr_same, p.x != nullptr, info));
+    CK(eloo_plan((int)S, N, p.x != nullptr, tail_len, info));
     if (!info[0]) {
-        const size_t need = align_up((size_t)info[1] * (size_t)((S + 1) & ~1ll) * 8, 256);
-        if (!ws || ws_bytes < need) return fail(B2L_E_WORKSPACE, "workspace too small: need %zu bytes", need);
+        // rows that do not fit shared memory: one scratch row per resident CTA, as many as the workspace holds
+        const size_t row = (size_t)((S + 1) & ~1ll) * 8;
+        const size_t rows_held = ws ? ws_bytes / row : 0;
+        if (rows_held < 1) return fail(B2L_E_WORKSPACE, "workspace too small: need at least %zu bytes", row);
         p.scratch = reinterpret_cast<double*>(ws);
+        p.grid_cap = (int)std::min<size_t>(rows_held, 1u << 20);
     }
     ProfScope prof(B2L_PROF_ELOO, st);
     CK(eloo_launch(p, st));

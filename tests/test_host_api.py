@@ -33,6 +33,13 @@ def test_no_cpu_fallback_without_gpu():
         pl.psislw(np.random.default_rng(0).normal(size=(4, 100)))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         engine.loo_host(np.zeros((100, 3)))
+    # the widened rows fail just as loudly
+    x = np.random.default_rng(1).normal(size=(3, 64))
+    for call in (lambda: pl.sislw(x), lambda: pl.tislw(x), lambda: pl.compute_importance_weights(x, method="tis"),
+                 lambda: pl.k_hat(x[0], x[1]), lambda: engine.eloo_quantile_host(x, x, [0.5]),
+                 lambda: engine.group_loo_host(x.T, [0, 1, 0], 2), lambda: engine.psis_expectation_host(x, x)):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            call()
 
 
 def test_stats_merge_is_host_arithmetic():
