@@ -23,7 +23,26 @@ namespace b2l {
 
 constexpr int IS_NT = 256;
 constexpr int IS_NW = IS_NT / 32;
-constexpr int IS_RED_WORDS = 130;  // 128 reduction words + mbarrier (16 B)
+constexpr int IS_RED_WORDS = 194;  // 128 reduction words + mbarrier (16 B) + 64 words of exp table
+
+// exp(a) for the normalising sums, a <= 0: table-driven (relative error < 4e-15, b2l_common.cuh) for the
+// ordinary range, the library routine for NaN / -inf / arguments below -1e7 (where the table's one-step
+// argument reduction no longer holds) so that IEEE special cases propagate like NumPy's.
+static __device__ __noinline__ double exp_slow(double a) { return exp(a); }
+__device__ __forceinline__ double exp_sum(double a, const ExpTab& tb) {
+    return (a >= -1e7) ? exp_tab_drop(a, tb, false) : exp_slow(a);
+}
+__device__ __forceinline__ ExpTab exp_table_init(double* red) {
+    double* tab = red + 130;
+    if (threadIdx.x < 32) {
+        tab[threadIdx.x] = exp2((double)threadIdx.x / 32.0);
+        tab[32 + threadIdx.x] = exp2(-(double)threadIdx.x / 32.0);
+    }
+    ExpTab tb;
+    tb.t = tab;
+    tb.tinv = tab + 32;
+    return tb;
+}
 
 __device__ __forceinline__ double np_minimum(double a, double b) {
     return (a != a || b != b) ? nan_f64() : fmin(a, b);
@@ -79,6 +98,7 @@ __global__ void __launch_bounds__(IS_NT) is_row_kernel(const IsParams p) {
     uint64_t* bar = reinterpret_cast<uint64_t*>(red + 128);
     double* buf = red + IS_RED_WORDS;
     const int tid = threadIdx.x, S = p.S;
+    const ExpTab tb = exp_table_init(red);
     if (STAGED && p.bulk && tid == 0) {
         mbar_init(bar, 1);
         fence_mbar_init();
@@ -131,19 +151,19 @@ __global__ void __launch_bounds__(IS_NT) is_row_kernel(const IsParams p) {
             for (int i = 0; i < EPT; ++i) {
                 const int s = tid + i * IS_NT;
                 const double v = (s < S) ? lwraw(s) : -inf_f64();
-                const double e = (s < S) ? exp(v - mx) : 0.0;
+                const double e = (s < S) ? exp_sum(v - mx, tb) : 0.0;
                 ecache[i] = e;
                 s1 += e;
-                if (MODE == IS_MODE_LOO && s < S) sl += exp(mn - v);
+                if (MODE == IS_MODE_LOO && s < S) sl += exp_sum(mn - v, tb);
             }
         } else {
 #pragma unroll 4
             for (int s = tid; s < S; s += IS_NT) {
                 const double v = lwraw(s);
-                const double e = exp(v - mx);
+                const double e = exp_sum(v - mx, tb);
                 s1 += e;
                 s2 += e * e;
-                if (MODE == IS_MODE_LOO) sl += exp(mn - v);  // exp(ll - max ll)
+                if (MODE == IS_MODE_LOO) sl += exp_sum(mn - v, tb);  // exp(ll - max ll)
             }
         }
         s1 = block_sum<IS_NT>(s1, red);
@@ -169,7 +189,7 @@ __global__ void __launch_bounds__(IS_NT) is_row_kernel(const IsParams p) {
             } else {
 #pragma unroll 4
                 for (int s = tid; s < S; s += IS_NT) {
-                    const double a = exp(np_minimum(lwraw(s) - mx, cut) - mx2);
+                    const double a = exp_sum(np_minimum(lwraw(s) - mx, cut) - mx2, tb);
                     t1 += a;
                     t2 += a * a;
                 }
@@ -207,7 +227,7 @@ __global__ void __launch_bounds__(IS_NT) is_row_kernel(const IsParams p) {
                 const double v = lwraw(s);
                 double x = v - mx;
                 if (METHOD == IS_METHOD_TIS) x = np_minimum(x, cut);
-                st += exp(((x - lse) + (-v)) - tmax);
+                st += exp_sum(((x - lse) + (-v)) - tmax, tb);
             }
             st = block_sum<IS_NT>(st, red);
             if (tid == 0) {
@@ -424,6 +444,7 @@ __global__ void __launch_bounds__(IS_NT, 3) eloo_row_kernel(const ElooParams p) 
     double* res = fcand + 3 * ELOO_FAST_CAP;  // [3] khat per tail
     double* thr = res + 4;                    // [3] thresholds
     int* cnt = reinterpret_cast<int*>(thr + 4);  // [3] candidate counts
+    const ExpTab tb = exp_table_init(red);
     if (STAGED && p.bulk && tid == 0) {
         mbar_init(bar, 1);
         fence_mbar_init();
@@ -502,13 +523,13 @@ __global__ void __launch_bounds__(IS_NT, 3) eloo_row_kernel(const ElooParams p) 
 #pragma unroll 4
             for (int s = tid; s < S; s += IS_NT) {
                 const double xv = X[s];
-                const double e = exp(LW[s] - lwmax);
+                const double e = exp_sum(LW[s] - lwmax, tb);
                 se += e;
                 sex += e * xv;
                 sexx += e * (xv * xv);
                 see += e * e;
                 if (need_hr) {
-                    const double hr = (sq ? xv * xv : xv) * (same ? e : exp(LR[s] - lrmax));
+                    const double hr = (sq ? xv * xv : xv) * (same ? e : exp_sum(LR[s] - lrmax, tb));
                     HR[s] = hr;
                     m_hi = fmax(m_hi, hr);
                     m_lo = fmax(m_lo, -hr);

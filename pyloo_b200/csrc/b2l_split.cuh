@@ -85,42 +85,7 @@ struct SplitParams {
     int a_chunk;               // draws per apply transfer (S, or a fraction of it when shared memory is short)
 };
 
-// ------------------------------------------------------------------ table-driven exp for the sums
-// exp(x) = 2^n * 2^(j/32) * e^r, |r| <= ln2/64, degree-5 polynomial: relative error < 4e-15 for
-// x >= -36 (one-step reduction; the error grows to 8e-14 at x = -700, where the term is negligible
-// next to the row maximum's exp(0) = 1).  Used ONLY for the normalising sums; tail values use exp().
-struct ExpTab {
-    const double* t;     // 2^(j/32)
-    const double* tinv;  // 2^(-j/32)
-};
-constexpr double EXP_L = 46.166241308446828;       // 32 / ln 2
-constexpr double EXP_C1 = -0.021660849392498290;   // -ln 2 / 32
-constexpr double EXP_MAGIC = 6755399441055744.0;   // 1.5 * 2^52
-
-__device__ __forceinline__ double exp_poly5(double r) {
-    double p = 8.3333333333333333e-03;
-    p = fma(p, r, 4.1666666666666664e-02);
-    p = fma(p, r, 1.6666666666666666e-01);
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
-    return p;
-}
-__device__ __forceinline__ double scale2(double y, int n) {  // y * 2^n, result normal
-    return __hiloint2double(__double2hiint(y) + (n << 20), __double2loint(y));
-}
-// exp(x) for finite x <= 0 with the result forced to (almost) zero when `drop`: the exponent
-// argument is clamped so that any finite x gives a finite, tiny value (no guard needed), and a
-// dropped term keeps only its low word (< 2^-1022): one SEL instead of a predicated FP64 add
-__device__ __forceinline__ double exp_tab_drop(double x, const ExpTab& tb, bool drop) {
-    const double t = fma(x, EXP_L, EXP_MAGIC);
-    const int ni = max(__double2loint(t), -1022 * 32);
-    const double nf = t - EXP_MAGIC;
-    const double r = fma(nf, EXP_C1, x);
-    const double y = tb.t[ni & 31] * exp_poly5(r);
-    const int hi = __double2hiint(y) + ((ni & ~31) << 15);
-    return __hiloint2double(drop ? 0 : hi, __double2loint(y));
-}
+// (ExpTab, exp_poly5, scale2 and exp_tab_drop live in b2l_common.cuh: the importance-sampling kernels use them too)
 __device__ __forceinline__ void exp_tab_pm_drop(double x, const ExpTab& tb, bool drop_p, bool drop_m, double& ep,
                                                 double& em) {
     const double t = fma(x, EXP_L, EXP_MAGIC);
