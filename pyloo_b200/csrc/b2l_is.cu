@@ -67,6 +67,27 @@ __device__ __forceinline__ int block_or(int v, double* red_) {
     return t;
 }
 
+// N reductions behind one pair of barriers: warp butterflies, one word per (value, warp), every thread folds
+// the 8 warp results in the same fixed order (deterministic, identical in all threads).  N <= 8.
+template <int N, bool IS_MAX>
+__device__ __forceinline__ void block_reduce_n(double (&v)[N], double* red) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = IS_MAX ? warp_max(v[i]) : warp_sum(v[i]);
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) red[i * IS_NW + (threadIdx.x >> 5)] = v[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        double t = red[i * IS_NW];
+#pragma unroll
+        for (int w = 1; w < IS_NW; ++w) t = IS_MAX ? fmax(t, red[i * IS_NW + w]) : t + red[i * IS_NW + w];
+        v[i] = t;
+    }
+    __syncthreads();
+}
+
 template <bool STAGED>
 __device__ __forceinline__ const double* stage_rows(double* const* dst, const double* const* src, int n_arr,
                                                     int S, int bulk, uint64_t* bar, uint32_t& parity) {
@@ -500,11 +521,13 @@ __global__ void __launch_bounds__(IS_NT, 3) eloo_row_kernel(const ElooParams p) 
             }
         }
         const double m_r = lrmax;  // this thread's largest log ratio
-        lwmax = block_max<IS_NT>(lwmax, red);
-        lrmax = block_max<IS_NT>(lrmax, red);
-        if (has_x) {
-            nemin = block_min<IS_NT>(nemin, red);
-            nemax = block_max<IS_NT>(nemax, red);
+        {
+            double mm[4] = {lwmax, lrmax, -nemin, nemax};
+            block_reduce_n<4, true>(mm, red);
+            lwmax = mm[0];
+            lrmax = mm[1];
+            nemin = -mm[2];
+            nemax = mm[3];
         }
         flags = block_or(flags, red);
         if (flags & 1) lwmax = nan_f64();
@@ -535,12 +558,12 @@ __global__ void __launch_bounds__(IS_NT, 3) eloo_row_kernel(const ElooParams p) 
                     m_lo = fmax(m_lo, -hr);
                 }
             }
-            se = block_sum<IS_NT>(se, red);
-            sex = block_sum<IS_NT>(sex, red);
-            if (p.type != ELOO_MEAN) {
-                sexx = block_sum<IS_NT>(sexx, red);
-                see = block_sum<IS_NT>(see, red);
-            }
+            double ss[4] = {se, sex, sexx, see};
+            block_reduce_n<4, false>(ss, red);
+            se = ss[0];
+            sex = ss[1];
+            sexx = ss[2];
+            see = ss[3];
         }
         __syncthreads();  // HR complete
 
