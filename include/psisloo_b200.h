@@ -166,7 +166,7 @@ int b2l_eloo_dev_f64(const double* x, int64_t x_stride_n, const double* lw, int6
 
 /* e_loo(type="quantile"): replaces pyloo/e_loo.py:466-515 (the Python loop over observations x probabilities
  * around _weighted_quantile, :534-554).  probs: HOST array of n_probs (<= 32) values in (0, 1);
- * value_out: N x n_probs (row-major, device).  Each row is sorted in shared memory, so S <= 8192; larger S
+ * value_out: N x n_probs (row-major, device).  Each row is sorted in shared memory, so S <= 16384; larger S
  * returns B2L_E_UNSUPPORTED.  Ties in x are ordered by draw index (np.argsort's order among ties is
  * unspecified); the Pareto k of a quantile comes from b2l_eloo_dev_f64 with B2L_ELOO_NONE.             */
 int b2l_eloo_quantile_dev_f64(const double* x, int64_t x_stride_n, const double* lw, int64_t lw_stride_n,

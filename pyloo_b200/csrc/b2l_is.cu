@@ -722,22 +722,20 @@ __global__ void __launch_bounds__(IS_NT, 3) eloo_row_kernel(const ElooParams p) 
 // accumulated in sorted order and every requested probability is located by binary search in the cumulative
 // weights and interpolated linearly.  Rows whose weights are all close to the first one take np.quantile's
 // linear rule instead (:536-537).
-__device__ __forceinline__ bool key_greater(double a, int ia, double b, int ib, int S) {
-    const bool pa = (ia >= S), pb = (ib >= S);  // padding sorts after everything, NaN included
-    if (pa != pb) return pa;
-    const bool an = (a != a), bn = (b != b);
-    if (an != bn) return an;
-    if (an) return ia > ib;
-    return (a > b) || (a == b && ia > ib);
-}
+// Sort key of a draw: the order-preserving 64-bit image of the double (b2l_common.cuh), NaN above every number
+// (np.argsort puts NaN last) and the padding slots above NaN, so one unsigned compare orders a pair.
+constexpr uint64_t QKEY_NAN = 0xfffffffffffffffeull, QKEY_PAD = 0xffffffffffffffffull;
+__device__ __forceinline__ uint64_t quant_key(double x) { return (x != x) ? QKEY_NAN : key_of(x); }
+__device__ __forceinline__ double quant_val(uint64_t k) { return (k >= QKEY_NAN) ? nan_f64() : val_of(k); }
 
 __global__ void __launch_bounds__(IS_NT) eloo_quantile_kernel(const QuantParams p) {
     extern __shared__ __align__(16) unsigned char is_smem[];
     double* red = reinterpret_cast<double*>(is_smem);
-    double* keys = red + IS_RED_WORDS;   // [P2] sorted draws
-    double* cs = keys + p.P2;            // [P2] cumulative weights in sorted order
-    double* part = cs + p.P2;            // [IS_NT] scan partials
-    int* idx = reinterpret_cast<int*>(part + IS_NT);  // [P2]
+    uint64_t* keys = reinterpret_cast<uint64_t*>(red + IS_RED_WORDS);  // [P2] sort keys, later the sorted draws
+    double* part = reinterpret_cast<double*>(keys + p.P2);  // [IS_NW] scan partials
+    double* ex = part + IS_NW;                              // [IS_NT] cumulative weight before each thread's chunk
+    double* ce = ex + IS_NT;                                // [IS_NT] cumulative weight at the end of each chunk
+    int* idx = reinterpret_cast<int*>(ce + IS_NT);          // [P2]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, S = p.S, P2 = p.P2;
 
     for (long long row = blockIdx.x; row < p.n_rows; row += gridDim.x) {
@@ -747,7 +745,7 @@ __global__ void __launch_bounds__(IS_NT) eloo_quantile_kernel(const QuantParams 
         double lwmax = -inf_f64();
         int bad = 0;
         for (int s = tid; s < P2; s += IS_NT) {
-            keys[s] = (s < S) ? gx[s] : inf_f64();
+            keys[s] = (s < S) ? quant_key(gx[s]) : QKEY_PAD;
             idx[s] = s;
             if (s < S) {
                 const double a = glw[s];
@@ -766,32 +764,49 @@ __global__ void __launch_bounds__(IS_NT) eloo_quantile_kernel(const QuantParams 
         for (int s = tid; s < S; s += IS_NT) far |= np_isclose(exp(glw[s] - lse), w0) ? 0 : 1;
         const bool uniform = !block_or(far, red);  // np.allclose(w, w[0]) (:536)
 
-        // ---- bitonic sort of (x, index), ascending, NaN last
+        // ---- bitonic sort of (x, index), ascending, NaN last.  Exchanges at distance j <= 32 of the pairs a warp
+        // owns in one sweep stay inside one block of 64 consecutive elements, so those sub-steps run back to back
+        // with warp-level synchronisation only; block barriers are needed for j > 32 and between stages.
+        auto exchange = [&](int t, int j, int k) {
+            const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+            const int l = i | j;
+            const uint64_t ka = keys[i], kb = keys[l];
+            const int ia = idx[i], ib = idx[l];
+            const bool up = ((i & k) == 0);
+            const bool greater = (ka > kb) || (ka == kb && ia > ib);  // ties in x: draw-index order
+            if (greater == up) {
+                keys[i] = kb; keys[l] = ka;
+                idx[i] = ib; idx[l] = ia;
+            }
+        };
         for (int k = 2; k <= P2; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int t = tid; t < (P2 >> 1); t += IS_NT) {
-                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                    const int l = i | j;
-                    const double ka = keys[i], kb = keys[l];
-                    const int ia = idx[i], ib = idx[l];
-                    const bool up = ((i & k) == 0);
-                    if (key_greater(ka, ia, kb, ib, S) == up) {
-                        keys[i] = kb; keys[l] = ka;
-                        idx[i] = ib; idx[l] = ia;
-                    }
-                }
+            int j = k >> 1;
+            for (; j > 32; j >>= 1) {
+                for (int t = tid; t < (P2 >> 1); t += IS_NT) exchange(t, j, k);
                 __syncthreads();
             }
+            for (int t = tid; t < (P2 >> 1); t += IS_NT) {
+                for (int jj = j; jj > 0; jj >>= 1) {
+                    exchange(t, jj, k);
+                    __syncwarp();
+                }
+            }
+            __syncthreads();
         }
 
+        double* xs = reinterpret_cast<double*>(keys);  // sorted draws, decoded in place
+        for (int s = tid; s < P2; s += IS_NT) xs[s] = quant_val(keys[s]);
+        __syncthreads();
+
+        const int C = P2 / IS_NT;  // sorted positions per thread
         if (!uniform) {
-            // ---- cumulative weights in sorted order: per-thread chunk sums, block scan, then the offsets
-            const int C = P2 / IS_NT;
+            // ---- cumulative weights in sorted order.  The cumulative weight of position i is defined as
+            // ex[c] + (running sum inside chunk c = i / C); only the per-chunk offsets ex[] and chunk-end values
+            // ce[] are kept, the few positions around a crossing are re-accumulated when a quantile is located.
             double run = 0.0;
             for (int i = tid * C; i < (tid + 1) * C; ++i) {
                 const int s = idx[i];
                 run += (s < S) ? exp(glw[s] - lse) : 0.0;
-                cs[i] = run;
             }
             double incl = run;  // inclusive scan of the chunk totals across the block
 #pragma unroll
@@ -804,7 +819,8 @@ __global__ void __launch_bounds__(IS_NT) eloo_quantile_kernel(const QuantParams 
             double base = 0.0;
             for (int w = 0; w < warp; ++w) base += part[w];
             const double excl = base + (incl - run);
-            for (int i = tid * C; i < (tid + 1) * C; ++i) cs[i] += excl;
+            ex[tid] = excl;
+            ce[tid] = excl + run;
             __syncthreads();
         }
         if (tid < p.n_probs) {
@@ -821,26 +837,40 @@ __global__ void __launch_bounds__(IS_NT) eloo_quantile_kernel(const QuantParams 
                 if (il < 0) il = 0;
                 if (ih > S - 1) ih = S - 1;
                 if (il > S - 1) il = S - 1;
-                const double a = keys[il], b = keys[ih];
+                const double a = xs[il], b = xs[ih];
                 const double d = b - a;
                 val = a + d * g;
                 if (g >= 0.5) val = b - d * (1.0 - g);
                 if (d == 0.0) val = a;
-                if (keys[S - 1] != keys[S - 1]) val = nan_f64();  // NaN in the data poisons np.quantile
+                if (xs[S - 1] != xs[S - 1]) val = nan_f64();  // NaN in the data poisons np.quantile
             } else {
-                const double total = cs[P2 - 1];
-                // first sorted position whose normalised cumulative weight reaches q (:542-544)
-                int lo = 0, hi = S;
+                const double total = ce[IS_NT - 1];
+                // first sorted position whose normalised cumulative weight reaches q (:542-544): the chunk by
+                // binary search over the chunk-end values, the position by re-accumulating that chunk
+                int lo = 0, hi = IS_NT;
                 while (lo < hi) {
                     const int mid = (lo + hi) >> 1;
-                    if (cs[mid] / total >= q) hi = mid; else lo = mid + 1;
+                    if (ce[mid] / total >= q) hi = mid; else lo = mid + 1;
                 }
-                if (lo >= S) val = keys[S - 1];      // :545-546
-                else if (lo == 0) val = keys[0];     // :549-550
+                int pos = S;
+                double c_prev = 0.0, c_cur = 0.0;
+                if (lo < IS_NT) {
+                    double run = 0.0;
+                    c_prev = (lo > 0) ? ce[lo - 1] : 0.0;
+                    for (int i = lo * C; i < (lo + 1) * C; ++i) {
+                        const int s = idx[i];
+                        run += (s < S) ? exp(glw[s] - lse) : 0.0;
+                        c_cur = ex[lo] + run;
+                        if (c_cur / total >= q) { pos = i; break; }
+                        c_prev = c_cur;
+                    }
+                }
+                if (pos >= S) val = xs[S - 1];      // :545-546
+                else if (pos == 0) val = xs[0];     // :549-550
                 else {
-                    const double w1 = cs[lo - 1] / total, w2 = cs[lo] / total;
-                    const double x1 = keys[lo - 1];
-                    val = x1 + (keys[lo] - x1) * (q - w1) / (w2 - w1);  // :552-554
+                    const double w1 = c_prev / total, w2 = c_cur / total;
+                    const double x1 = xs[pos - 1];
+                    val = x1 + (xs[pos] - x1) * (q - w1) / (w2 - w1);  // :552-554
                 }
             }
             p.out[row * p.n_probs + tid] = val;
@@ -986,7 +1016,7 @@ cudaError_t eloo_quantile_launch(QuantParams p, cudaStream_t st) {
     int p2 = IS_NT;
     while (p2 < p.S) p2 <<= 1;
     p.P2 = p2;
-    const size_t smem = sizeof(double) * (IS_RED_WORDS + 2 * (size_t)p2 + IS_NT) + sizeof(int) * (size_t)p2;
+    const size_t smem = sizeof(double) * (IS_RED_WORDS + (size_t)p2 + IS_NW + 2 * IS_NT) + sizeof(int) * (size_t)p2;
     int info[4];
     cudaError_t e = plan_kernel(eloo_quantile_kernel, smem, p.n_rows, info);
     if (e != cudaSuccess) return e;

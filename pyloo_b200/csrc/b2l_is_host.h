@@ -47,7 +47,7 @@ struct ElooParams {
 };
 
 constexpr int ELOO_MAX_PROBS = 32;
-constexpr int ELOO_QUANT_MAX_S = 8192;  // sort buffer: 20 B per (padded) draw in shared memory
+constexpr int ELOO_QUANT_MAX_S = 16384;  // sort buffer: 12 B per (padded) draw in shared memory
 
 struct QuantParams {
     const double* x;  // draws, rows of S doubles

@@ -137,7 +137,7 @@ def e_loo(data, var_name=None, group="posterior_predictive", weights=None, log_w
     """Weighted mean / variance / sd of posterior(-predictive) draws under importance weights.
 
     Same parameters and errors as ``pyloo.e_loo`` (e_loo.py:56-263).  ``type="quantile"`` returns a trailing
-    ``quantile`` dimension of ``len(probs)`` (e_loo.py:509-515) and supports up to 8192 draws per observation.
+    ``quantile`` dimension of ``len(probs)`` (e_loo.py:509-515) and supports up to 16384 draws per observation.
     """
     if type not in ["mean", "variance", "sd", "quantile"]:
         raise ValueError("type must be 'mean', 'variance', 'sd' or 'quantile'")

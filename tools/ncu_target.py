@@ -21,6 +21,11 @@ elif mode == "eloo":
     h = torch.randn(N, S, dtype=torch.float64, device="cuda")
     for _ in range(3):
         engine.eloo_cuda(h, lw, x, "mean")
+elif mode == "quant":
+    lw, _ = engine.islw_cuda(x, "tis")
+    h = torch.randn(N, S, dtype=torch.float64, device="cuda")
+    for _ in range(3):
+        engine.eloo_quantile_cuda(h, lw, [0.05, 0.5, 0.95])
 elif mode == "loo_rows":
     for _ in range(4):
         engine.loo_cuda(x.t(), 1.0)
