@@ -1,17 +1,20 @@
-// SIS / TIS importance weights and e_loo weighted expectations for sm_100a.
+// SIS / TIS importance weights, e_loo weighted expectations / quantiles and the LOGO group sums for sm_100a.
 //
-// These are the callers either side of psislw.  One CTA per observation
-// row; the row (e_loo: up to three rows) is staged in shared memory by 1-D bulk TMA when it fits and is
-// read straight from global memory otherwise, so every S is supported.  All arithmetic is IEEE FP64 with
-// the CUDA math library (no table exps here): the kernels move 16*S (weights) / 8*S (loo) / 16-24*S
-// (e_loo) bytes per observation and are bound by HBM, not by the FP64 pipe.
+// These are the callers either side of psislw.  One CTA of 256 threads per
+// observation row, persistent grid of SMs x occupancy; the row (e_loo: the ratios and the draws) is staged in
+// shared memory by 1-D bulk TMA when it fits and read straight from global memory otherwise, so every S is
+// supported (the quantile kernel sorts in shared memory: S <= 16384).  All arithmetic is IEEE FP64; the exps of
+// the normalising sums are table-driven (exp_sum below), everything else uses the CUDA math library.  The
+// kernels move 16*S (weights) / 8*S (loo) / 16-24*S (e_loo) bytes per observation.
 //
 // Reference semantics
 //   SIS   pyloo/sis.py:101-106    x -= max; x -= logsumexp(x); ess = 1 / sum(exp(x)^2)
 //   TIS   pyloo/tis.py:108-120    x -= max; log_Z = lse(x) - log S; cut = log_Z + 0.5 log S;
 //                                 x = minimum(x, cut); x -= logsumexp(x); ess = 1 / sum(exp(x)^2)
 //   loo   pyloo/loo.py:286-289    lw += ll;  :319-324 elpd_i = lse(lw);  :329-337 lppd_i = lse(ll) - log S
-//   e_loo pyloo/e_loo.py:429-463,518-531 (weighted mean / variance / sd), :328-390 (k_hat)
+//   e_loo pyloo/e_loo.py:429-463,518-531 (weighted mean / variance / sd), :328-390 (k_hat),
+//         :466-554 (weighted quantiles)
+//   logo  pyloo/loo_group.py:215-222 (per-group sums of the log-likelihood)
 // NaN handling follows NumPy: np.max and np.minimum propagate NaN, so a row holding NaN (or whose
 // maximum is not finite) comes out all-NaN through ordinary IEEE arithmetic.
 #include <math_constants.h>
