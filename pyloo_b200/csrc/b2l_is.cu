@@ -925,6 +925,170 @@ __global__ void __launch_bounds__(256) group_sum_kernel(const GroupSumParams p) 
     if (p.counters && c_nan) atomicAdd(&p.counters[0], (unsigned long long)c_nan);
 }
 
+// ===================================================================================== WAIC, column form
+// lppd_i = logsumexp_s(ll) - log S and var_s(ll) (ddof 0) for every observation of an observation-fastest
+// (S, N) matrix in ONE pass over it (pyloo/waic.py:137-145).  A block is 32 observations (lanes, coalesced
+// 256 B per draw) x 8 segments of the draw axis (warps).  Each thread runs an online logsumexp (running
+// maximum, rescaled sum; chunks of 8 draws so the exps are independent) and a chunked Chan / Welford update of
+// (mean, M2) whose shift is the running mean, so there is no E[x^2] - E[x]^2 cancellation; the 8 segments are
+// merged in a fixed order.  NaN -> -1e10 and +-inf -> +-1e10 before the sums (waic.py:113-132).  The loo-policy
+// lppd_i (infinities kept, pyloo/loo.py:329-337) equals the WAIC one unless the column holds +-inf; those rare
+// columns are redone exactly by one lane with two plain passes.
+constexpr int WC_SEG = 8, WC_CHUNK = 8;
+
+struct WcAcc {
+    double m, s;         // online logsumexp: running maximum, sum of exp(x - m)
+    double n, mean, m2;  // Chan / Welford
+};
+__device__ __forceinline__ void wc_merge(WcAcc& a, const WcAcc& b, const ExpTab& tb) {
+    if (b.n == 0.0) return;
+    if (a.n == 0.0) { a = b; return; }
+    const double mm = fmax(a.m, b.m);
+    a.s = a.s * exp_sum(a.m - mm, tb) + b.s * exp_sum(b.m - mm, tb);
+    a.m = mm;
+    const double nt = a.n + b.n, d = b.mean - a.mean;
+    a.mean += d * (b.n / nt);
+    a.m2 += b.m2 + d * d * (a.n * b.n / nt);
+    a.n = nt;
+}
+
+__global__ void __launch_bounds__(32 * WC_SEG) waic_cols_kernel(const WaicColsParams p) {
+    __shared__ double tabs[64];
+    __shared__ WcAcc part[WC_SEG][32];
+    __shared__ int infs[WC_SEG][32];
+    const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5, S = p.S;
+    if (threadIdx.x < 32) {
+        tabs[threadIdx.x] = exp2((double)threadIdx.x / 32.0);
+        tabs[32 + threadIdx.x] = exp2(-(double)threadIdx.x / 32.0);
+    }
+    __syncthreads();
+    ExpTab tb;
+    tb.t = tabs;
+    tb.tinv = tabs + 32;
+    const long long obs = (long long)blockIdx.x * 32 + lane;
+    const bool live = obs < p.N;
+    const int per = (S + WC_SEG - 1) / WC_SEG;
+    const int s0 = seg * per, s1 = min(S, s0 + per);
+    unsigned c_nan = 0, c_pinf = 0, c_ninf = 0;
+    WcAcc a = {-inf_f64(), 0.0, 0.0, 0.0, 0.0};
+    if (live) {
+        const double* col = p.ll + obs;
+        // one chunk of nb <= 8 sanitised draws folded into the accumulators
+        auto fold = [&](const double (&w)[WC_CHUNK], int nb) {
+            double cm = w[0];
+#pragma unroll
+            for (int i = 1; i < WC_CHUNK; ++i)
+                if (i < nb) cm = fmax(cm, w[i]);
+            if (cm > a.m) {  // new running maximum: rescale the sum (exp_sum(-inf) = 0 on the first chunk)
+                a.s *= exp_sum(a.m - cm, tb);
+                a.m = cm;
+            }
+            const double c = (a.n == 0.0) ? w[0] : a.mean;  // shift = running mean
+            double es = 0.0, sd = 0.0, sdd = 0.0;
+#pragma unroll
+            for (int i = 0; i < WC_CHUNK; ++i) {
+                if (i < nb) {
+                    es += exp_sum(w[i] - a.m, tb);
+                    const double d = w[i] - c;
+                    sd += d;
+                    sdd += d * d;
+                }
+            }
+            a.s += es;
+            const double nbd = (double)nb, inv = 1.0 / nbd;
+            const double mean_b = c + sd * inv, m2_b = sdd - sd * sd * inv;
+            if (a.n == 0.0) {
+                a.n = nbd; a.mean = mean_b; a.m2 = m2_b;
+            } else {
+                const double nt = a.n + nbd, f = nbd / nt, d = mean_b - a.mean;
+                a.mean += d * f;
+                a.m2 += m2_b + d * d * (a.n * f);
+                a.n = nt;
+            }
+        };
+        auto sanitise = [&](double (&w)[WC_CHUNK], int nb) {
+            bool fin = true;
+#pragma unroll
+            for (int i = 0; i < WC_CHUNK; ++i) fin = fin && (i >= nb || is_finite(w[i]));
+            if (fin) return;
+#pragma unroll
+            for (int i = 0; i < WC_CHUNK; ++i) {
+                if (i >= nb) continue;
+                const double v = w[i];
+                if (v != v) { w[i] = -1e10; ++c_nan; }
+                else if (v == inf_f64()) { w[i] = 1e10; ++c_pinf; }
+                else if (v == -inf_f64()) { w[i] = -1e10; ++c_ninf; }
+            }
+        };
+        int s = s0;
+        double nx[WC_CHUNK];
+        const bool any_full = (s + WC_CHUNK <= s1);
+        if (any_full) {
+#pragma unroll
+            for (int i = 0; i < WC_CHUNK; ++i) nx[i] = col[(long long)(s + i) * p.stride_s];
+        }
+        for (; s + WC_CHUNK <= s1; s += WC_CHUNK) {
+            double w[WC_CHUNK];
+#pragma unroll
+            for (int i = 0; i < WC_CHUNK; ++i) w[i] = nx[i];
+            if (s + 2 * WC_CHUNK <= s1) {  // the next chunk's loads are in flight while this one is folded
+#pragma unroll
+                for (int i = 0; i < WC_CHUNK; ++i) nx[i] = col[(long long)(s + WC_CHUNK + i) * p.stride_s];
+            }
+            sanitise(w, WC_CHUNK);
+            fold(w, WC_CHUNK);
+        }
+        if (s < s1) {
+            const int nb = s1 - s;
+            double w[WC_CHUNK];
+#pragma unroll
+            for (int i = 0; i < WC_CHUNK; ++i) w[i] = (i < nb) ? col[(long long)(s + i) * p.stride_s] : 0.0;
+            sanitise(w, nb);
+            fold(w, nb);
+        }
+    }
+    part[seg][lane] = a;
+    infs[seg][lane] = (int)(c_pinf + c_ninf);
+    __syncthreads();
+    if (seg == 0 && live) {
+        WcAcc t = part[0][lane];
+        int n_inf = infs[0][lane];
+        for (int g = 1; g < WC_SEG; ++g) {
+            wc_merge(t, part[g][lane], tb);
+            n_inf += infs[g][lane];
+        }
+        const double lppdw = log(t.s) + (t.m - p.log_S);  // utils.py:352-357 with b_inv = S
+        double lppd = lppdw;
+        if (n_inf > 0) {
+            // loo policy keeps the infinities: plain two-pass logsumexp of the NaN-replaced column
+            const double* col = p.ll + obs;
+            double mx = -inf_f64();
+            for (int s = 0; s < S; ++s) {
+                double v = col[(long long)s * p.stride_s];
+                if (v != v) v = -1e10;
+                mx = fmax(mx, v);
+            }
+            double sum = 0.0;
+            for (int s = 0; s < S; ++s) {
+                double v = col[(long long)s * p.stride_s];
+                if (v != v) v = -1e10;
+                sum += exp(v - mx);
+            }
+            lppd = log(sum) + (mx - p.log_S);
+        }
+        p.lppdw_i[obs] = lppdw;
+        p.lppd_i[obs] = lppd;
+        p.var_i[obs] = t.m2 / (double)S;
+        p.k_i[obs] = inf_f64();    // no PSIS stage: same values as the general kernel writes in this mode
+        p.elpd_i[obs] = nan_f64();
+    }
+    if (p.counters) {
+        if (c_nan) atomicAdd(&p.counters[0], (unsigned long long)c_nan);
+        if (c_pinf) atomicAdd(&p.counters[1], (unsigned long long)c_pinf);
+        if (c_ninf) atomicAdd(&p.counters[2], (unsigned long long)c_ninf);
+    }
+}
+
 // ===================================================================================== host side
 static size_t is_smem_bytes(int S) { return sizeof(double) * (IS_RED_WORDS + (size_t)((S + 1) & ~1)); }
 constexpr size_t SMEM_LIMIT = 227 * 1024;
@@ -1032,6 +1196,13 @@ cudaError_t group_sum_launch(const GroupSumParams& p, cudaStream_t st) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     group_sum_kernel<<<sms * 8, 256, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t waic_cols_launch(const WaicColsParams& p, cudaStream_t st) {
+    const long long blocks = (p.N + 31) / 32;
+    if (blocks > 0x7fffffffll) return cudaErrorInvalidConfiguration;
+    waic_cols_kernel<<<(unsigned)blocks, 32 * WC_SEG, 0, st>>>(p);
     return cudaGetLastError();
 }
 

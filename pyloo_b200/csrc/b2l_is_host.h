@@ -76,6 +76,19 @@ struct GroupSumParams {
 };
 cudaError_t group_sum_launch(const GroupSumParams& p, cudaStream_t st);
 
+// WAIC pointwise pass straight on the observation-fastest (S, N) matrix (pyloo/waic.py:122-145): no
+// transposed panels, one read of the matrix.  Outputs as b2l_loo_dev_f64 with B2L_FLAG_WAIC_ONLY.
+struct WaicColsParams {
+    const double* ll;      // element (s, i) at ll[s * stride_s + i]
+    long long stride_s;
+    double *elpd_i, *k_i, *lppd_i, *var_i, *lppdw_i;  // N each
+    unsigned long long* counters;                     // nullable: NaN / +inf / -inf inputs
+    long long N;
+    int S;
+    double log_S;
+};
+cudaError_t waic_cols_launch(const WaicColsParams& p, cudaStream_t st);
+
 // Launch planners + launchers.  `*_info`: [0] staged in shared memory, [1] grid, [2] dynamic smem bytes,
 // [3] CTAs per SM.  The e_loo launcher needs `scratch` only when info[0] == 0.
 cudaError_t is_plan(int method, int mode, int S, long long n_rows, int* info);

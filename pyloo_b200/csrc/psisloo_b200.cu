@@ -676,6 +676,17 @@ extern "C" int b2l_loo_dev_f64(const double* ll, int64_t S, int64_t N, int64_t s
     }
     if (!(stride_n == 1 || N == 1))
         return fail(B2L_E_INVALID, "one of (stride_s, stride_n) must be 1");
+    if (rp.waic_only && !diag && !getenv("B2L_FORCE_LEGACY")) {
+        // WAIC alone needs no rows: one pass over the observation-fastest matrix
+        WaicColsParams wp;
+        memset(&wp, 0, sizeof(wp));
+        wp.ll = ll; wp.stride_s = stride_s; wp.N = N; wp.S = (int)S; wp.log_S = std::log((double)S);
+        wp.elpd_i = elpd_i; wp.k_i = k_i; wp.lppd_i = lppd_i; wp.var_i = var_i; wp.lppdw_i = lppdw_i;
+        wp.counters = counters;
+        ProfScope prof(B2L_PROF_IS, st);
+        CK(waic_cols_launch(wp, st));
+        return 0;
+    }
     const long long P = panel_obs(S, N);
     const size_t panel_bytes = align_up((size_t)P * (size_t)S * 8, 256);
     rc = plan_split(S, M, MODE_LOO, P, &sp);

@@ -222,6 +222,33 @@ def test_waic_only_flag_skips_psis_but_keeps_waic_outputs():
     assert np.all(np.isinf(wo["pareto_k"]))
 
 
+@pytest.mark.parametrize("S,N", [(3, 3), (7, 33), (63, 31), (64, 40), (1000, 70), (4000, 257), (16000, 9)])
+def test_waic_column_kernel_against_oracle(S, N):
+    """WAIC alone on the (chain, draw, obs) layout runs the one-pass column kernel (online logsumexp + chunked
+    Chan variance): against the oracle for ragged S / N, an outlier as the first draw, NaN and +-inf columns."""
+    rng = np.random.default_rng(S * 1000 + N)
+    ll = -1.4 + rng.normal(size=(S, N)) * rng.uniform(0.1, 3.0, size=N)
+    ll[0, 0] = 40.0                                   # the variance shift starts on an outlier
+    if S >= 7:
+        ll[3, 1] = np.nan
+        ll[5, 2 % N] = np.inf
+        ll[6, min(N - 1, 4)] = -np.inf
+    if N > 6:
+        ll[:, 5] = -np.inf                            # loo-policy lppd_i is NaN, the WAIC one is -1e10
+        ll[:, 6] = 0.25                               # constant column: variance exactly 0
+    wo = gpu_loo(ll, 1.0, waic_only=True)
+    with np.errstate(all="ignore"):
+        ww = orc.waic_pointwise(ll)
+        lppd_loo = np.array([orc.logsumexp_row(np.where(np.isnan(c), -1e10, c), b_inv=S) for c in ll.T])
+    close(wo["lppdw_i"], ww["lppd_i"])
+    close(wo["var_i"], ww["var_i"], rtol=1e-10, atol=1e-18)
+    same_special(wo["lppd_i"], lppd_loo)
+    close(wo["lppd_i"], lppd_loo)
+    assert np.all(np.isinf(wo["pareto_k"])) and np.all(np.isnan(wo["elpd_i"]))
+    c = wo["counters"]
+    assert c[0] == int(np.isnan(ll).sum()) and c[1] == int(np.isposinf(ll).sum()) and c[2] == int(np.isneginf(ll).sum())
+
+
 def test_layouts_agree_bitwise():
     """Rows layout, obs-fastest layout (panel transpose) and odd-S / unaligned (non-TMA) path give
     the same bits: an observation's result must not depend on the tile it lands in
