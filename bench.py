@@ -345,6 +345,23 @@ def main():
                "roofline": {"bound": "hbm", "achieved": loo_bytes / (ms_loo * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                             "frac": loo_bytes / (ms_loo * 1e-3) / 1e9 / peak},
                "elpd_loo": merged.elpd_sum, "n_total": merged.n, "collective": "all_gather(32 f64)" if world > 1 else None}
+        # waic alone (pl.waic, loo_compare(ic="waic")): the one-pass column kernel, no transposed panels
+        def waic_step():
+            return engine.loo_cuda(ll, LOO_REFF, workspace=wsl, waic_only=True)
+
+        for _ in range(3):
+            waic_step()
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            waic_step()
+        ev1.record()
+        barrier()
+        ms_waic = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+        waic_bytes = n_loo * (8 * S + 24)
+        loo["waic_only"] = {"value": world * n_loo / (ms_waic * 1e-3), "unit": "obs/s", "ms_per_step": ms_waic,
+                            "roofline": {"bound": "hbm", "achieved": waic_bytes / (ms_waic * 1e-3) / 1e9, "peak": peak,
+                                         "unit": "GB/s", "frac": waic_bytes / (ms_waic * 1e-3) / 1e9 / peak}}
         del ll
 
     # ---- the callers either side of psislw: SIS / TIS weights and e_loo on a 2-round slab
