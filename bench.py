@@ -362,6 +362,25 @@ def main():
         loo["waic_only"] = {"value": world * n_loo / (ms_waic * 1e-3), "unit": "obs/s", "ms_per_step": ms_waic,
                             "roofline": {"bound": "hbm", "achieved": waic_bytes / (ms_waic * 1e-3) / 1e9, "peak": peak,
                                          "unit": "GB/s", "frac": waic_bytes / (ms_waic * 1e-3) / 1e9 / peak}}
+        # pl.loo end to end through the host-buffer C-ABI entry: pinned (S, N) host log-likelihood in, pointwise
+        # vectors + statistics record out (H2D of the matrix inside the timed region)
+        if not args.skip_e2e:
+            hll = torch.empty((S, n_loo), dtype=torch.float64, pin_memory=True)
+            hll.copy_(ll)
+            torch.cuda.synchronize()
+            hll_np = hll.numpy()
+            engine.loo_host(hll_np, LOO_REFF, device=local)
+            barrier()
+            n_e2e = max(2, min(args.steps, 5))
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                r_host = engine.loo_host(hll_np, LOO_REFF, device=local)
+            t_loo = max_over_ranks((time.perf_counter() - t0) / n_e2e * 1e3) * 1e-3
+            assert abs(r_host["stats"].elpd_sum - merged.elpd_sum / world) < 1e-6 * abs(merged.elpd_sum) or world > 1
+            loo["e2e"] = {"value": world * n_loo / t_loo, "unit": "obs/s", "h2d_bytes_per_step": n_loo * S * 8,
+                          "d2h_bytes_per_step": n_loo * 40 + 256, "ms_per_step": t_loo * 1e3, "steps": n_e2e,
+                          "api": "b2l_loo_host_f64 via pyloo_b200.engine.loo_host (pinned host in)"}
+            del hll
         del ll
 
     # ---- the callers either side of psislw: SIS / TIS weights and e_loo on a 2-round slab
