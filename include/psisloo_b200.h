@@ -183,6 +183,14 @@ int b2l_group_sum_dev_f64(const double* ll, int64_t S, int64_t N, int64_t stride
                           const int32_t* members, const int32_t* offsets, int32_t G, double* out,
                           int64_t out_stride_g, unsigned long long* counters, void* stream);
 
+/* loo_subsample's PSIS stage: the subsampled observations (pyloo/loo_subsample.py:330,
+ * `log_likelihood.isel(...)`, feeding :371-383) gathered on the device into contiguous rows,
+ *   out[j * out_stride_n + s] = ll[s * stride_s + idx[j] * stride_n],  j < m,
+ * which then go through b2l_loo_dev_f64 with stride_s = 1.  idx: m observation indices (device, int64;
+ * repeats allowed -- the reference samples with replacement); the caller guarantees 0 <= idx[j] < N.       */
+int b2l_gather_rows_dev_f64(const double* ll, int64_t S, int64_t N, int64_t stride_s, int64_t stride_n,
+                            const int64_t* idx, int64_t m, double* out, int64_t out_stride_n, void* stream);
+
 /* Per-kernel device timing for benchmarks (no reference counterpart): with b2l_profile(1) every kernel
  * launch is bracketed by CUDA events on its stream; b2l_profile_read() synchronises them and returns
  * summed milliseconds and launch counts per kernel kind since the last read.  Not thread safe.    */

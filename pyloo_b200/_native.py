@@ -37,7 +37,7 @@ EXPORTS = [
     "b2l_psislw_host_f64", "b2l_loo_host_f64", "b2l_row_launch_info", "b2l_profile", "b2l_profile_read",
     "b2l_split_launch_info", "b2l_handover_reasons",
     "b2l_islw_dev_f64", "b2l_is_workspace_bytes", "b2l_loo_is_dev_f64", "b2l_eloo_workspace_bytes",
-    "b2l_eloo_dev_f64", "b2l_eloo_quantile_dev_f64", "b2l_group_sum_dev_f64",
+    "b2l_eloo_dev_f64", "b2l_eloo_quantile_dev_f64", "b2l_group_sum_dev_f64", "b2l_gather_rows_dev_f64",
 ]
 PROF_KINDS = ("stream", "tail", "apply", "row", "transpose", "stats", "is", "eloo")
 IS_SIS, IS_TIS = 1, 2
@@ -139,6 +139,8 @@ def _declare(lib) -> None:
     lib.b2l_eloo_quantile_dev_f64.argtypes = [vp, i64, vp, i64, i64, i64, vp, i32, vp, vp]
     lib.b2l_group_sum_dev_f64.restype = c.c_int
     lib.b2l_group_sum_dev_f64.argtypes = [vp, i64, i64, i64, i64, vp, vp, i32, vp, i64, vp, vp]
+    lib.b2l_gather_rows_dev_f64.restype = c.c_int
+    lib.b2l_gather_rows_dev_f64.argtypes = [vp, i64, i64, i64, i64, vp, i64, vp, i64, vp]
     lib.b2l_row_launch_info.restype = c.c_int
     lib.b2l_row_launch_info.argtypes = [i64, i32, i32] + [c.POINTER(i32)] * 5
 

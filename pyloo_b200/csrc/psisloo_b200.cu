@@ -904,6 +904,46 @@ extern "C" int b2l_group_sum_dev_f64(const double* ll, int64_t S, int64_t N, int
     return 0;
 }
 
+// ------------------------------------------------------------------------------------ gather (loo_subsample)
+// dst[j * dst_ld + s] = src[s * stride_s + idx[j] * stride_n]  for j < m, s < S   (32 x 32 tiles, padded smem):
+// the subsampled observations of pyloo/loo_subsample.py:330 (`log_likelihood.isel(...)`) as contiguous rows.
+__global__ void __launch_bounds__(256) gather_rows_kernel(const double* __restrict__ src, long long stride_s,
+                                                          long long stride_n, const long long* __restrict__ idx,
+                                                          double* __restrict__ dst, long long dst_ld, int S, int m) {
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const long long j0 = (long long)blockIdx.x * 32, s0 = (long long)blockIdx.y * 32;
+    const long long col = (j0 + tx < m) ? idx[j0 + tx] : 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const long long s = s0 + ty + 8 * k;
+        if (s < S && j0 + tx < m) tile[ty + 8 * k][tx] = src[s * stride_s + col * stride_n];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const long long j = j0 + ty + 8 * k, s = s0 + tx;
+        if (j < m && s < S) dst[j * dst_ld + s] = tile[tx][ty + 8 * k];
+    }
+}
+
+extern "C" int b2l_gather_rows_dev_f64(const double* ll, int64_t S, int64_t N, int64_t stride_s, int64_t stride_n,
+                                       const int64_t* idx, int64_t m, double* out, int64_t out_stride_n,
+                                       void* stream) {
+    if (!ll || !idx || !out || S < 1 || N < 1 || m < 0) return fail(B2L_E_INVALID, "null pointer or bad size");
+    if (out_stride_n < S) return fail(B2L_E_INVALID, "out_stride_n < S");
+    if (S > INT32_MAX || m > INT32_MAX) return fail(B2L_E_UNSUPPORTED, "S or m too large");
+    if (m == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((unsigned)((m + 31) / 32), (unsigned)((S + 31) / 32));
+    if (grid.y > 65535u) return fail(B2L_E_UNSUPPORTED, "gather: too many draws (%lld)", (long long)S);
+    ProfScope prof(B2L_PROF_TRANSPOSE, st);
+    gather_rows_kernel<<<grid, 256, 0, st>>>(ll, stride_s, stride_n, reinterpret_cast<const long long*>(idx), out,
+                                             out_stride_n, (int)S, (int)m);
+    CK(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int b2l_handover_reasons(uint64_t* out16, int32_t reset) {
     if (!out16) return fail(B2L_E_INVALID, "null pointer");
     unsigned long long a[HO_REASONS], b[HO_REASONS];

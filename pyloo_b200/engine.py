@@ -590,3 +590,28 @@ def group_loo_host(ll_sn, group_index, n_groups: int, reff: float = 1.0, method:
 
 def _method_name(method) -> str:
     return str(getattr(method, "value", method)).lower()
+
+
+def loo_subset_cuda(ll_sn, obs_index, reff: float = 1.0, *, waic_only: bool = False):
+    """The PSIS stage of ``loo_subsample`` (pyloo/loo_subsample.py:330, :371-383) on a device-resident
+    ``(S, N)`` log-likelihood: the observations ``obs_index`` (int64 tensor or sequence, repeats allowed) are
+    gathered into contiguous rows on the device and go through the fused LOO pass.  Asynchronous.
+    Returns the dict of :func:`loo_cuda` with one entry per element of ``obs_index``."""
+    torch = _torch()
+    lib = _native.load()
+    if ll_sn.dtype != torch.float64 or ll_sn.dim() != 2 or not ll_sn.is_cuda:
+        raise ValueError("expected a 2-D float64 CUDA tensor")
+    S, N = ll_sn.shape
+    idx = torch.as_tensor(obs_index, dtype=torch.int64, device=ll_sn.device).contiguous()
+    if idx.dim() != 1:
+        raise ValueError("obs_index must be one-dimensional")
+    if idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= N):
+        raise IndexError("obs_index out of range")
+    m = idx.numel()
+    rows = torch.empty((m, S), dtype=torch.float64, device=ll_sn.device)
+    ss, sn = ll_sn.stride()
+    with torch.cuda.device(ll_sn.device):
+        rc = lib.b2l_gather_rows_dev_f64(ll_sn.data_ptr(), S, N, ss, sn, idx.data_ptr(), m, rows.data_ptr(), S,
+                                         _stream_ptr(torch, ll_sn.device))
+    _native.check(rc)
+    return loo_cuda(rows.t(), reff, waic_only=waic_only)

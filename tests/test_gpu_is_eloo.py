@@ -18,6 +18,7 @@ import pyloo_b200 as pl
 from pyloo_b200 import engine
 from pyloo_b200.data import LiteDataArray, from_dict
 from oracle import is_oracle as iso
+from oracle.psis_oracle import loo_pointwise as orc_loo
 
 RTOL = 1e-10
 
@@ -416,3 +417,26 @@ def test_host_wrappers_are_slab_invariant(monkeypatch):
     pieces = run_all()
     for a, b in zip(whole, pieces):
         assert np.array_equal(a, b, equal_nan=True)
+
+
+def test_loo_subset_gathers_on_the_device():
+    # loo_subsample's PSIS stage (loo_subsample.py:330, :371-383): same numbers as the full pass at those indices
+    import torch
+
+    rng = np.random.default_rng(41)
+    S, N = 2000, 500
+    ll = -1.2 + 0.8 * rng.normal(size=(S, N))
+    idx = np.concatenate([rng.choice(N, size=70, replace=False), [3, 3, N - 1]])   # repeats allowed
+    d_ll = torch.from_numpy(ll).cuda()
+    full = engine.loo_cuda(d_ll, 1.0)
+    sub = engine.loo_subset_cuda(d_ll, idx, 1.0)
+    rows = engine.loo_subset_cuda(d_ll.t().contiguous().t(), idx, 1.0)          # row-contiguous storage
+    torch.cuda.synchronize()
+    for key in ("elpd_i", "pareto_k", "lppd_i", "var_i"):
+        a, b = full[key].cpu().numpy()[idx], sub[key].cpu().numpy()
+        close(b, a, 1e-13)
+        assert np.array_equal(rows[key].cpu().numpy(), b)
+    ref = orc_loo(ll[:, idx[:5]], 1.0)
+    close(sub["elpd_i"].cpu().numpy()[:5], ref["elpd_i"])
+    with pytest.raises(IndexError):
+        engine.loo_subset_cuda(d_ll, [0, N], 1.0)
