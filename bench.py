@@ -221,9 +221,19 @@ def main():
     os.environ["B2L_DEVICE"] = str(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version there)
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL announces its version on stdout when the communicator is created: send that to stderr so that
+        # stdout carries the one JSON line only
+        sys.stdout.flush()
+        saved_out = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_out, 1)
+            os.close(saved_out)
 
     def barrier():
         if world > 1:
