@@ -181,3 +181,91 @@ def test_ess_mean_sane():
         ar[:, t] = 0.9 * ar[:, t - 1] + eps[:, t]
     # AR(1) with phi = 0.9: ESS ~ N (1 - phi) / (1 + phi) ~ 0.053 N
     assert 0.02 * 8000 < ess_mean(ar) < 0.12 * 8000
+
+
+# ------------------------------------------------------------------ widened rows: host-side contracts (no GPU)
+def _small_idata():
+    rng = np.random.default_rng(3)
+    ll = rng.normal(size=(2, 50, 6))
+    return from_dict(posterior={"mu": rng.normal(size=(2, 50))}, log_likelihood={"y": ll},
+                     posterior_predictive={"y": rng.normal(size=(2, 50, 6)), "z": rng.normal(size=(2, 50, 6))},
+                     observed_data={"y": rng.normal(size=6)}, dims={"y": ["obs"], "z": ["obs"]})
+
+
+def test_e_loo_argument_errors_precede_any_device_work():
+    idata = _small_idata()
+    lw = LiteDataArray(np.zeros((6, 100)), ("obs", "__sample__"))
+    with pytest.raises(ValueError, match="type must be 'mean', 'variance', 'sd' or 'quantile'"):
+        pl.e_loo(idata, var_name="y", log_weights=lw, type="mode")                  # e_loo.py:151-152
+    with pytest.raises(ValueError, match="probs must be provided"):
+        pl.e_loo(idata, var_name="y", log_weights=lw, type="quantile")              # :155-156
+    with pytest.raises(ValueError, match="probs must be between 0 and 1"):
+        pl.e_loo(idata, var_name="y", log_weights=lw, type="quantile", probs=[0.0, 0.5])
+    with pytest.raises(ValueError, match="Either weights or log_weights must be provided"):
+        pl.e_loo(idata, var_name="y")                                               # :166-167
+    with pytest.raises(ValueError, match="does not have a prior group"):
+        pl.e_loo(idata, group="prior", log_weights=lw)                              # :174-175
+    with pytest.raises(ValueError, match="Multiple variables found in posterior_predictive group"):
+        pl.e_loo(idata, log_weights=lw)                                             # :183-187
+    with pytest.raises(ValueError, match="Variable 'q' not found"):
+        pl.e_loo(idata, var_name="q", log_weights=lw)                               # :188-192
+    with pytest.raises(ValueError, match="tail_len must be at least 5"):
+        pl.compute_pareto_k(np.zeros(10), np.zeros(10), tail_len=4)                 # :295-296
+    with pytest.raises(ValueError, match="log_ratios must have '__sample__' dimension"):
+        pl.compute_pareto_k(None, LiteDataArray(np.zeros((3, 10)), ("a", "b")))     # :299-300
+
+
+def test_pareto_diagnostics_of_e_loo():
+    from pyloo_b200.e_loo import _pareto_convergence_rate, _pareto_khat_threshold, _pareto_min_ss
+
+    assert _pareto_min_ss(0.5) == pytest.approx(100.0) and _pareto_min_ss(-1.0) == pytest.approx(10.0)
+    assert _pareto_min_ss(1.0) == np.inf and _pareto_min_ss(np.nan) == np.inf      # e_loo.py:393-398
+    assert _pareto_khat_threshold(1000) == pytest.approx(1 - 1 / 3)                # :401-403
+    assert _pareto_convergence_rate(-0.1, 100) == 1.0 and _pareto_convergence_rate(1.5, 100) == 0.0
+    assert _pareto_convergence_rate(0.5, 100) == pytest.approx(1 - 1 / np.log(100))  # :415-416
+    k, n = 0.3, 400
+    expect = max(0, (2 * (k - 1) * n ** (2 * k + 1) + (1 - 2 * k) * n ** (2 * k) + n**2) / ((n - 1) * (n - n ** (2 * k))))
+    assert _pareto_convergence_rate(k, n) == pytest.approx(expect, rel=1e-14)
+    np.testing.assert_allclose(_pareto_convergence_rate(np.array([-1.0, 0.0, 1.0, 2.0]), 50), [1.0, 1.0, 1.0, 0.0])
+
+
+def test_loo_group_and_metric_argument_errors():
+    idata = _small_idata()
+    with pytest.raises(ValueError, match=r"Length of group_ids \(3\) must match the number of observations"):
+        pl.loo_group(idata, [0, 1, 2], reff=1.0)                                     # loo_group.py:156-160
+    with pytest.raises(TypeError, match="Valid scale values"):
+        pl.loo_group(idata, np.arange(6) % 2, reff=1.0, scale="bits")                # :171-172
+    with pytest.raises(ValueError, match="Invalid method 'xx'"):
+        pl.loo_group(idata, np.arange(6) % 2, reff=1.0, method="xx")                 # :199-203
+    y = np.zeros(6)
+    with pytest.raises(ValueError, match="does not have a nope group"):
+        pl.loo_predictive_metric(idata, y, var_name="y", group="nope")               # loo_predictive_metric.py:158-159
+    with pytest.raises(ValueError, match="Variable 'q' not found in log_likelihood group"):
+        pl.loo_predictive_metric(idata, y, var_name="y", log_lik_var_name="q")       # :174-178
+    with pytest.raises(ValueError, match=r"Length of y \(2\) must match"):
+        pl.loo_predictive_metric(idata, y[:2], var_name="y")                         # :196-200
+    with pytest.raises(ValueError, match="Invalid metric: f1"):
+        pl.loo_predictive_metric(idata, y, var_name="y", metric="f1")                # :202-206
+    with pytest.raises(ValueError, match="Multiple variables found in posterior_predictive group"):
+        pl.loo_score(idata, y_var="y")                                               # loo_score.py:458-462
+    with pytest.raises(ValueError, match="Variable 'q' not found in posterior_predictive group"):
+        pl.loo_score(idata, x_var="y", x2_var="q", y_var="y")                        # :485-489
+    with pytest.raises(ValueError, match="does not have a nope group"):
+        pl.loo_score(idata, x_var="y", y_group="nope")                               # :493-494
+    with pytest.raises(ValueError, match="Invalid method 'nope'"):
+        pl.compute_importance_weights(np.zeros((2, 10)), method="nope")              # base.py:100-107
+    with pytest.raises(ValueError, match="log_weights must have a __sample__ dimension"):
+        pl.compute_importance_weights(LiteDataArray(np.zeros((2, 10)), ("a", "b")), method="sis")  # base.py:93-98
+
+
+def test_elpddata_logo_report():
+    e = pl.ELPDData(data=[-12.5, 1.25, 3.5, 0.4, 1000, 10, True, "log", 25.0, 2.5, np.array([0.1, 0.9, 1.4] + [0.2] * 7), 0.67],
+                    index=["elpd_logo", "se", "p_logo", "p_logo_se", "n_samples", "n_groups", "warning", "scale",
+                           "logoic", "logoic_se", "pareto_k", "good_k"])
+    text = str(e)
+    assert "Computed from 1000 posterior samples and 10 groups log-likelihood matrix." in text   # elpd.py:74-81
+    assert "elpd_logo   -12.50      1.25" in text and "p_logo       3.50        0.40" in text
+    assert "logoic      25.00       2.50" in text
+    assert "There has been a warning during the calculation." in text
+    assert "(-Inf, 0.67]   (good)      8   80.0%" in text and "(1, Inf)   (very bad)    1    10.0%" in text
+    assert e.n_groups == 10
