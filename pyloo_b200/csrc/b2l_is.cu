@@ -1089,6 +1089,266 @@ __global__ void __launch_bounds__(32 * WC_SEG) waic_cols_kernel(const WaicColsPa
     }
 }
 
+// ===================================================================================== SIS / TIS loo, column form
+// loo(method = "sis" | "tis") on the observation-fastest matrix without transposed panels: the same block
+// shape as waic_cols_kernel (32 observations x 8 draw segments), one sweep of the matrix per logsumexp that
+// needs the previous one's result -- SIS: (max, sum, sum of squares of -ll; logsumexp of ll) then
+// logsumexp(lw + ll); TIS: one more sweep for the truncated sum.  Every sweep is an online logsumexp in chunks of
+// 8 draws with the next chunk's loads in flight.  Columns holding +-inf are redone by one lane with the plain
+// multi-pass arithmetic of is_row_kernel, so the IEEE special cases come out as NumPy's.
+template <class F>
+__device__ __forceinline__ void col_sweep(const double* col, long long stride_s, int s0, int s1, F&& fold) {
+    int s = s0;
+    double nx[WC_CHUNK];
+    if (s + WC_CHUNK <= s1) {
+#pragma unroll
+        for (int i = 0; i < WC_CHUNK; ++i) nx[i] = col[(long long)(s + i) * stride_s];
+    }
+    for (; s + WC_CHUNK <= s1; s += WC_CHUNK) {
+        double w[WC_CHUNK];
+#pragma unroll
+        for (int i = 0; i < WC_CHUNK; ++i) w[i] = nx[i];
+        if (s + 2 * WC_CHUNK <= s1) {
+#pragma unroll
+            for (int i = 0; i < WC_CHUNK; ++i) nx[i] = col[(long long)(s + WC_CHUNK + i) * stride_s];
+        }
+        fold(w, WC_CHUNK);
+    }
+    if (s < s1) {
+        const int nb = s1 - s;
+        double w[WC_CHUNK];
+#pragma unroll
+        for (int i = 0; i < WC_CHUNK; ++i) w[i] = (i < nb) ? col[(long long)(s + i) * stride_s] : 0.0;
+        fold(w, nb);
+    }
+}
+
+struct LseAcc {
+    double m, s, q;  // running maximum, sum of exp(x - m), sum of exp(x - m)^2
+};
+__device__ __forceinline__ void lse_fold(LseAcc& a, const double (&x)[WC_CHUNK], int nb, const ExpTab& tb) {
+    double cm = x[0];
+#pragma unroll
+    for (int i = 1; i < WC_CHUNK; ++i)
+        if (i < nb) cm = fmax(cm, x[i]);
+    if (cm > a.m) {
+        const double f = exp_sum(a.m - cm, tb);
+        a.s *= f;
+        a.q *= f * f;
+        a.m = cm;
+    }
+    double es = 0.0, eq = 0.0;
+#pragma unroll
+    for (int i = 0; i < WC_CHUNK; ++i) {
+        if (i < nb) {
+            const double e = exp_sum(x[i] - a.m, tb);
+            es += e;
+            eq += e * e;
+        }
+    }
+    a.s += es;
+    a.q += eq;
+}
+__device__ __forceinline__ void lse_merge(LseAcc& a, const LseAcc& b, const ExpTab& tb) {
+    const double mm = fmax(a.m, b.m);
+    const double fa = exp_sum(a.m - mm, tb), fb = exp_sum(b.m - mm, tb);
+    a.s = a.s * fa + b.s * fb;
+    a.q = a.q * fa * fa + b.q * fb * fb;
+    a.m = mm;
+}
+
+// plain serial evaluation for one column (rare: +-inf present), same arithmetic as is_row_kernel in loo mode
+template <int METHOD>
+__device__ __noinline__ void is_loo_serial(const double* col, long long stride_s, int S, double log_S, double& elpd,
+                                           double& ess, double& lppd) {
+    auto ll = [&](int s) {
+        const double v = col[(long long)s * stride_s];
+        return (v != v) ? -1e10 : v;
+    };
+    double mx = -inf_f64(), mn = inf_f64();
+    for (int s = 0; s < S; ++s) {
+        const double v = -ll(s);
+        mx = fmax(mx, v);
+        mn = fmin(mn, v);
+    }
+    double s1 = 0.0, s2 = 0.0, sl = 0.0;
+    for (int s = 0; s < S; ++s) {
+        const double v = -ll(s), e = exp(v - mx);
+        s1 += e;
+        s2 += e * e;
+        sl += exp(mn - v);
+    }
+    double lse, cut = inf_f64();
+    if (METHOD == IS_METHOD_SIS) {
+        lse = log(s1);
+        ess = (s1 * s1) / s2;
+    } else {
+        cut = (log(s1) - log_S) + 0.5 * log_S;
+        const double mx2 = np_minimum(0.0, cut);
+        double t1 = 0.0, t2 = 0.0;
+        for (int s = 0; s < S; ++s) {
+            const double a = exp(np_minimum(-ll(s) - mx, cut) - mx2);
+            t1 += a;
+            t2 += a * a;
+        }
+        lse = log(t1) + mx2;
+        ess = (t1 * t1) / t2;
+    }
+    double tmax = -inf_f64();
+    for (int s = 0; s < S; ++s) {
+        const double v = -ll(s);
+        double x = v - mx;
+        if (METHOD == IS_METHOD_TIS) x = np_minimum(x, cut);
+        tmax = fmax(tmax, (x - lse) + (-v));
+    }
+    double st = 0.0;
+    for (int s = 0; s < S; ++s) {
+        const double v = -ll(s);
+        double x = v - mx;
+        if (METHOD == IS_METHOD_TIS) x = np_minimum(x, cut);
+        st += exp(((x - lse) + (-v)) - tmax);
+    }
+    elpd = log(st) + tmax;
+    lppd = log(sl) + ((-mn) - log_S);
+}
+
+template <int METHOD>
+__global__ void __launch_bounds__(32 * WC_SEG) is_cols_kernel(const IsColsParams p) {
+    __shared__ double tabs[64];
+    __shared__ LseAcc part[2][WC_SEG][32];
+    __shared__ int infs[WC_SEG][32];
+    const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5, S = p.S;
+    if (threadIdx.x < 32) {
+        tabs[threadIdx.x] = exp2((double)threadIdx.x / 32.0);
+        tabs[32 + threadIdx.x] = exp2(-(double)threadIdx.x / 32.0);
+    }
+    __syncthreads();
+    ExpTab tb;
+    tb.t = tabs;
+    tb.tinv = tabs + 32;
+    const long long obs = (long long)blockIdx.x * 32 + lane;
+    const bool live = obs < p.N;
+    const double* col = p.ll + (live ? obs : 0);
+    const int per = (S + WC_SEG - 1) / WC_SEG;
+    const int s0 = min(S, seg * per), s1 = min(S, s0 + per);
+    const LseAcc zero = {-inf_f64(), 0.0, 0.0};
+    unsigned c_nan = 0, c_pinf = 0, c_ninf = 0;
+
+    // ---- sweep 1: logsumexp (+ squares) of -ll and logsumexp of ll
+    LseAcc av = zero, al = zero;
+    if (live) {
+        col_sweep(col, p.stride_s, s0, s1, [&](double (&w)[WC_CHUNK], int nb) {
+            double v[WC_CHUNK];
+#pragma unroll
+            for (int i = 0; i < WC_CHUNK; ++i) {
+                if (i < nb) {
+                    if (!is_finite(w[i])) {
+                        if (w[i] != w[i]) { w[i] = -1e10; ++c_nan; }  // pyloo/loo.py:227
+                        else if (w[i] > 0) ++c_pinf;
+                        else ++c_ninf;
+                    }
+                }
+                v[i] = -w[i];
+            }
+            lse_fold(av, v, nb, tb);
+            lse_fold(al, w, nb, tb);
+        });
+    }
+    part[0][seg][lane] = av;
+    part[1][seg][lane] = al;
+    infs[seg][lane] = (int)(c_pinf + c_ninf);
+    __syncthreads();
+    bool special = false;
+    double ess = 0.0, lppd = 0.0, lse = 0.0, cut = inf_f64(), mx = 0.0, mx2 = 0.0;
+    {
+        // every segment folds the 8 partials in the same order: identical values in all of them
+        LseAcc tv = part[0][0][lane], tl = part[1][0][lane];
+        int n_inf = infs[0][lane];
+        for (int g = 1; g < WC_SEG; ++g) {
+            lse_merge(tv, part[0][g][lane], tb);
+            lse_merge(tl, part[1][g][lane], tb);
+            n_inf += infs[g][lane];
+        }
+        special = n_inf > 0;
+        mx = tv.m;
+        lppd = log(tl.s) + (tl.m - p.log_S);
+        if (METHOD == IS_METHOD_SIS) {
+            lse = log(tv.s);
+            ess = (tv.s * tv.s) / tv.q;
+        } else {
+            cut = (log(tv.s) - p.log_S) + 0.5 * p.log_S;  // tis.py:112-114
+            mx2 = fmin(0.0, cut);
+        }
+    }
+    __syncthreads();
+
+    // ---- TIS sweep 2: sums over the truncated row
+    if (METHOD == IS_METHOD_TIS) {
+        double t1 = 0.0, t2 = 0.0;
+        if (live && !special) {
+            col_sweep(col, p.stride_s, s0, s1, [&](double (&w)[WC_CHUNK], int nb) {
+#pragma unroll
+                for (int i = 0; i < WC_CHUNK; ++i) {
+                    if (i < nb) {
+                        const double llv = (w[i] != w[i]) ? -1e10 : w[i];
+                        const double a = exp_sum(fmin(-llv - mx, cut) - mx2, tb);
+                        t1 += a;
+                        t2 += a * a;
+                    }
+                }
+            });
+        }
+        part[0][seg][lane].s = t1;
+        part[0][seg][lane].q = t2;
+        __syncthreads();
+        double a1 = part[0][0][lane].s, a2 = part[0][0][lane].q;
+        for (int g = 1; g < WC_SEG; ++g) {
+            a1 += part[0][g][lane].s;
+            a2 += part[0][g][lane].q;
+        }
+        lse = log(a1) + mx2;
+        ess = (a1 * a1) / a2;
+        __syncthreads();
+    }
+
+    // ---- last sweep: elpd_i = logsumexp(lw + ll)  (loo.py:289, :319-324)
+    LseAcc at = zero;
+    if (live && !special) {
+        col_sweep(col, p.stride_s, s0, s1, [&](double (&w)[WC_CHUNK], int nb) {
+            double t[WC_CHUNK];
+#pragma unroll
+            for (int i = 0; i < WC_CHUNK; ++i) {
+                const double llv = (w[i] != w[i]) ? -1e10 : w[i];
+                const double v = -llv;
+                double x = v - mx;
+                if (METHOD == IS_METHOD_TIS) x = fmin(x, cut);
+                t[i] = (x - lse) + (-v);
+            }
+            lse_fold(at, t, nb, tb);
+        });
+    }
+    part[0][seg][lane] = at;
+    __syncthreads();
+    if (seg == 0 && live) {
+        double elpd;
+        if (special) {
+            is_loo_serial<METHOD>(col, p.stride_s, S, p.log_S, elpd, ess, lppd);
+        } else {
+            LseAcc tt = part[0][0][lane];
+            for (int g = 1; g < WC_SEG; ++g) lse_merge(tt, part[0][g][lane], tb);
+            elpd = log(tt.s) + tt.m;
+        }
+        p.elpd[obs] = elpd;
+        p.ess[obs] = ess;
+        p.lppd[obs] = lppd;
+    }
+    if (p.counters) {
+        if (c_nan) atomicAdd(&p.counters[0], (unsigned long long)c_nan);
+        if (c_pinf) atomicAdd(&p.counters[1], (unsigned long long)c_pinf);
+        if (c_ninf) atomicAdd(&p.counters[2], (unsigned long long)c_ninf);
+    }
+}
+
 // ===================================================================================== host side
 static size_t is_smem_bytes(int S) { return sizeof(double) * (IS_RED_WORDS + (size_t)((S + 1) & ~1)); }
 constexpr size_t SMEM_LIMIT = 227 * 1024;
@@ -1203,6 +1463,14 @@ cudaError_t waic_cols_launch(const WaicColsParams& p, cudaStream_t st) {
     const long long blocks = (p.N + 31) / 32;
     if (blocks > 0x7fffffffll) return cudaErrorInvalidConfiguration;
     waic_cols_kernel<<<(unsigned)blocks, 32 * WC_SEG, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t is_cols_launch(int method, const IsColsParams& p, cudaStream_t st) {
+    const long long blocks = (p.N + 31) / 32;
+    if (blocks > 0x7fffffffll) return cudaErrorInvalidConfiguration;
+    if (method == IS_METHOD_SIS) is_cols_kernel<IS_METHOD_SIS><<<(unsigned)blocks, 32 * WC_SEG, 0, st>>>(p);
+    else is_cols_kernel<IS_METHOD_TIS><<<(unsigned)blocks, 32 * WC_SEG, 0, st>>>(p);
     return cudaGetLastError();
 }
 

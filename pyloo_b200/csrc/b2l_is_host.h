@@ -89,6 +89,19 @@ struct WaicColsParams {
 };
 cudaError_t waic_cols_launch(const WaicColsParams& p, cudaStream_t st);
 
+// loo(method = "sis" | "tis") pointwise pass straight on the observation-fastest (S, N) matrix: two (SIS) or
+// three (TIS) reads of the matrix, no transposed panels.  Same outputs as is_launch in IS_MODE_LOO.
+struct IsColsParams {
+    const double* ll;  // element (s, i) at ll[s * stride_s + i]
+    long long stride_s;
+    double *elpd, *ess, *lppd;     // N each
+    unsigned long long* counters;  // nullable: NaN / +inf / -inf inputs
+    long long N;
+    int S;
+    double log_S;
+};
+cudaError_t is_cols_launch(int method, const IsColsParams& p, cudaStream_t st);
+
 // Launch planners + launchers.  `*_info`: [0] staged in shared memory, [1] grid, [2] dynamic smem bytes,
 // [3] CTAs per SM.  The e_loo launcher needs `scratch` only when info[0] == 0.
 cudaError_t is_plan(int method, int mode, int S, long long n_rows, int* info);
