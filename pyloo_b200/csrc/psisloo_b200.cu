@@ -808,8 +808,8 @@ extern "C" int b2l_loo_is_dev_f64(const double* ll, int64_t S, int64_t N, int64_
         return 0;
     }
     if (stride_n != 1 && N != 1) return fail(B2L_E_INVALID, "one of (stride_s, stride_n) must be 1");
-    if (getenv("B2L_IS_COLS") && !getenv("B2L_FORCE_LEGACY")) {
-        // observation-fastest layout: column form, no transposed panels (opt-in until verified on the GPU)
+    if (!getenv("B2L_FORCE_LEGACY")) {
+        // observation-fastest layout: column form, no transposed panels
         IsColsParams cp;
         memset(&cp, 0, sizeof(cp));
         cp.ll = ll; cp.stride_s = stride_s; cp.N = N; cp.S = (int)S; cp.log_S = std::log((double)S);

@@ -125,16 +125,11 @@ def test_loo_method_api(method):
     assert list(dev.index[-4:]) == ["scale", "looic", "looic_se", "subsample_size"]
 
 
-@pytest.mark.skipif(__import__("os").environ.get("B2L_VERIFY_IS_COLS") != "1",
-                    reason="column-form SIS / TIS loo is opt-in (B2L_IS_COLS) until verified on the GPU")
 @pytest.mark.parametrize("method", ["sis", "tis"])
 @pytest.mark.parametrize("S,N", [(3, 5), (9, 33), (64, 31), (1001, 70), (4000, 130)])
 def test_loo_is_column_form_against_oracle(S, N, method):
     """(chain, draw, obs) layout: the column-form kernel (no transposed panels) against the oracle for ragged
     shapes, wide ratios, NaN and +-inf columns (redone serially with the row kernel's arithmetic)."""
-    import os
-
-    os.environ["B2L_IS_COLS"] = "1"
     rng = np.random.default_rng(S * 7 + N)
     ll = -1.0 + rng.normal(size=(S, N)) * rng.uniform(0.05, 4.0, size=N)
     ll[0, 0] = -60.0                                  # one dominant ratio
@@ -143,10 +138,7 @@ def test_loo_is_column_form_against_oracle(S, N, method):
         ll[2 % S, 2] = np.inf
         ll[0, 3] = -np.inf
         ll[:, 4] = -np.inf
-    try:
-        res = engine.loo_is_host(ll, method)
-    finally:
-        os.environ.pop("B2L_IS_COLS", None)
+    res = engine.loo_is_host(ll, method)
     with np.errstate(all="ignore"):
         ref = iso.loo_is_pointwise(ll, method)
     for key in ("elpd_i", "ess_i", "lppd_i"):
