@@ -422,6 +422,10 @@ def main():
             "e_loo_mean": timed(lambda: engine.eloo_cuda(hs, lw_tis, xs, "mean"), 24 * S + 16),
         }
         del hs, lw_tis
+        lls = torch.randn(S, n_nx, dtype=torch.float64, device=dev, generator=gen).sub_(1.4)   # (chain, draw, obs)
+        next_rows["loo_sis"] = timed(lambda: engine.loo_is_cuda(lls, "sis"), 8 * S + 24)
+        next_rows["loo_tis"] = timed(lambda: engine.loo_is_cuda(lls, "tis"), 8 * S + 24)
+        del lls
 
     # ---- end to end through the host-buffer C-ABI entry (pinned host memory both ways)
     e2e = None
