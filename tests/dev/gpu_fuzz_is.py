@@ -78,6 +78,13 @@ for case in range(n_cases):
             if kind != "ties" and not np.any(x == np.round(x)):   # ties in x: argsort order is unspecified
                 check(f"{tag} quantile", q, rq, 1e-8, 1e-9 * float(np.nanmax(np.abs(x))))
         ll_sn = np.ascontiguousarray(-lr.T)
+        for method in ("sis", "tis"):   # column-form kernel on the (S, N) layout, row kernel on its transpose
+            got = engine.loo_is_host(ll_sn, method)
+            rows = engine.loo_is_host(np.ascontiguousarray(ll_sn.T).T, method)
+            ref = iso.loo_is_pointwise(ll_sn, method)
+            for key in ("elpd_i", "ess_i", "lppd_i"):
+                check(f"{tag} loo_{method} cols {key}", got[key], ref[key], 1e-10, 1e-12)
+                check(f"{tag} loo_{method} rows {key}", rows[key], ref[key], 1e-10, 1e-12)
         if S >= 8:
             res = engine.loo_cuda(torch.from_numpy(ll_sn).cuda(), 1.0, waic_only=True)
             ww = orc.waic_pointwise(ll_sn)
