@@ -975,10 +975,10 @@ __global__ void __launch_bounds__(32 * WC_SEG) waic_cols_kernel(const WaicColsPa
         const double* col = p.ll + obs;
         // one chunk of nb <= 8 sanitised draws folded into the accumulators
         auto fold = [&](const double (&w)[WC_CHUNK], int nb) {
-            double cm = w[0];
+            double cm = w[0];  // compare-select: the draws are NaN-free after sanitise (an IEEE fmax costs twice as much)
 #pragma unroll
             for (int i = 1; i < WC_CHUNK; ++i)
-                if (i < nb) cm = fmax(cm, w[i]);
+                if (i < nb) cm = (w[i] > cm) ? w[i] : cm;
             if (cm > a.m) {  // new running maximum: rescale the sum (exp_sum(-inf) = 0 on the first chunk)
                 a.s *= exp_sum(a.m - cm, tb);
                 a.m = cm;
@@ -1022,10 +1022,10 @@ __global__ void __launch_bounds__(32 * WC_SEG) waic_cols_kernel(const WaicColsPa
         };
         int s = s0;
         double nx[WC_CHUNK];
-        const bool any_full = (s + WC_CHUNK <= s1);
-        if (any_full) {
+        const double* pn = col + (long long)s0 * p.stride_s;  // next draw to load (pointer stepping, no 64-bit multiplies)
+        if (s + WC_CHUNK <= s1) {
 #pragma unroll
-            for (int i = 0; i < WC_CHUNK; ++i) nx[i] = col[(long long)(s + i) * p.stride_s];
+            for (int i = 0; i < WC_CHUNK; ++i, pn += p.stride_s) nx[i] = *pn;
         }
         for (; s + WC_CHUNK <= s1; s += WC_CHUNK) {
             double w[WC_CHUNK];
@@ -1033,7 +1033,7 @@ __global__ void __launch_bounds__(32 * WC_SEG) waic_cols_kernel(const WaicColsPa
             for (int i = 0; i < WC_CHUNK; ++i) w[i] = nx[i];
             if (s + 2 * WC_CHUNK <= s1) {  // the next chunk's loads are in flight while this one is folded
 #pragma unroll
-                for (int i = 0; i < WC_CHUNK; ++i) nx[i] = col[(long long)(s + WC_CHUNK + i) * p.stride_s];
+                for (int i = 0; i < WC_CHUNK; ++i, pn += p.stride_s) nx[i] = *pn;
             }
             sanitise(w, WC_CHUNK);
             fold(w, WC_CHUNK);
@@ -1042,7 +1042,7 @@ __global__ void __launch_bounds__(32 * WC_SEG) waic_cols_kernel(const WaicColsPa
             const int nb = s1 - s;
             double w[WC_CHUNK];
 #pragma unroll
-            for (int i = 0; i < WC_CHUNK; ++i) w[i] = (i < nb) ? col[(long long)(s + i) * p.stride_s] : 0.0;
+            for (int i = 0; i < WC_CHUNK; ++i) w[i] = (i < nb) ? pn[(long long)i * p.stride_s] : 0.0;
             sanitise(w, nb);
             fold(w, nb);
         }
@@ -1100,9 +1100,10 @@ template <class F>
 __device__ __forceinline__ void col_sweep(const double* col, long long stride_s, int s0, int s1, F&& fold) {
     int s = s0;
     double nx[WC_CHUNK];
+    const double* pn = col + (long long)s0 * stride_s;
     if (s + WC_CHUNK <= s1) {
 #pragma unroll
-        for (int i = 0; i < WC_CHUNK; ++i) nx[i] = col[(long long)(s + i) * stride_s];
+        for (int i = 0; i < WC_CHUNK; ++i, pn += stride_s) nx[i] = *pn;
     }
     for (; s + WC_CHUNK <= s1; s += WC_CHUNK) {
         double w[WC_CHUNK];
@@ -1110,7 +1111,7 @@ __device__ __forceinline__ void col_sweep(const double* col, long long stride_s,
         for (int i = 0; i < WC_CHUNK; ++i) w[i] = nx[i];
         if (s + 2 * WC_CHUNK <= s1) {
 #pragma unroll
-            for (int i = 0; i < WC_CHUNK; ++i) nx[i] = col[(long long)(s + WC_CHUNK + i) * stride_s];
+            for (int i = 0; i < WC_CHUNK; ++i, pn += stride_s) nx[i] = *pn;
         }
         fold(w, WC_CHUNK);
     }
@@ -1118,7 +1119,7 @@ __device__ __forceinline__ void col_sweep(const double* col, long long stride_s,
         const int nb = s1 - s;
         double w[WC_CHUNK];
 #pragma unroll
-        for (int i = 0; i < WC_CHUNK; ++i) w[i] = (i < nb) ? col[(long long)(s + i) * stride_s] : 0.0;
+        for (int i = 0; i < WC_CHUNK; ++i) w[i] = (i < nb) ? pn[(long long)i * stride_s] : 0.0;
         fold(w, nb);
     }
 }
@@ -1130,7 +1131,7 @@ __device__ __forceinline__ void lse_fold(LseAcc& a, const double (&x)[WC_CHUNK],
     double cm = x[0];
 #pragma unroll
     for (int i = 1; i < WC_CHUNK; ++i)
-        if (i < nb) cm = fmax(cm, x[i]);
+        if (i < nb) cm = (x[i] > cm) ? x[i] : cm;  // NaN never wins: such columns are redone serially
     if (cm > a.m) {
         const double f = exp_sum(a.m - cm, tb);
         a.s *= f;
