@@ -15,7 +15,7 @@ import threading
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "lib", "libpsisloo_b200.so")
-SRCS = [os.path.join(_PKG, "csrc", n) for n in ("psisloo_b200.cu", "b2l_split_stream.cu", "b2l_split_tail.cu", "b2l_is.cu")]
+SRCS = [os.path.join(_PKG, "csrc", n) for n in ("psisloo_b200.cu", "b2l_split_stream.cu", "b2l_split_tail.cu", "b2l_is.cu", "b2l_tile.cu")]
 SRC = SRCS[0]
 HEADERS = [
     os.path.join(_PKG, "csrc", "b2l_common.cuh"),
@@ -23,6 +23,7 @@ HEADERS = [
     os.path.join(_PKG, "csrc", "b2l_split.cuh"),
     os.path.join(_PKG, "csrc", "b2l_split_host.h"),
     os.path.join(_PKG, "csrc", "b2l_is_host.h"),
+    os.path.join(_PKG, "csrc", "b2l_tile_host.h"),
     os.path.join(_ROOT, "include", "psisloo_b200.h"),
 ]
 

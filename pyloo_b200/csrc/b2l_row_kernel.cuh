@@ -52,6 +52,10 @@ struct RowParams {
     // non-null: process rows row_list[0 .. *n_list) instead of 0 .. n_rows (rows the split path handed over)
     const int* row_list;
     const int* n_list;
+    // element stride inside a row (0 or 1: contiguous).  Larger values serve the rows handed over by the tile
+    // path, which reads the observation-fastest (S, N) matrix where it lies: in_stride = 1, in_estride = stride_s,
+    // use_bulk = 0
+    long long in_estride;
 };
 
 struct RowSmemLayout {
@@ -519,7 +523,11 @@ __global__ void __launch_bounds__(NT, (NT == 128) ? 4 : ((NT == 256) ? 3 : 1)) p
             mbar_wait(&bars[bsel], parity);
         } else {
             const double* src = p.in + row * p.in_stride;
-            for (int s = tid; s < S; s += NT) rbuf[s] = src[s];
+            if (p.in_estride > 1) {
+                for (int s = tid; s < S; s += NT) rbuf[s] = src[(long long)s * p.in_estride];
+            } else {
+                for (int s = tid; s < S; s += NT) rbuf[s] = src[s];
+            }
             __syncthreads();
         }
 

@@ -29,7 +29,7 @@ namespace b2l {
 
 // why rows leave the split path (debug histogram, read by b2l_handover_reasons): one copy per kernel TU
 enum : int { HO_SPECIAL = 1, HO_RANGE = 2, HO_RETRY = 3, HO_RUNS = 4, HO_ORDER = 5, HO_GPD_TQ = 6, HO_GPD_FMX = 7,
-             HO_GPD_PROD = 8, HO_GPD_PROFILE = 9, HO_REASONS = 16 };
+             HO_GPD_PROD = 8, HO_GPD_PROFILE = 9, HO_CANCEL = 10, HO_REASONS = 16 };
 static __device__ unsigned long long g_handover[HO_REASONS];
 __device__ __forceinline__ void note_handover(int reason) { atomicAdd(&g_handover[reason], 1ull); }
 
@@ -48,7 +48,10 @@ struct __align__(16) SplitHeader {  // 80 B per observation: stream kernel -> ta
     int flags;      // != 0: the row was handed to the general kernel
     int attempts;
     int n_patch;    // tail kernel -> apply kernel: smoothed draws to patch in (0: none)
+    int C2;         // tile path: candidates of the looser second list, stored from the END of the row's scratch
+    int pad_;
 };
+static_assert(sizeof(SplitHeader) == 80, "SplitHeader is 80 bytes");
 
 struct SplitParams {
     const double* in;      // row i = in + i * in_stride (PSISLW: r = log weight; LOO: ll, r = -ll)
@@ -83,6 +86,11 @@ struct SplitParams {
     const unsigned short* a_cs;
     long long a_rows;
     int a_chunk;               // draws per apply transfer (S, or a fraction of it when shared memory is short)
+    // tile path (b2l_tile.cu): `body` holds the sum over ALL draws (the tail kernel subtracts the raw tail terms)
+    // and the candidates come as two lists: C tight ones from the front of the scratch row, C2 looser ones from
+    // its end (only read when the tight list is shorter than M + 1 or longer than one sort)
+    int total_body;
+    int ab_lists;
 };
 
 // (ExpTab, exp_poly5, scale2 and exp_tab_drop live in b2l_common.cuh: the importance-sampling kernels use them too)
@@ -597,7 +605,7 @@ __global__ void __launch_bounds__(stream_block(NT, MODE), stream_min_blocks<NT>(
             SplitHeader h;
             h.mx = mx; h.body = body; h.lsum = lsum; h.vsum = vsum;
             h.lshift = wide ? ll_max : ll_min; h.taux = taux_used;
-            h.lse = 0.0; h.C = C; h.flags = ok ? 0 : 1; h.attempts = attempts; h.n_patch = 0;
+            h.lse = 0.0; h.C = C; h.flags = ok ? 0 : 1; h.attempts = attempts; h.n_patch = 0; h.C2 = 0; h.pad_ = 0;
             p.hdr[row] = h;
             if (!ok) {
                 p.fb_list[atomicAdd(p.fb_count, 1)] = (int)(p.row_base + row);
@@ -770,8 +778,8 @@ __device__ __forceinline__ int gpdfit_warp(const double* t, int n, int m, double
     es = warp_sum(es);
     const double thr = 10.0 * 2.220446049250313e-16;
     double ws = 0.0;
-#pragma unroll
     const double inv_es = 1.0 / es;
+#pragma unroll
     for (int r = 0; r < 2; ++r) {
         w[r] = w[r] * inv_es;
         if (w[r] < thr) w[r] = 0.0;  // psis.py:194-197 (dead grid points already carry 0)
@@ -924,14 +932,18 @@ __device__ __forceinline__ unsigned quant_key(double x, double taux) {
 // further down can never be in the tail: their exp goes straight to the normaliser (returned).
 // Equal quantised values leave a short run in unspecified order; fix_runs() orders it exactly.
 template <int CAPL, int TL>
-__device__ __forceinline__ DD sort_and_stage(int C, double taux, const TailStage& st, const ExpTab& tab, int lane) {
+__device__ __forceinline__ DD sort_and_stage(int C, int CA, int cap, bool need_rest, double taux, const TailStage& st,
+                                             const ExpTab& tab, int lane) {
     constexpr int PB = (TL == 4) ? 8 : ((TL == 8) ? 9 : 10);  // bits of a candidate slot (cap = 64 TL)
     constexpr int QB = 32 - PB;
+    // candidate e of the (tight ++ loose) order -> slot of the row's scratch: the tight list grows from the
+    // front, the loose one (tile path) from the end; CA = C when there is one list only
+    auto slot_of = [&](int e) { return (e < CA) ? e : cap - 1 - (e - CA); };
     unsigned k[CAPL];
 #pragma unroll
     for (int i = 0; i < CAPL; ++i) {
         const int e = 32 * i + lane;
-        k[i] = (e < C) ? ((quant_key<QB>(st.gx[e], taux) << PB) | (unsigned)e) : 0xffffffffu;
+        k[i] = (e < C) ? ((quant_key<QB>(st.gx[slot_of(e)], taux) << PB) | (unsigned)e) : 0xffffffffu;
     }
     warp_bitonic_sort32<CAPL>(k, lane);
     // exact value and draw index of every element of the order: gathered by slot from the row's scratch
@@ -940,11 +952,11 @@ __device__ __forceinline__ DD sort_and_stage(int C, double taux, const TailStage
 #pragma unroll
     for (int i = 0; i < CAPL; ++i) {
         const int e = 32 * i + lane;
-        const unsigned pidx = k[i] & ((1u << PB) - 1u);
+        const int pidx = slot_of((int)(k[i] & ((1u << PB) - 1u)));
         if (i < TL) {
             st.xs[e] = (e < C) ? st.gx[pidx] : -inf_f64();
             st.ss[e] = (e < C) ? st.gs[pidx] : (unsigned short)0;
-        } else if (32 * i < C) {
+        } else if (need_rest && 32 * i < C) {
             if (e < C) {
                 const double x = st.gx[pidx];
                 if (x >= -700.0) dd_add(rest, exp_tab(x, tab));
@@ -1024,7 +1036,10 @@ __device__ __forceinline__ bool fix_runs(const TailStage& st, int C, int M, doub
 template <int TL, int MODE>
 __device__ __forceinline__ int tail_row(const SplitParams& p, long long row, const SplitHeader& h,
                                          const double* l1p, const TailStage& st, const ExpTab& tab, int lane) {
-    const int S = p.S, M = p.M, C = h.C;
+    const int S = p.S, M = p.M;
+    // tile path: the tight list alone when it holds the tail and fits one sort, else both lists
+    const bool tight_only = !p.ab_lists || (h.C >= M + 1 && h.C <= 32 * TL);
+    const int CA = h.C, C = tight_only ? h.C : h.C + h.C2;
     const double mx = h.mx;
     double* xs = st.xs;
     double* tb = st.tb;
@@ -1033,8 +1048,9 @@ __device__ __forceinline__ int tail_row(const SplitParams& p, long long row, con
     double* cx = st.gx;
     unsigned short* cs = st.gs;
     DD nont;  // double-double: order-independent sum
-    if (C <= 32 * TL) nont = sort_and_stage<TL, TL>(C, h.taux, st, tab, lane);
-    else nont = sort_and_stage<2 * TL, TL>(C, h.taux, st, tab, lane);
+    const bool total_body = p.total_body != 0;  // body = sum over all draws: nothing to add back for the non-tail candidates
+    if (C <= 32 * TL) nont = sort_and_stage<TL, TL>(C, CA, p.cap, !total_body, h.taux, st, tab, lane);
+    else nont = sort_and_stage<2 * TL, TL>(C, CA, p.cap, !total_body, h.taux, st, tab, lane);
     if (!fix_runs<TL>(st, C, M, h.taux, lane)) return HO_RUNS;
     // cutoff = (M+1)-th largest = element M of the order (psis.py:135-136); draws equal to it are
     // not in the tail (psis.py:139)
@@ -1064,7 +1080,8 @@ __device__ __forceinline__ int tail_row(const SplitParams& p, long long row, con
     if (!deep) {
         // staged candidates at or below the cutoff belong to the normaliser's body too
 #pragma unroll 1
-        for (int e = n + lane; e < min(C, 32 * TL); e += 32) dd_add(nont, exp_tab(xs[e], tab));
+        if (!total_body)
+            for (int e = n + lane; e < min(C, 32 * TL); e += 32) dd_add(nont, exp_tab(xs[e], tab));
         // t_i = exp(x_i) - exp(c) (psis.py:146-147), descending
 #pragma unroll 1
         for (int e = lane; e < n; e += 32) {
@@ -1075,7 +1092,7 @@ __device__ __forceinline__ int tail_row(const SplitParams& p, long long row, con
             traw += ex;
         }
     } else {
-        tail_t_literal(xs, tb, n, min(C, 32 * TL), exp_c, lane, nont, tsum, traw);
+        tail_t_literal(xs, tb, n, total_body ? n : min(C, 32 * TL), exp_c, lane, nont, tsum, traw);
     }
     tsum = warp_sum(tsum);
     traw = warp_sum(traw);
@@ -1126,7 +1143,11 @@ __device__ __forceinline__ int tail_row(const SplitParams& p, long long row, con
         tails = warp_sum(tsm);
         __syncwarp();
     }
-    const double body = h.body + nont_sum;
+    // tile path: h.body is the sum over all S draws, so the body is what remains without the raw tail terms;
+    // when the tail carries (almost) the whole sum the difference is rounding noise -- harmless as long as the
+    // smoothed tail is of the same order, else the row goes to the general kernel
+    const double body = total_body ? h.body - traw : h.body + nont_sum;
+    if (total_body && !(body + tails > 1e-6 * h.body)) return HO_CANCEL;
     const double lse = log_tab(body + tails, tab.t + 64);  // psis.py:158
 
     if (MODE == MODE_PSISLW) {

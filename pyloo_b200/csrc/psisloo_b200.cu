@@ -14,6 +14,7 @@
 #include "../../include/psisloo_b200.h"
 #include "b2l_row_kernel.cuh"
 #include "b2l_split_host.h"
+#include "b2l_tile_host.h"
 #include "b2l_is_host.h"
 
 using namespace b2l;
@@ -60,6 +61,8 @@ struct ProfScope {
     }
 };
 }  // namespace
+
+static bool aligned16_ptr(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 // ------------------------------------------------------------------------------------ planning
 constexpr int GROWS_MAX_CTAS = 192;  // global-memory row mode: at most this many resident rows
@@ -383,6 +386,73 @@ static int process_rows(int mode, const RowPlan& pl, const SplitPlan& sp, const 
     return launch_rows(mode, pl, rp, st);
 }
 
+// ------------------------------------------------------------------------------------ tile path
+// pl.loo on the observation-fastest (S, N) matrix without a transposed copy: per round of observations the
+// cluster kernel of b2l_tile.cu (one read of HBM through 2-D TMA boxes) and the split path's tail kernel, then
+// the general kernel on the observations those two hand over (strided reads of their columns).
+static bool tile_eligible(const double* ll, long long S, long long N, long long stride_s, int M) {
+    if (getenv("B2L_FORCE_LEGACY")) return false;
+    if (N < 1 || N > (1ll << 30) || stride_s < N) return false;
+    if (!aligned16_ptr(ll) || (stride_s % 2) != 0) return false;          // TMA: 16 B aligned base and row pitch
+    if ((unsigned long long)stride_s * 8ull >= (1ull << 40)) return false;  // TMA: pitch < 2^40 bytes
+    TilePlan tp;
+    return tile_shape(S, M, TILE_MAXC, &tp);
+}
+
+static int launch_tiles(const RowPlan& pl, const SplitPlan& sp, const TilePlan& tp, const double* ll, long long S,
+                        long long N, long long stride_s, const RowParams& rp, void* sws, cudaStream_t st) {
+    alignas(64) unsigned char tmap[128];
+    CK(tile_tensor_map(ll, S, N, stride_s, tp.box_rows, tmap));
+    char* w = (char*)sws;
+    SplitHeader* hdr = reinterpret_cast<SplitHeader*>(w);
+    w += align_up((size_t)sp.batch * sizeof(SplitHeader), 256);
+    double* cx = reinterpret_cast<double*>(w);
+    w += align_up((size_t)sp.batch * sp.cap * 8, 256);
+    unsigned short* cs = reinterpret_cast<unsigned short*>(w);
+    w = (char*)sws + 2 * split_slot_bytes(sp);
+    int* fb_list = reinterpret_cast<int*>(w);
+    w += align_up((size_t)std::max<long long>(N, 1) * 4, 256);
+    int* fb_count = reinterpret_cast<int*>(w);
+    int msq = (int)std::sqrt((double)rp.M);
+    while (msq * msq > rp.M) --msq;
+    while ((msq + 1) * (msq + 1) <= rp.M) ++msq;
+    CK(cudaMemsetAsync(fb_count, 0, sizeof(int), st));
+    // rounds of whole tiles; equal rounds, so that the last one is not a sliver
+    const long long per_max = std::max<long long>(TILE_W, sp.batch / TILE_W * TILE_W);
+    const long long n_rounds = std::max<long long>(1, (N + per_max - 1) / per_max);
+    const long long per_round = std::min<long long>(per_max, ((N + n_rounds - 1) / n_rounds + TILE_W - 1) / TILE_W * TILE_W);
+    for (long long i0 = 0; i0 < N; i0 += per_round) {
+        const long long nb = std::min<long long>(per_round, N - i0);
+        TileParams tq;
+        memset(&tq, 0, sizeof(tq));
+        tq.S = (int)S; tq.M = rp.M; tq.cap = sp.cap; tq.R = tp.R; tq.nbox = tp.nbox; tq.box_rows = tp.box_rows;
+        tq.q_t = tp.q_t; tq.q_l = tp.q_l; tq.n_tiles = (nb + TILE_W - 1) / TILE_W; tq.col0 = i0; tq.n_obs = nb;
+        tq.hdr = hdr; tq.cx = cx; tq.cs = cs; tq.fb_list = fb_list; tq.fb_count = fb_count;
+        tq.counters = rp.counters; tq.row_base = i0;
+        {
+            ProfScope prof(B2L_PROF_STREAM, st);
+            CK(tile_launch(tp, tmap, tq, st));
+        }
+        SplitParams q;
+        memset(&q, 0, sizeof(q));
+        q.k_out = rp.k_out + i0; q.elpd_i = rp.elpd_i + i0; q.lppd_i = rp.lppd_i + i0; q.var_i = rp.var_i + i0;
+        q.lppdw_i = rp.lppdw_i + i0; q.diag = rp.diag ? rp.diag + i0 * DIAG_STRIDE : nullptr;
+        q.n_rows = nb; q.S = (int)S; q.M = rp.M; q.cap = sp.cap; q.m_full = 30 + msq; q.cutoffmin = rp.cutoffmin;
+        q.counters = rp.counters; q.hdr = hdr; q.cx = cx; q.cs = cs; q.fb_list = fb_list; q.fb_count = fb_count;
+        q.row_base = i0; q.total_body = 1; q.ab_lists = 1;
+        const int g2 = (int)std::min<long long>(sp.grid2, (nb + TAIL_WARPS - 1) / TAIL_WARPS);
+        ProfScope prof(B2L_PROF_TAIL, st);
+        CK(split_tail_launch(sp.tl, MODE_LOO, g2, sp.smem2, st, q));
+    }
+    // observations handed over: the general kernel reads their columns where they lie
+    RowParams r = rp;
+    r.in = ll; r.in_stride = 1; r.in_estride = stride_s; r.use_bulk = 0; r.n_rows = N;
+    r.row_list = fb_list; r.n_list = fb_count;
+    RowPlan pf = pl;
+    pf.grid = std::min(pl.grid, pl.sms);
+    return launch_rows(MODE_LOO, pf, r, st);
+}
+
 // ------------------------------------------------------------------------------------ transpose
 // dst[c * dst_ld + r] = src[r * src_ld + c]   for r < rows, c < cols   (32 x 32 tiles, padded smem)
 __global__ void __launch_bounds__(256) transpose_f64_kernel(const double* __restrict__ src,
@@ -689,6 +759,19 @@ extern "C" int b2l_loo_dev_f64(const double* ll, int64_t S, int64_t N, int64_t s
     }
     const long long P = panel_obs(S, N);
     const size_t panel_bytes = align_up((size_t)P * (size_t)S * 8, 256);
+    if (!rp.waic_only && !gro && tile_eligible(ll, S, N, stride_s, M)) {
+        // the matrix is read where it lies (2-D TMA tiles, one pass over HBM): no panels
+        rc = plan_split(S, M, MODE_LOO, P, &sp);  // same scratch slots as the panel path sizes (b2l_workspace_bytes)
+        if (rc) return rc;
+        TilePlan tp;
+        CK(tile_plan(S, M, &tp));
+        const size_t need = sws_off + 2 * split_slot_bytes(sp) + align_up((size_t)N * 4, 256) + 256;
+        if (sp.ok && tp.ok && ws && ws_bytes >= need) {
+            rp.k_out = k_i; rp.elpd_i = elpd_i; rp.lppd_i = lppd_i; rp.var_i = var_i; rp.lppdw_i = lppdw_i;
+            rp.diag = diag;
+            return launch_tiles(pl, sp, tp, ll, S, N, stride_s, rp, (char*)ws + sws_off, st);
+        }
+    }
     rc = plan_split(S, M, MODE_LOO, P, &sp);
     if (rc) return rc;
     const size_t pan_off = sws_off + split_ws_bytes(sp, P);
@@ -956,11 +1039,12 @@ extern "C" int b2l_gather_rows_dev_f64(const double* ll, int64_t S, int64_t N, i
 
 extern "C" int b2l_handover_reasons(uint64_t* out16, int32_t reset) {
     if (!out16) return fail(B2L_E_INVALID, "null pointer");
-    unsigned long long a[HO_REASONS], b[HO_REASONS];
+    unsigned long long a[HO_REASONS], b[HO_REASONS], c[HO_REASONS];
     CK(cudaDeviceSynchronize());
     CK(split_stream_reasons(a, reset));
     CK(split_tail_reasons(b, reset));
-    for (int i = 0; i < HO_REASONS; ++i) out16[i] = a[i] + b[i];
+    CK(tile_reasons(c, reset));
+    for (int i = 0; i < HO_REASONS; ++i) out16[i] = a[i] + b[i] + c[i];
     return 0;
 }
 

@@ -193,7 +193,7 @@ def profile_read() -> dict:
 def handover_reasons(reset: bool = True) -> dict:
     """Diagnostics: observations handed from the split path to the general kernel, by reason."""
     names = {1: "nan_inf", 2: "range", 3: "threshold_retries", 4: "key_runs", 5: "order_check",
-             6: "gpd_quantile", 7: "gpd_factor_overflow", 8: "gpd_product", 9: "gpd_profile"}
+             6: "gpd_quantile", 7: "gpd_factor_overflow", 8: "gpd_product", 9: "gpd_profile", 10: "body_cancellation"}
     out = np.zeros(16, dtype=np.uint64)
     _native.check(_native.load().b2l_handover_reasons(out.ctypes.data, 1 if reset else 0))
     return {names[i]: int(out[i]) for i in names if out[i]}

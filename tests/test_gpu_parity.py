@@ -250,15 +250,22 @@ def test_waic_column_kernel_against_oracle(S, N):
 
 
 def test_layouts_agree_bitwise():
-    """Rows layout, obs-fastest layout (panel transpose) and odd-S / unaligned (non-TMA) path give
-    the same bits: an observation's result must not depend on the tile it lands in
-    (batch-invariance property, pyloo/tests/base_tests/test_loo_i.py:41-58)."""
+    """Rows layout, obs-fastest layout and odd-S / unaligned (non-TMA) path agree: an observation's result
+    must not depend on the tile it lands in (batch-invariance property,
+    pyloo/tests/base_tests/test_loo_i.py:41-58).  The obs-fastest layout runs the tile kernel (2-D TMA tiles
+    of the matrix where it lies): the tail index set and hence Pareto k are the same bits as the row path's,
+    the normalising sums are accumulated in another order (1e-12)."""
     rng = np.random.default_rng(13)
     ll_ns = np.ascontiguousarray(-1.4 + rng.normal(size=(1300, 2000)))      # rows contiguous
     a = gpu_loo(ll_ns.T, 1.0)                                               # stride_s == 1
     b = gpu_loo(np.ascontiguousarray(ll_ns.T), 1.0)                         # stride_n == 1
+    assert np.array_equal(a["pareto_k"], b["pareto_k"])
+    for key in ("elpd_i", "lppd_i", "var_i"):
+        close(a[key], b[key], rtol=1e-12)
+    # inside the tile path: a column's result does not depend on the tile / round / position it lands in
+    c = gpu_loo(np.ascontiguousarray(ll_ns[21:1300].T), 1.0)
     for key in ("elpd_i", "pareto_k", "lppd_i", "var_i"):
-        assert np.array_equal(a[key], b[key])
+        assert np.array_equal(b[key][21:], c[key])
     sub = gpu_loo(np.ascontiguousarray(ll_ns[37:38].T), 1.0)                # one observation alone
     for key in ("elpd_i", "pareto_k", "lppd_i", "var_i"):
         assert a[key][37] == sub[key][0]
