@@ -123,6 +123,21 @@ int b2l_loo_host_f64(const double* ll, int64_t S, int64_t N, int64_t stride_s, i
                      double* k_i, double* lppd_i, double* var_i, double* lppdw_i, double* stats_out,
                      int32_t device, int64_t chunk_obs);
 
+/* The same two calls over SEVERAL GPUs of one box from ONE process: the observation axis is cut into
+ * contiguous shards (whole 16-observation tiles), one host thread and one chunk pipeline per device run
+ * concurrently, and the shard records are merged in shard order (b2l_stats_merge).  This is the reference's
+ * per-observation independence (pyloo/utils.py:171-176) used across devices: no data-path exchange.
+ * `devices`: n_devices CUDA device indices.  Pointwise outputs are bit-identical to the one-device call.
+ * B2L_HOST_REGISTER=1 pins a pageable input (and psislw output) for the duration of the call.          */
+int b2l_loo_host_mgpu_f64(const double* ll, int64_t S, int64_t N, int64_t stride_s, int64_t stride_n,
+                          int32_t M, double cutoffmin, uint32_t flags, double good_k, double* elpd_i,
+                          double* k_i, double* lppd_i, double* var_i, double* lppdw_i, double* stats_out,
+                          const int32_t* devices, int32_t n_devices, int64_t chunk_obs);
+int b2l_psislw_host_mgpu_f64(const double* lw, int64_t S, int64_t N, int64_t stride_s, int64_t stride_n,
+                             int32_t M, double cutoffmin, double* lw_out, int64_t ostride_s,
+                             int64_t ostride_n, double* k_out, const int32_t* devices, int32_t n_devices,
+                             int64_t chunk_obs);
+
 /* ---------------------------------------------------------------------------------------------------
  * The callers either side of psislw ("next" rows 3 and 1).  Device pointers, asynchronous
  * on `stream`, rows of S doubles with element stride 1 unless stated otherwise.

@@ -37,39 +37,39 @@ namespace b2l {
 
 // ---------------------------------------------------------------- shared-memory carve-up
 struct XchA {  // exchange 1, one per (source CTA, column)
-    double mn;
-    float st, sl;
+    double mn;     // minimum of ll over the source CTA's draws
+    float st, sl;  // its tight / loose threshold statistic
 };
-struct RSum {  // exchange 2, one per (source CTA, owned column)
-    double q[4];  // sum exp(-u), sum exp(u), sum u, sum u^2
-    int umax;     // max over the high words of u (u >= 0: integer order = value order)
+struct RSum {  // exchange 2, one per (source CTA, owned column); double-buffered by tile parity
+    double q[4];  // about the SOURCE CTA's minimum c: sum exp(-(ll - c)), sum exp(ll - c), sum (ll - c), sum (ll - c)^2
+    double c;
+    int umax;     // max over the high words of ll - c (>= 0: integer order = value order)
     int pad;
 };
 struct ColInfo {
-    double llmin, tu_t, tu_l, pad;
+    double llmin, t_t, t_l;  // column minimum, tight / loose candidate threshold (ll <= t)
 };
+constexpr int TILE_RSUM = 16;  // csize * (16 / csize): the cluster size is a power of two
 struct TileSmemLayout {
-    size_t off_tab, off_scr, off_cnt, off_um, off_xch, off_xcnt, off_rsum, off_info, off_bar, total;
+    size_t off_tab, off_scr, off_um, off_xch, off_rsum, off_info, off_cl, off_bar, total;
 };
 __host__ __device__ inline TileSmemLayout tile_smem(int R) {
     TileSmemLayout L;
     size_t o = (size_t)R * TILE_W * 8;  // the tile: R draws x 16 observations, 128 B per draw
-    L.off_tab = o;   // 128 x (2^(j/128), 2^(-j/128))
-    o += 128 * 16;
+    L.off_tab = o;   // 64 x (2^(j/64), 2^(-j/64))
+    o += 64 * 16;
     L.off_scr = o;   // pass A: 32 x 16 float bin minima + 16 x 16 double thread minima; pass B: 8 x 16 x 4 partial sums
     o += 4096;
-    L.off_cnt = o;   // 16 x 16 packed candidate counts (tight | loose << 16), then their exclusive prefixes
-    o += 16 * TILE_W * 4;
     L.off_um = o;    // 8 x 16 high-word maxima
     o += 8 * TILE_W * 4;
-    L.off_xch = o;   // written by the other CTAs of the cluster
-    o += TILE_MAXC * TILE_W * sizeof(XchA);
-    L.off_xcnt = o;  // written by the other CTAs of the cluster
-    o += TILE_MAXC * TILE_W * 4;
-    L.off_rsum = o;  // written by the other CTAs of the cluster: [source CTA][owned slot], <= 24 entries
-    o += 24 * sizeof(RSum);
-    L.off_info = o;
-    o += TILE_W * sizeof(ColInfo);
+    L.off_xch = o;   // written by the other CTAs of the cluster: [parity][source CTA][column]
+    o += 2 * TILE_MAXC * TILE_W * sizeof(XchA);
+    L.off_rsum = o;  // written by the other CTAs of the cluster: [parity][source CTA][owned slot]
+    o += 2 * TILE_RSUM * sizeof(RSum);
+    L.off_info = o;  // [parity][column]
+    o += 2 * TILE_W * sizeof(ColInfo);
+    L.off_cl = o;    // this CTA's column minima
+    o += TILE_W * 8;
     L.off_bar = o;
     o += 64;
     L.total = align_up(o, 128);
@@ -87,8 +87,12 @@ __device__ __forceinline__ uint32_t cluster_nctarank() {
     asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
     return r;
 }
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+// split cluster barrier: what a CTA wrote to its peers' shared memory before arrive is visible to them after wait
+__device__ __forceinline__ void cluster_arrive() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait() {
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // address of the same shared-memory location in CTA `rank` of the cluster
 __device__ __forceinline__ uint32_t dsmem_addr(const void* local, uint32_t rank) {
@@ -110,28 +114,40 @@ __device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int c0, int c1
                  : "memory");
 }
 
-// exp(u) and exp(-u) from one range reduction, 0 <= u <= 600: u = n ln2/128 + r, |r| <= ln2/256,
-// e^(+-u) = 2^(+-(n >> 7)) 2^(+-(n & 127)/128) (cosh r +- sinh r) with cosh r ~ 1 + r^2/2, sinh r ~ r (1 + r^2/6):
-// relative error < 2.3e-12 (the dropped r^4/24 term) -- these feed normalising sums of S terms whose logarithm is
-// compared at 1e-10; the exact tail values are formed by the tail kernel from the exact x.
-constexpr double TE_L = 184.66496523378731;     // 128 / ln 2
-constexpr double TE_C = 0.0054152123481245727;  // ln 2 / 128
-__device__ __forceinline__ void exp_pm128(double u, const double2* tab, double& ep, double& em) {
+// exp(u) and exp(-u) from one range reduction, 0 <= u <= 600: u = n ln2/64 + r, |r| <= ln2/128,
+// e^(+-u) = 2^(+-(n >> 6)) 2^(+-(n & 63)/64) (cosh r +- sinh r), cosh r ~ 1 + r^2/2 + r^4/24, sinh r ~ r (1 + r^2/6):
+// relative error < 4e-14 (the dropped r^5/120 term).  These feed the normalising sums only; the exact tail values
+// are formed by the tail kernel from the exact x.
+constexpr double TE_L = 92.332482616893657;    // 64 / ln 2
+constexpr double TE_C = 0.010830424696249145;  // ln 2 / 64
+__device__ __forceinline__ void exp_pm64(double u, const double2* tab, double& ep, double& em) {
     const double t = fma(u, TE_L, EXP_MAGIC);
     const int ni = __double2loint(t);
     const double nf = t - EXP_MAGIC;
     const double r = fma(nf, -TE_C, u);
     const double r2 = r * r;
-    const double c = fma(r2, 0.5, 1.0);
+    const double c = fma(r2, fma(r2, 1.0 / 24.0, 0.5), 1.0);
     const double s1 = fma(r2, 1.0 / 6.0, 1.0);
-    const double2 T = tab[ni & 127];
-    const int sh = (ni << 13) & 0xfff00000;
+    const double2 T = tab[ni & 63];
+    const int sh = (ni << 14) & 0xfff00000;
     const double yp = T.x * fma(r, s1, c), ym = T.y * fma(-r, s1, c);
     ep = __hiloint2double(__double2hiint(yp) + sh, __double2loint(yp));
     em = __hiloint2double(__double2hiint(ym) - sh, __double2loint(ym));
 }
 
-constexpr int WIDE_HI = 0x4082c000;  // high word of 600.0
+// two independent ascending 32-lane bitonic sorts in one pass (the direction logic is shared)
+__device__ __forceinline__ void warp_sort32_f2(float& a, float& b, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const float oa = __shfl_xor_sync(FULL, a, j), ob = __shfl_xor_sync(FULL, b, j);
+            const bool keep_min = (((lane & k) == 0) == ((lane & j) == 0));
+            a = keep_min ? fminf(a, oa) : fmaxf(a, oa);
+            b = keep_min ? fminf(b, ob) : fmaxf(b, ob);
+        }
+    }
+}
 
 // ---------------------------------------------------------------- the kernel
 __global__ void __launch_bounds__(TILE_NT, 3) loo_tile_kernel(const __grid_constant__ CUtensorMap tmap,
@@ -140,19 +156,18 @@ __global__ void __launch_bounds__(TILE_NT, 3) loo_tile_kernel(const __grid_const
     const TileSmemLayout L = tile_smem(p.R);
     double* tile = reinterpret_cast<double*>(smem_raw);
     double2* etab = reinterpret_cast<double2*>(smem_raw + L.off_tab);
-    float* binsf = reinterpret_cast<float*>(smem_raw + L.off_scr);         // [32][16]
-    double* cmin = reinterpret_cast<double*>(smem_raw + L.off_scr + 2048);  // [16][16]
-    double* part = reinterpret_cast<double*>(smem_raw + L.off_scr);        // [8][16][4]
-    unsigned* cntT = reinterpret_cast<unsigned*>(smem_raw + L.off_cnt);    // [16][16]
-    int* umW = reinterpret_cast<int*>(smem_raw + L.off_um);                // [8][16]
-    XchA* xch = reinterpret_cast<XchA*>(smem_raw + L.off_xch);             // [csize][16]
-    unsigned* xcnt = reinterpret_cast<unsigned*>(smem_raw + L.off_xcnt);   // [csize][16]
-    RSum* rsum = reinterpret_cast<RSum*>(smem_raw + L.off_rsum);           // [csize][nslot]
-    ColInfo* info = reinterpret_cast<ColInfo*>(smem_raw + L.off_info);
+    float* binsf = reinterpret_cast<float*>(smem_raw + L.off_scr);          // [32][16]
+    double* cmin = reinterpret_cast<double*>(smem_raw + L.off_scr + 2048);   // [16][16]
+    double* part = reinterpret_cast<double*>(smem_raw + L.off_scr);         // [8][16][4]
+    int* umW = reinterpret_cast<int*>(smem_raw + L.off_um);                 // [8][16]
+    XchA* xch = reinterpret_cast<XchA*>(smem_raw + L.off_xch);              // [2][csize][16]
+    RSum* rsum = reinterpret_cast<RSum*>(smem_raw + L.off_rsum);            // [2][csize * nslot]
+    ColInfo* info = reinterpret_cast<ColInfo*>(smem_raw + L.off_info);      // [2][16]
+    double* clocal = reinterpret_cast<double*>(smem_raw + L.off_cl);        // [16]
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.off_bar);
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int col = lane & 15, rw = 2 * w + (lane >> 4);  // observation of the tile, draw slot 0..15
+    const int col = lane & 15, hf = lane >> 4, rw = 2 * w + hf;  // observation of the tile, draw slot 0..15
     const int crank = (int)cluster_ctarank(), csize = (int)cluster_nctarank();
     const int nslot = (TILE_W + csize - 1) / csize;  // columns a CTA owns: col = slot * csize + rank
     const long long cluster_id = blockIdx.x / csize, n_clusters = gridDim.x / csize;
@@ -168,9 +183,10 @@ __global__ void __launch_bounds__(TILE_NT, 3) loo_tile_kernel(const __grid_const
         mbar_init(bar, 1);
         fence_mbar_init();
     }
-    if (tid < 128) etab[tid] = make_double2(exp2((double)tid / 128.0), exp2(-(double)tid / 128.0));
+    if (tid < 64) etab[tid] = make_double2(exp2((double)tid / 64.0), exp2(-(double)tid / 64.0));
     __syncthreads();
-    cluster_sync_all();  // every CTA of the cluster is running: its shared memory may be written remotely
+    cluster_arrive();  // every CTA of the cluster is running: its shared memory may be written remotely
+    cluster_wait();
 
     auto issue = [&](long long t) {  // one thread: the CTA's R draws of tile t, nbox boxes on one mbarrier
         mbar_expect_tx(bar, tile_tx);
@@ -178,12 +194,72 @@ __global__ void __launch_bounds__(TILE_NT, 3) loo_tile_kernel(const __grid_const
             tma_load_2d(tile + (size_t)b * p.box_rows * TILE_W, &tmap, (int)(p.col0 + t * TILE_W),
                         row0 + b * p.box_rows, bar);
     };
+    // The header of a tile (what the tail kernel reads) is written by the owner CTA of each column one tile
+    // LATER, after the next cluster barrier: by then every CTA's partial sums and candidate counts are in.
+    auto write_headers = [&](long long tt, int par) {  // warp 7: lane = 8 * slot' + source rank
+        const int slot = lane >> 3, r = lane & 7;
+        for (int s0 = 0; s0 < nslot; s0 += 4) {
+            const int sl_ = s0 + slot;
+            const int c = sl_ * csize + crank;
+            const long long oo = tt * TILE_W + c;
+            const bool live_col = sl_ < nslot && c < TILE_W && oo < p.n_obs;
+            const bool have = live_col && r < csize;
+            const ColInfo ci = info[par * TILE_W + (live_col ? c : 0)];
+            double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0, um = 0.0;
+            if (have) {
+                const RSum e = rsum[par * TILE_RSUM + r * nslot + sl_];
+                const double n_r = (double)max(0, min(R, S - r * R));
+                if (n_r > 0.0) {
+                    const double d = e.c - ci.llmin;  // >= 0: this CTA's sums are about its own minimum
+                    q0 = e.q[0] * exp(-d);
+                    q1 = e.q[1] * exp(d);
+                    q2 = fma(n_r, d, e.q[2]);
+                    q3 = fma(d, fma(n_r, d, 2.0 * e.q[2]), e.q[3]);
+                    um = __hiloint2double(e.umax, 0) * 1.000002 + d;  // upper bound of max (ll - min ll)
+                }
+            }
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {  // over the 8 source CTAs, fixed order
+                q0 += __shfl_xor_sync(FULL, q0, o);
+                q1 += __shfl_xor_sync(FULL, q1, o);
+                q2 += __shfl_xor_sync(FULL, q2, o);
+                q3 += __shfl_xor_sync(FULL, q3, o);
+                um = fmax(um, __shfl_xor_sync(FULL, um, o));
+            }
+            if (live_col && r == 0) {
+                const int ca = (int)atomicAdd(&p.cnt[2 * oo], 0u), cb = (int)atomicAdd(&p.cnt[2 * oo + 1], 0u);
+                const bool special = !(is_finite(q2) && is_finite(q3) && is_finite(q0) && is_finite(q1));
+                const bool wide = !(um <= 600.0);
+                const bool count_bad = (ca + cb < M + 1) || (ca + cb > cap);
+                const bool ok = !special && !wide && !count_bad;
+                SplitHeader h;
+                h.mx = -ci.llmin;
+                h.body = q0;
+                h.lsum = q1;
+                h.vsum = q3 - q2 * q2 / (double)S;  // sum (ll - mean)^2 taken about the minimum
+                if (h.vsum < 0.0) h.vsum = 0.0;
+                h.lshift = ci.llmin;
+                h.taux = ci.llmin - ci.t_l;  // every candidate has ll <= t_l, i.e. x = fl(min ll - ll) >= taux
+                h.lse = 0.0;
+                h.C = ca; h.flags = ok ? 0 : 1; h.attempts = 0; h.n_patch = 0; h.C2 = cb; h.pad_ = 0;
+                p.hdr[oo] = h;
+                if (!ok) {
+                    p.fb_list[atomicAdd(p.fb_count, 1)] = (int)(p.row_base + oo);
+                    if (p.counters) atomicAdd(&p.counters[3], 1ull);
+                    note_handover(special ? HO_SPECIAL : (wide ? HO_RANGE : HO_RETRY));
+                }
+            }
+        }
+    };
+
     long long t = cluster_id;
     if (tid == 0 && t < p.n_tiles) issue(t);
     uint32_t phase = 0;
     const double* pcol = tile + rw * TILE_W + col;  // this thread's draws: pcol[k * 256]
+    long long t_prev = -1;
+    int par = 0;
 
-    for (; t < p.n_tiles; t += n_clusters) {
+    for (; t < p.n_tiles; t += n_clusters, par ^= 1) {
         // the next tile of this CTA: HBM -> L2 while this one is worked on
         if (tid == 0 && t + n_clusters < p.n_tiles)
             for (int b = 0; b < p.nbox; ++b)
@@ -208,191 +284,168 @@ __global__ void __launch_bounds__(TILE_NT, 3) loo_tile_kernel(const __grid_const
             cmin[rw * TILE_W + col] = min_sel(mA, mB);
         }
         __syncthreads();
-        // per column: CTA minimum, q_t-th and q_l-th smallest bin minimum -> every CTA of the cluster
-#pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
-            const int c = 2 * w + cc;
-            const float sorted = warp_sort32_f(binsf[lane * TILE_W + c], lane);
-            const float st = __shfl_sync(FULL, sorted, p.q_t - 1), sl = __shfl_sync(FULL, sorted, p.q_l - 1);
-            double mn = cmin[(lane & 15) * TILE_W + c];
+        // per column: this CTA's minimum and the q_t-th / q_l-th smallest of its 32 bin minima -> every CTA
+        {
+            const int c0 = 2 * w;
+            float a = binsf[lane * TILE_W + c0], b = binsf[lane * TILE_W + c0 + 1];
+            warp_sort32_f2(a, b, lane);
+            const float st0 = __shfl_sync(FULL, a, p.q_t - 1), sl0 = __shfl_sync(FULL, a, p.q_l - 1);
+            const float st1 = __shfl_sync(FULL, b, p.q_t - 1), sl1 = __shfl_sync(FULL, b, p.q_l - 1);
+            double mn = cmin[col * TILE_W + c0 + hf];  // lanes 0..15: column c0, lanes 16..31: column c0 + 1
 #pragma unroll
             for (int o = 8; o > 0; o >>= 1) mn = min_sel(mn, __shfl_xor_sync(FULL, mn, o));
-            if (lane < csize) {
-                const uint32_t a = dsmem_addr(&xch[crank * TILE_W + c], (uint32_t)lane);
-                dsmem_st_f64(a, mn);
-                dsmem_st_v2f32(a + 8, st, sl);
+            if (col == 0) clocal[c0 + hf] = mn;
+            if (col < csize) {
+                const uint32_t ad = dsmem_addr(&xch[(par * TILE_MAXC + crank) * TILE_W + c0 + hf], (uint32_t)col);
+                dsmem_st_f64(ad, mn);
+                dsmem_st_v2f32(ad + 8, hf ? st1 : st0, hf ? sl1 : sl0);
             }
         }
-        cluster_sync_all();  // exchange 1
-        if (tid < TILE_W) {
-            double mn = INF;
-            for (int r = 0; r < csize; ++r) mn = min_sel(mn, xch[r * TILE_W + tid].mn);
-            // lower / upper median of the CTAs' thresholds (ranked with the CTA index as tie-break)
-            const int want_t = (csize - 1) / 2, want_l = csize / 2;
-            float st = 0.f, sl = 0.f;
-            for (int r = 0; r < csize; ++r) {
-                const float vt = xch[r * TILE_W + tid].st, vl = xch[r * TILE_W + tid].sl;
-                int rt = 0, rl = 0;
-                for (int q = 0; q < csize; ++q) {
-                    const float ot = xch[q * TILE_W + tid].st, ol = xch[q * TILE_W + tid].sl;
-                    rt += (ot < vt || (ot == vt && q < r)) ? 1 : 0;
-                    rl += (ol < vl || (ol == vl && q < r)) ? 1 : 0;
-                }
-                if (rt == want_t) st = vt;
-                if (rl == want_l) sl = vl;
-            }
-            ColInfo ci;
-            ci.llmin = mn;
-            ci.tu_t = (double)st - mn;
-            ci.tu_l = (double)sl - mn;
-            ci.pad = 0.0;
-            info[tid] = ci;
-        }
+        cluster_arrive();  // exchange 1 is on its way; its wait sits behind pass B
         __syncthreads();
 
-        // ---------------- pass B: sums over all draws, marks of the draws at or below the loose threshold
-        const double llmin = info[col].llmin, tu_t = info[col].tu_t, tu_l = info[col].tu_l;
-        double bs = 0.0, ls = 0.0, su = 0.0, suu = 0.0;
-        unsigned mask = 0;
-        int umax = 0;
-        auto fold = [&](double v, unsigned bit, unsigned& msk) {
-            const double u = v - llmin;  // = -x with x = fl(r - max r) (psis.py:134): exact, >= 0
-            double ep, em;
-            exp_pm128(u, etab, ep, em);
-            msk |= (u <= tu_l) ? bit : 0u;
-            bs += em;  // exp(x)
-            ls += ep;  // exp(ll - min ll)
-            su += u;
-            suu = fma(u, u, suu);
-            umax = max(umax, __double2hiint(u));
-        };
+        // ---------------- pass B: sums over all draws about this CTA's column minimum (no peer data needed)
         {
+            const double cl = clocal[col];
+            double bs = 0.0, ls = 0.0, su = 0.0, suu = 0.0;
+            int umax = 0;
+            auto fold = [&](double v) {
+                const double u = v - cl;  // >= 0
+                double ep, em;
+                exp_pm64(u, etab, ep, em);
+                bs += em;  // exp(-(ll - c))
+                ls += ep;  // exp(ll - c)
+                su += u;
+                suu = fma(u, u, suu);
+                umax = max(umax, __double2hiint(u));
+            };
             int k = 0;
-            for (; k + 4 <= kmin; k += 4) {
-                unsigned nib = 0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) fold(pcol[(k + j) * 256], 1u << j, nib);
-                mask |= nib << k;
+#pragma unroll 4
+            for (; k < kmin; ++k) fold(pcol[k * 256]);
+            if (extra) fold(pcol[kmin * 256]);
+            // the two draw slots of a warp that share a column, then the 8 warps through shared memory
+            bs += __shfl_xor_sync(FULL, bs, 16);
+            ls += __shfl_xor_sync(FULL, ls, 16);
+            su += __shfl_xor_sync(FULL, su, 16);
+            suu += __shfl_xor_sync(FULL, suu, 16);
+            umax = max(umax, __shfl_xor_sync(FULL, umax, 16));
+            if (lane < 16) {
+                double* d = part + (w * TILE_W + col) * 4;
+                d[0] = bs; d[1] = ls; d[2] = su; d[3] = suu;
+                umW[w * TILE_W + col] = umax;
             }
-            for (; k < kmin; ++k) fold(pcol[k * 256], 1u << k, mask);
-            if (extra) fold(pcol[kmin * 256], 1u << kmin, mask);
         }
-        // tight candidates among the marked draws; counts of both kinds
-        unsigned maskA = 0;
-        for (unsigned m = mask; m; m &= m - 1) {
-            const int b = __ffs((int)m) - 1;
-            if (pcol[b * 256] - llmin <= tu_t) maskA |= 1u << b;
+        cluster_wait();  // exchange 1 has arrived from every CTA
+        // per column: the global minimum and the lower / upper median of the CTAs' thresholds
+        {
+            const int c = 2 * w + hf;
+            const int r = col & 7;  // lanes 8..15 of each half mirror lanes 0..7
+            const bool have = r < csize;
+            const XchA e = xch[(par * TILE_MAXC + (have ? r : 0)) * TILE_W + c];
+            double mn = have ? e.mn : INF;
+            const float st = have ? e.st : __int_as_float(0x7f800000), sl = have ? e.sl : __int_as_float(0x7f800000);
+            int rt = 0, rl = 0;
+#pragma unroll
+            for (int q = 0; q < TILE_MAXC; ++q) {
+                const float ot = __shfl_sync(FULL, st, (lane & 16) + q), ol = __shfl_sync(FULL, sl, (lane & 16) + q);
+                rt += (ot < st || (ot == st && q < r)) ? 1 : 0;
+                rl += (ol < sl || (ol == sl && q < r)) ? 1 : 0;
+            }
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) mn = min_sel(mn, __shfl_xor_sync(FULL, mn, o));
+            // (ranks count the padding lanes' +inf as larger: positions 0 .. csize - 1 belong to the real CTAs)
+            const unsigned bt = __ballot_sync(FULL, have && col < 8 && rt == (csize - 1) / 2);
+            const unsigned bl = __ballot_sync(FULL, have && col < 8 && rl == csize / 2);
+            const unsigned mine = hf ? 0xffff0000u : 0x0000ffffu;
+            const float tt_ = __shfl_sync(FULL, st, __ffs(bt & mine) - 1), tl_ = __shfl_sync(FULL, sl, __ffs(bl & mine) - 1);
+            if (col == 0) {
+                ColInfo ci;
+                ci.llmin = mn; ci.t_t = (double)tt_; ci.t_l = (double)tl_;
+                info[par * TILE_W + c] = ci;
+            }
         }
-        const unsigned nA = (unsigned)__popc(maskA), nB = (unsigned)__popc(mask) - nA;
-        // the two draw slots of a warp that share a column, then the 8 warps through shared memory
-        bs += __shfl_xor_sync(FULL, bs, 16);
-        ls += __shfl_xor_sync(FULL, ls, 16);
-        su += __shfl_xor_sync(FULL, su, 16);
-        suu += __shfl_xor_sync(FULL, suu, 16);
-        umax = max(umax, __shfl_xor_sync(FULL, umax, 16));
-        if (lane < 16) {
-            double* d = part + (w * TILE_W + col) * 4;
-            d[0] = bs; d[1] = ls; d[2] = su; d[3] = suu;
-            umW[w * TILE_W + col] = umax;
-        }
-        cntT[rw * TILE_W + col] = nA | (nB << 16);
         __syncthreads();
-        if (tid < 64) {  // CTA partial of one (column, quantity) -> the column's owner
+        // this CTA's partial sums -> the column's owner (for the header written one tile later)
+        if (tid < 64) {
             const int c = tid & 15, q = tid >> 4;
             double a = 0.0;
 #pragma unroll
             for (int ww = 0; ww < 8; ++ww) a += part[(ww * TILE_W + c) * 4 + q];
-            dsmem_st_f64(dsmem_addr(&rsum[crank * nslot + c / csize].q[q], (uint32_t)(c % csize)), a);
+            dsmem_st_f64(dsmem_addr(&rsum[par * TILE_RSUM + crank * nslot + c / csize].q[q], (uint32_t)(c % csize)), a);
         } else if (tid < 80) {
             const int c = tid - 64;
             int a = 0;
 #pragma unroll
             for (int ww = 0; ww < 8; ++ww) a = max(a, umW[ww * TILE_W + c]);
-            dsmem_st_u32(dsmem_addr(&rsum[crank * nslot + c / csize].umax, (uint32_t)(c % csize)), (uint32_t)a);
-        } else if (tid >= 96 && tid < 112) {  // exclusive prefix of the packed counts over the 16 draw slots
-            const int c = tid - 96;
-            unsigned run = 0;
-            for (int s = 0; s < 16; ++s) {
-                const unsigned v = cntT[s * TILE_W + c];
-                cntT[s * TILE_W + c] = run;
-                run += v;
-            }
-            for (int r = 0; r < csize; ++r) dsmem_st_u32(dsmem_addr(&xcnt[crank * TILE_W + c], (uint32_t)r), run);
+            RSum* dst = &rsum[par * TILE_RSUM + crank * nslot + c / csize];
+            dsmem_st_u32(dsmem_addr(&dst->umax, (uint32_t)(c % csize)), (uint32_t)a);
+            dsmem_st_f64(dsmem_addr(&dst->c, (uint32_t)(c % csize)), clocal[c]);
         }
-        cluster_sync_all();  // exchange 2
+        // the previous tile's headers: everything they need arrived before this tile's barrier
+        if (w == 7 && t_prev >= 0) write_headers(t_prev, par ^ 1);
 
-        // ---------------- emit: fixed order (CTA rank, draw slot, draw)
+        // ---------------- pass C: candidates = draws at or below the loose threshold; tight ones separately
         {
-            unsigned before = 0, total = 0;
-            for (int r = 0; r < csize; ++r) {
-                const unsigned v = xcnt[r * TILE_W + col];
-                total += v;
-                before += (r < crank) ? v : 0u;
+            const ColInfo ci = info[par * TILE_W + col];
+            unsigned mask = 0;
+            int k = 0;
+            for (; k + 4 <= kmin; k += 4) {
+                unsigned nib = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) nib |= (pcol[(k + j) * 256] <= ci.t_l) ? (1u << j) : 0u;
+                mask |= nib << k;
             }
-            const int CA = (int)(total & 0xffffu), CB = (int)(total >> 16);
-            const long long o = t * TILE_W + col;  // observation of the round
-            if (mask && CA + CB <= cap && o < p.n_obs) {
-                const unsigned pre = cntT[rw * TILE_W + col];
-                int posA = (int)((before & 0xffffu) + (pre & 0xffffu));
-                int posB = (int)((before >> 16) + (pre >> 16));
+            for (; k < kmin; ++k) mask |= (pcol[k * 256] <= ci.t_l) ? (1u << k) : 0u;
+            if (extra) mask |= (pcol[kmin * 256] <= ci.t_l) ? (1u << kmin) : 0u;
+            unsigned maskA = 0;
+            for (unsigned m = mask; m; m &= m - 1) {
+                const int b = __ffs((int)m) - 1;
+                if (pcol[b * 256] <= ci.t_t) maskA |= 1u << b;
+            }
+            // positions: one atomic per (warp, column, list) on the observation's global counters
+            const long long o = t * TILE_W + col;
+            const unsigned nA = (unsigned)__popc(maskA), nB = (unsigned)__popc(mask) - nA;
+            const unsigned nA2 = __shfl_down_sync(FULL, nA, 16), nB2 = __shfl_down_sync(FULL, nB, 16);
+            unsigned baseA = 0, baseB = 0;
+            if (lane < 16 && o < p.n_obs) {
+                if (nA + nA2) baseA = atomicAdd(&p.cnt[2 * o], nA + nA2);
+                if (nB + nB2) baseB = atomicAdd(&p.cnt[2 * o + 1], nB + nB2);
+            }
+            const unsigned bA = __shfl_sync(FULL, baseA, col), bB = __shfl_sync(FULL, baseB, col);
+            const unsigned nA1 = __shfl_sync(FULL, nA, col), nB1 = __shfl_sync(FULL, nB, col);
+            unsigned posA = bA + (hf ? nA1 : 0u), posB = bB + (hf ? nB1 : 0u);
+            if (mask && o < p.n_obs) {
                 double* dx = p.cx + (size_t)o * (size_t)cap;
                 unsigned short* ds = p.cs + (size_t)o * (size_t)cap;
                 for (unsigned m = mask; m; m &= m - 1) {
                     const int b = __ffs((int)m) - 1;
-                    const int slot = ((maskA >> b) & 1u) ? posA++ : cap - 1 - posB++;
-                    dx[slot] = llmin - pcol[b * 256];  // x = fl(r - max r), exactly
-                    ds[slot] = (unsigned short)(row0 + 16 * b + rw);
-                }
-            }
-            if (tid < nslot) {  // owner of column tid * csize + crank: the header the tail kernel reads
-                const int c = tid * csize + crank;
-                const long long oo = t * TILE_W + c;
-                if (c < TILE_W && oo < p.n_obs) {
-                    double q[4] = {0.0, 0.0, 0.0, 0.0};
-                    int um = 0;
-                    unsigned tot = 0;
-                    for (int r = 0; r < csize; ++r) {
-                        const RSum& e = rsum[r * nslot + tid];
-                        q[0] += e.q[0]; q[1] += e.q[1]; q[2] += e.q[2]; q[3] += e.q[3];
-                        um = max(um, e.umax);
-                        tot += xcnt[r * TILE_W + c];
-                    }
-                    const int ca = (int)(tot & 0xffffu), cb = (int)(tot >> 16);
-                    const bool special = !(is_finite(q[2]) && is_finite(q[3]) && is_finite(q[0]) && is_finite(q[1]));
-                    const bool wide = um > WIDE_HI;
-                    const bool count_bad = (ca + cb < M + 1) || (ca + cb > cap);
-                    const bool ok = !special && !wide && !count_bad;
-                    SplitHeader h;
-                    h.mx = -info[c].llmin;
-                    h.body = q[0];
-                    h.lsum = q[1];
-                    h.vsum = q[3] - q[2] * q[2] / (double)S;  // sum (ll - mean)^2 about the minimum: >= 0 up to rounding
-                    h.lshift = info[c].llmin;
-                    h.taux = -info[c].tu_l;
-                    h.lse = 0.0;
-                    h.C = ca; h.flags = ok ? 0 : 1; h.attempts = 0; h.n_patch = 0; h.C2 = cb; h.pad_ = 0;
-                    if (h.vsum < 0.0) h.vsum = 0.0;
-                    p.hdr[oo] = h;
-                    if (!ok) {
-                        p.fb_list[atomicAdd(p.fb_count, 1)] = (int)(p.row_base + oo);
-                        if (p.counters) atomicAdd(&p.counters[3], 1ull);
-                        note_handover(special ? HO_SPECIAL : (wide ? HO_RANGE : HO_RETRY));
+                    const bool isA = (maskA >> b) & 1u;
+                    const unsigned pos = isA ? posA++ : posB++;
+                    if (pos < (unsigned)cap) {  // (an overflowing column is flagged by its owner and never read)
+                        const unsigned slot = isA ? pos : (unsigned)cap - 1u - pos;
+                        dx[slot] = ci.llmin - pcol[b * 256];  // x = fl(r - max r), exactly (psis.py:134)
+                        ds[slot] = (unsigned short)(row0 + 16 * b + rw);
                     }
                 }
             }
         }
+        t_prev = t;
         __syncthreads();  // the tile has been read for the last time
         if (tid == 0 && t + n_clusters < p.n_tiles) {
             fence_proxy_async();
             issue(t + n_clusters);
         }
     }
+    // the last tile's headers
+    cluster_arrive();
+    cluster_wait();
+    if (w == 7 && t_prev >= 0) write_headers(t_prev, par ^ 1);
 }
 
 // ---------------------------------------------------------------- host side
 bool tile_shape(long long S, int M, int csize, TilePlan* tp) {
     memset(tp, 0, sizeof(*tp));
-    if (csize < 1 || csize > TILE_MAXC) return false;
+    if (csize < 1 || csize > TILE_MAXC || (csize & (csize - 1)) != 0) return false;
     if (S < 1024 || S > SPLIT_MAX_S) return false;
     const long long per = (S + csize - 1) / csize;
     if (per > TILE_MAX_R) return false;
@@ -400,16 +453,24 @@ bool tile_shape(long long S, int M, int csize, TilePlan* tp) {
     const int box_rows = (int)((per + nbox - 1) / nbox);
     tp->csize = csize; tp->nbox = nbox; tp->box_rows = box_rows; tp->R = nbox * box_rows;
     if (tp->R > TILE_MAX_R) return false;
-    // threshold ranks: 32 bins of R / 32 draws per CTA and column, i.e. 32 * csize bins per column (the split
-    // path's balls-in-bins estimate, b2l_split.cuh); the loose rank sits three bins further down
-    const double ratio = (double)(M + 1) / (32.0 * csize);
-    if (ratio > 0.95) return false;
-    int q = (int)std::lround(32.0 * (1.0 - std::exp(-1.25 * ratio))) + ((ratio > 0.45 && ratio <= 0.6) ? 1 : 0);
-    if (const char* ev = getenv("B2L_TILE_QT")) q = atoi(ev);
-    tp->q_t = std::min(29, std::max(1, q));
-    int ql = tp->q_t + 3;
+    // threshold ranks: 32 bins of R / 32 draws per CTA and column, i.e. B = 32 * csize bins per column.  The draws
+    // at or below the q-th smallest bin minimum of a CTA (lower / upper median over the CTAs) number about
+    // K(q) = -0.9 B ln(1 - q / 32) with a spread of ~8 % (balls in bins; the 0.9 is measured).  Tight rank: K in
+    // the middle of [M + 1, one sort of the tail kernel]; loose rank: K ~ 1.65 (M + 1), far from M + 1 and from cap.
+    const double B = 32.0 * csize;
+    if ((double)(M + 1) > 0.9 * B) return false;
+    auto K_of = [&](int q) { return -0.9 * B * std::log(1.0 - (double)q / 32.0); };
+    const int tl = (M + 2 <= 128) ? 4 : ((M + 2 <= 256) ? 8 : 16);  // the tail kernel's registers per lane (split_shape)
+    const double want_t = 0.5 * ((double)(M + 1) + 32.0 * tl), want_l = std::min(1.65 * (M + 1), 0.8 * 64.0 * tl);
+    int qt = 1, ql = 1;
+    for (int q = 1; q <= 31; ++q) {
+        if (std::fabs(K_of(q) - want_t) < std::fabs(K_of(qt) - want_t)) qt = q;
+        if (std::fabs(K_of(q) - want_l) < std::fabs(K_of(ql) - want_l)) ql = q;
+    }
+    if (const char* ev = getenv("B2L_TILE_QT")) qt = atoi(ev);
     if (const char* ev = getenv("B2L_TILE_QL")) ql = atoi(ev);
-    tp->q_l = std::min(32, std::max(tp->q_t, ql));
+    tp->q_t = std::min(31, std::max(1, qt));
+    tp->q_l = std::min(31, std::max(tp->q_t, ql));
     tp->smem = tile_smem(tp->R).total;
     return true;
 }

@@ -34,6 +34,7 @@ struct TileParams {
     SplitHeader* hdr;    // [n_tiles * TILE_W]   round scratch, as the split path's
     double* cx;          // [n_tiles * TILE_W][cap]
     unsigned short* cs;  // [n_tiles * TILE_W][cap]
+    unsigned* cnt;       // [n_tiles * TILE_W][2] candidates emitted so far (tight, loose): zeroed before the launch
     int* fb_list;        // observations (row_base + index in the round) for the general kernel
     int* fb_count;
     unsigned long long* counters;  // optional [4]; [3] += observations handed over

@@ -9,6 +9,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/psisloo_b200.h"
@@ -46,6 +48,7 @@ struct ProfRec {
 };
 bool g_prof = false;
 std::vector<ProfRec> g_prof_recs;
+std::mutex g_prof_mu;  // the host pipelines of different devices may run on different threads
 struct ProfScope {
     cudaEvent_t a = nullptr, b = nullptr;
     cudaStream_t st;
@@ -56,6 +59,7 @@ struct ProfScope {
     ~ProfScope() {
         if (a && b) {
             cudaEventRecord(b, st);
+            std::lock_guard<std::mutex> lock(g_prof_mu);
             g_prof_recs.push_back({a, b, kind});
         }
     }
@@ -409,6 +413,7 @@ static int launch_tiles(const RowPlan& pl, const SplitPlan& sp, const TilePlan& 
     double* cx = reinterpret_cast<double*>(w);
     w += align_up((size_t)sp.batch * sp.cap * 8, 256);
     unsigned short* cs = reinterpret_cast<unsigned short*>(w);
+    unsigned* cnt = reinterpret_cast<unsigned*>((char*)sws + split_slot_bytes(sp));  // second slot: unused by loo
     w = (char*)sws + 2 * split_slot_bytes(sp);
     int* fb_list = reinterpret_cast<int*>(w);
     w += align_up((size_t)std::max<long long>(N, 1) * 4, 256);
@@ -427,8 +432,9 @@ static int launch_tiles(const RowPlan& pl, const SplitPlan& sp, const TilePlan& 
         memset(&tq, 0, sizeof(tq));
         tq.S = (int)S; tq.M = rp.M; tq.cap = sp.cap; tq.R = tp.R; tq.nbox = tp.nbox; tq.box_rows = tp.box_rows;
         tq.q_t = tp.q_t; tq.q_l = tp.q_l; tq.n_tiles = (nb + TILE_W - 1) / TILE_W; tq.col0 = i0; tq.n_obs = nb;
-        tq.hdr = hdr; tq.cx = cx; tq.cs = cs; tq.fb_list = fb_list; tq.fb_count = fb_count;
+        tq.hdr = hdr; tq.cx = cx; tq.cs = cs; tq.cnt = cnt; tq.fb_list = fb_list; tq.fb_count = fb_count;
         tq.counters = rp.counters; tq.row_base = i0;
+        CK(cudaMemsetAsync(cnt, 0, (size_t)tq.n_tiles * TILE_W * 2 * sizeof(unsigned), st));
         {
             ProfScope prof(B2L_PROF_STREAM, st);
             CK(tile_launch(tp, tmap, tq, st));
@@ -1113,6 +1119,7 @@ struct Slot {
     size_t bytes = 0;
 };
 struct DevCtx {
+    std::mutex mu;  // one host pipeline at a time per device; different devices run concurrently
     Slot slot[NSLOT];
     bool init = false;
     // pinned staging for the small per-observation outputs: an async copy into the caller's (usually
@@ -1120,8 +1127,23 @@ struct DevCtx {
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
 };
-std::mutex g_ctx_mu;
 DevCtx g_ctx[64];
+
+// the calling thread's current device is restored on every exit path of a host entry point
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+// work queued on the chunk streams must not outlive a failed call (its buffers may be reused or freed)
+struct SlotDrain {
+    DevCtx& cx;
+    explicit SlotDrain(DevCtx& c) : cx(c) {}
+    ~SlotDrain() {
+        for (int s = 0; s < NSLOT; ++s)
+            if (cx.slot[s].st) cudaStreamSynchronize(cx.slot[s].st);
+    }
+};
 
 int pinned_reserve(DevCtx& cx, size_t bytes) {
     if (cx.pinned_bytes < bytes) {
@@ -1169,9 +1191,12 @@ extern "C" int b2l_psislw_host_f64(const double* lw, int64_t S, int64_t N, int64
     const bool rows_in = (stride_s == 1 || S == 1), rows_out = (ostride_s == 1 || S == 1);
     if (!rows_in && !(stride_n == 1 || N == 1)) return fail(B2L_E_INVALID, "input must have a unit stride");
     if (!rows_out && !(ostride_n == 1 || N == 1)) return fail(B2L_E_INVALID, "output must have a unit stride");
-    std::lock_guard<std::mutex> lock(g_ctx_mu);
+    if (device < 0 || device >= 64) return fail(B2L_E_INVALID, "device index %d out of range", device);
+    DevCtx& cx = g_ctx[device];
+    std::lock_guard<std::mutex> lock(cx.mu);
+    DeviceGuard restore;
     CK(cudaSetDevice(device));
-    DevCtx& cx = g_ctx[device & 63];
+    SlotDrain drain(cx);
     const long long chunk = chunk_obs > 0 ? std::min<long long>(chunk_obs, N) : default_chunk(S, N);
     size_t wsb = 0;
     b2l_workspace_bytes(S, chunk, M, (!rows_in || !rows_out) ? 1 : 0, &wsb);
@@ -1236,9 +1261,12 @@ extern "C" int b2l_loo_host_f64(const double* ll, int64_t S, int64_t N, int64_t 
     if (b2l_device_count() < 1) return B2L_E_NODEVICE;
     const bool rows_in = (stride_s == 1 || S == 1);
     if (!rows_in && !(stride_n == 1 || N == 1)) return fail(B2L_E_INVALID, "input must have a unit stride");
-    std::lock_guard<std::mutex> lock(g_ctx_mu);
+    if (device < 0 || device >= 64) return fail(B2L_E_INVALID, "device index %d out of range", device);
+    DevCtx& cx = g_ctx[device];
+    std::lock_guard<std::mutex> lock(cx.mu);
+    DeviceGuard restore;
     CK(cudaSetDevice(device));
-    DevCtx& cx = g_ctx[device & 63];
+    SlotDrain drain(cx);
     const long long chunk = chunk_obs > 0 ? std::min<long long>(chunk_obs, std::max<long long>(N, 1))
                                           : default_chunk(S, N);
     size_t wsb = 0;
@@ -1314,5 +1342,110 @@ extern "C" int b2l_loo_host_f64(const double* ll, int64_t S, int64_t N, int64_t 
             if (rc) return rc;
         }
     }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ several GPUs, one process
+// Observations are independent (pyloo/utils.py:171-176): contiguous shards of the observation axis, one host
+// thread and one b2l_*_host_f64 pipeline per device, no data-path exchange.  Shard records are merged in
+// shard order with Chan's update (b2l_stats_merge), so the totals do not depend on the device count.
+namespace {
+// pins the caller's (pageable) buffer for the duration of a call when B2L_HOST_REGISTER=1: the chunk copies
+// then run as true asynchronous DMA instead of through the driver's staging buffers
+struct HostPin {
+    void* p = nullptr;
+    HostPin(const void* base, size_t bytes) {
+        const char* ev = getenv("B2L_HOST_REGISTER");
+        if (!ev || atoi(ev) == 0 || !base || bytes == 0) return;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, base) == cudaSuccess && at.type != cudaMemoryTypeUnregistered) return;
+        cudaGetLastError();
+        if (cudaHostRegister(const_cast<void*>(base), bytes, cudaHostRegisterPortable) == cudaSuccess) p = const_cast<void*>(base);
+        else cudaGetLastError();
+    }
+    ~HostPin() { if (p) cudaHostUnregister(p); }
+};
+size_t span_bytes(int64_t S, int64_t N, int64_t stride_s, int64_t stride_n) {
+    if (S < 1 || N < 1) return 0;
+    return (size_t)((S - 1) * stride_s + (N - 1) * stride_n + 1) * 8;
+}
+void shard_bounds(int64_t N, int n, std::vector<int64_t>& b) {
+    b.assign(n + 1, 0);
+    const int64_t per = ((N + n - 1) / n + 15) / 16 * 16;  // whole tiles: shards stay 16 B aligned and tile aligned
+    for (int d = 1; d <= n; ++d) b[d] = std::min<int64_t>(N, b[d - 1] + per);
+}
+}  // namespace
+
+extern "C" int b2l_loo_host_mgpu_f64(const double* ll, int64_t S, int64_t N, int64_t stride_s, int64_t stride_n,
+                                     int32_t M, double cutoffmin, uint32_t flags, double good_k, double* elpd_i,
+                                     double* k_i, double* lppd_i, double* var_i, double* lppdw_i, double* stats_out,
+                                     const int32_t* devices, int32_t n_devices, int64_t chunk_obs) {
+    if (!devices || n_devices < 1 || n_devices > 64) return fail(B2L_E_INVALID, "bad device list");
+    if (!ll || !elpd_i || !k_i || !lppd_i || !var_i || !lppdw_i || N < 0 || S < 1)
+        return fail(B2L_E_INVALID, "bad arguments");
+    HostPin pin(ll, span_bytes(S, N, stride_s, stride_n));
+    if (n_devices == 1 || N < 32)
+        return b2l_loo_host_f64(ll, S, N, stride_s, stride_n, M, cutoffmin, flags, good_k, elpd_i, k_i, lppd_i, var_i,
+                                lppdw_i, stats_out, devices[0], chunk_obs);
+    std::vector<int64_t> b;
+    shard_bounds(N, n_devices, b);
+    std::vector<double> recs((size_t)n_devices * B2L_STATS_LEN, 0.0);
+    std::vector<int> rcs(n_devices, 0);
+    std::vector<std::string> msgs(n_devices);
+    std::vector<std::thread> th;
+    int used = 0;
+    for (int d = 0; d < n_devices; ++d) {
+        const int64_t i0 = b[d], n = b[d + 1] - b[d];
+        if (n <= 0) continue;
+        ++used;
+        th.emplace_back([&, d, i0, n]() {
+            rcs[d] = b2l_loo_host_f64(ll + i0 * stride_n, S, n, stride_s, stride_n, M, cutoffmin, flags, good_k,
+                                      elpd_i + i0, k_i + i0, lppd_i + i0, var_i + i0, lppdw_i + i0,
+                                      recs.data() + (size_t)d * B2L_STATS_LEN, devices[d], chunk_obs);
+            if (rcs[d]) msgs[d] = b2l_last_error();
+        });
+    }
+    for (auto& t : th) t.join();
+    for (int d = 0; d < n_devices; ++d)
+        if (rcs[d]) return fail(rcs[d], "device %d: %s", devices[d], msgs[d].c_str());
+    if (stats_out) {
+        std::vector<double> packed;
+        for (int d = 0; d < n_devices; ++d)
+            if (b[d + 1] > b[d]) packed.insert(packed.end(), recs.begin() + (size_t)d * B2L_STATS_LEN,
+                                               recs.begin() + (size_t)(d + 1) * B2L_STATS_LEN);
+        return b2l_stats_merge(packed.data(), used, stats_out);
+    }
+    return 0;
+}
+
+extern "C" int b2l_psislw_host_mgpu_f64(const double* lw, int64_t S, int64_t N, int64_t stride_s, int64_t stride_n,
+                                        int32_t M, double cutoffmin, double* lw_out, int64_t ostride_s,
+                                        int64_t ostride_n, double* k_out, const int32_t* devices, int32_t n_devices,
+                                        int64_t chunk_obs) {
+    if (!devices || n_devices < 1 || n_devices > 64) return fail(B2L_E_INVALID, "bad device list");
+    if (!lw || !lw_out || !k_out || N < 0 || S < 1) return fail(B2L_E_INVALID, "bad arguments");
+    HostPin pin_in(lw, span_bytes(S, N, stride_s, stride_n));
+    HostPin pin_out(lw_out, span_bytes(S, N, ostride_s, ostride_n));
+    if (n_devices == 1 || N < 32)
+        return b2l_psislw_host_f64(lw, S, N, stride_s, stride_n, M, cutoffmin, lw_out, ostride_s, ostride_n, k_out,
+                                   devices[0], chunk_obs);
+    std::vector<int64_t> b;
+    shard_bounds(N, n_devices, b);
+    std::vector<int> rcs(n_devices, 0);
+    std::vector<std::string> msgs(n_devices);
+    std::vector<std::thread> th;
+    for (int d = 0; d < n_devices; ++d) {
+        const int64_t i0 = b[d], n = b[d + 1] - b[d];
+        if (n <= 0) continue;
+        th.emplace_back([&, d, i0, n]() {
+            rcs[d] = b2l_psislw_host_f64(lw + i0 * stride_n, S, n, stride_s, stride_n, M, cutoffmin,
+                                         lw_out + i0 * ostride_n, ostride_s, ostride_n, k_out + i0, devices[d],
+                                         chunk_obs);
+            if (rcs[d]) msgs[d] = b2l_last_error();
+        });
+    }
+    for (auto& t : th) t.join();
+    for (int d = 0; d < n_devices; ++d)
+        if (rcs[d]) return fail(rcs[d], "device %d: %s", devices[d], msgs[d].c_str());
     return 0;
 }

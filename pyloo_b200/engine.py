@@ -17,7 +17,7 @@ from . import _native
 __all__ = [
     "CUTOFFMIN", "tail_length", "good_k_threshold", "psislw_host", "loo_host", "psislw_cuda",
     "loo_cuda", "stats_cuda", "stats_merge", "StatsRecord", "row_launch_info", "current_device",
-    "workspace_for", "profile", "profile_read", "split_launch_info", "handover_reasons",
+    "workspace_for", "profile", "profile_read", "split_launch_info", "handover_reasons", "host_devices",
 ]
 
 CUTOFFMIN = float(np.log(np.finfo(float).tiny))  # pyloo/psis.py:90
@@ -36,10 +36,34 @@ def good_k_threshold(n_samples: int) -> float:
 
 def current_device() -> int:
     """GPU this process drives: LOCAL_RANK under torchrun, else B2L_DEVICE, else 0."""
-    for key in ("B2L_DEVICE", "LOCAL_RANK"):
+    for key in ("LOCAL_RANK", "B2L_DEVICE"):
         if key in os.environ:
             return int(os.environ[key])
     return 0
+
+
+_MGPU_MIN_BYTES = 1 << 30  # below this one GPU finishes before the other contexts exist
+
+
+def host_devices(device=None, devices=None, nbytes: int = 0) -> list:
+    """Devices a host-array call is spread over (observation shards, one pipeline per device).
+
+    ``device`` (one index) or ``devices`` (a sequence) pin the choice.  Otherwise: a process that torchrun
+    gave a LOCAL_RANK (or the user a B2L_DEVICE) drives that one GPU; ``B2L_DEVICES`` ("all" or "0,2,3") names
+    a list; else every visible GPU once the input is at least 1 GiB, and GPU 0 for smaller inputs."""
+    if device is not None:
+        return [int(device)]
+    if devices is not None:
+        return [int(d) for d in devices]
+    if "LOCAL_RANK" in os.environ or "B2L_DEVICE" in os.environ:
+        return [current_device()]
+    spec = os.environ.get("B2L_DEVICES", "").strip().lower()
+    if spec and spec != "all":
+        return [int(d) for d in spec.split(",") if d.strip()]
+    if not spec and nbytes < _MGPU_MIN_BYTES:
+        return [0]
+    n = _native.load().b2l_device_count()
+    return list(range(max(1, n)))
 
 
 def _check_tail(S: int, M: int) -> None:
@@ -103,11 +127,12 @@ def _as_strided_f64_2d(a) -> np.ndarray:
     return a if ok else np.ascontiguousarray(a)
 
 
-def psislw_host(lw_ns: np.ndarray, reff: float = 1.0, *, out=None, device=None, chunk_obs: int = 0):
+def psislw_host(lw_ns: np.ndarray, reff: float = 1.0, *, out=None, device=None, devices=None, chunk_obs: int = 0):
     """Batch PSIS on a HOST ``(N, S)`` array (samples on the last axis, any unit-stride layout).
 
     Returns ``(lw_out, k)``: C-contiguous ``(N, S)`` smoothed log weights and ``(N,)`` Pareto k.
-    The input is never modified (pyloo/psis.py:78)."""
+    The input is never modified (pyloo/psis.py:78).  Observation shards go to the GPUs of
+    :func:`host_devices`."""
     lib = _native.load()
     a = _as_strided_f64_2d(lw_ns)
     N, S = a.shape
@@ -120,14 +145,14 @@ def psislw_host(lw_ns: np.ndarray, reff: float = 1.0, *, out=None, device=None, 
         return out, k
     sn, ss = _elem_strides(a)
     osn, oss = _elem_strides(out)
-    dev = current_device() if device is None else int(device)
-    rc = lib.b2l_psislw_host_f64(a.ctypes.data, S, N, ss, sn, M, CUTOFFMIN, out.ctypes.data, oss, osn,
-                                 k.ctypes.data, dev, int(chunk_obs))
+    devs = np.asarray(host_devices(device, devices, a.nbytes), dtype=np.int32)
+    rc = lib.b2l_psislw_host_mgpu_f64(a.ctypes.data, S, N, ss, sn, M, CUTOFFMIN, out.ctypes.data, oss, osn,
+                                      k.ctypes.data, devs.ctypes.data, int(devs.size), int(chunk_obs))
     _native.check(rc)
     return out, k
 
 
-def loo_host(ll_sn: np.ndarray, reff: float = 1.0, *, waic_only: bool = False, device=None,
+def loo_host(ll_sn: np.ndarray, reff: float = 1.0, *, waic_only: bool = False, device=None, devices=None,
              chunk_obs: int = 0):
     """Fused pointwise PSIS-LOO + WAIC on a HOST sample-major ``(S, N)`` log-likelihood
     (ArviZ ``(chain, draw, obs)`` flattened; a transposed ``(N, S)``-contiguous view also works).
@@ -143,10 +168,10 @@ def loo_host(ll_sn: np.ndarray, reff: float = 1.0, *, waic_only: bool = False, d
     outs = [np.empty(N, dtype=np.float64) for _ in range(5)]
     stats = np.zeros(_native.STATS_LEN)
     ss, sn = _elem_strides(a)
-    dev = current_device() if device is None else int(device)
-    rc = lib.b2l_loo_host_f64(a.ctypes.data, S, N, ss, sn, M, CUTOFFMIN,
-                              _native.FLAG_WAIC_ONLY if waic_only else 0, gk, *[o.ctypes.data for o in outs],
-                              stats.ctypes.data, dev, int(chunk_obs))
+    devs = np.asarray(host_devices(device, devices, a.nbytes), dtype=np.int32)
+    rc = lib.b2l_loo_host_mgpu_f64(a.ctypes.data, S, N, ss, sn, M, CUTOFFMIN,
+                                   _native.FLAG_WAIC_ONLY if waic_only else 0, gk, *[o.ctypes.data for o in outs],
+                                   stats.ctypes.data, devs.ctypes.data, int(devs.size), int(chunk_obs))
     _native.check(rc)
     return {"elpd_i": outs[0], "pareto_k": outs[1], "lppd_i": outs[2], "var_i": outs[3],
             "lppdw_i": outs[4], "stats": StatsRecord(stats), "M": M, "good_k": gk, "n_samples": S}
