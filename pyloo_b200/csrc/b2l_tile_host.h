@@ -8,16 +8,16 @@
 
 namespace b2l {
 
-constexpr int TILE_W = 16;      // observations per tile: 128 B of every draw
-constexpr int TILE_NT = 256;    // threads per CTA: 16 draw slots x 16 observations
+constexpr int TILE_W = 16;      // default observations per tile: 128 B of every draw (8 is the other build: 64 B)
 constexpr int TILE_MAXC = 8;    // largest (portable) cluster
 constexpr int TILE_MAX_R = 512; // draws per CTA: one 32-bit candidate mask per thread (16 draw slots x 32)
 
 struct TilePlan {
     int ok;
+    int tw;        // observations per tile (16 or 8); threads per CTA = 16 * tw
     int csize;     // CTAs per cluster = segments of the draw axis
-    int R;         // draws per CTA (nbox * box_rows)
-    int nbox, box_rows;
+    int R;         // draws a CTA owns: ceil(S / csize)
+    int nbox, box_rows;  // its TMA boxes: nbox * box_rows >= R rows, box_rows a multiple of 8
     int q_t, q_l;  // ranks (1..32) of a CTA's sorted bin minima that give the tight / loose candidate threshold
     int occ;       // resident CTAs per SM
     int max_clusters;
@@ -28,24 +28,26 @@ struct TileParams {
     int S, M, cap;
     int R, nbox, box_rows;
     int q_t, q_l;
-    long long n_tiles;   // tiles of this round
+    long long n_tiles;   // tiles (tw observations each) of this round
     long long col0;      // matrix column of the round's first observation
     long long n_obs;     // observations of this round (the last tile may be partial)
-    SplitHeader* hdr;    // [n_tiles * TILE_W]   round scratch, as the split path's
-    double* cx;          // [n_tiles * TILE_W][cap]
-    unsigned short* cs;  // [n_tiles * TILE_W][cap]
-    unsigned* cnt;       // [n_tiles * TILE_W][2] candidates emitted so far (tight, loose): zeroed before the launch
+    SplitHeader* hdr;    // [n_tiles * tw]   round scratch, as the split path's
+    double* cx;          // [n_tiles * tw][cap]
+    unsigned short* cs;  // [n_tiles * tw][cap]
+    unsigned* cnt;       // [n_tiles * tw][2] candidates emitted so far (tight, loose): zeroed before the launch
     int* fb_list;        // observations (row_base + index in the round) for the general kernel
     int* fb_count;
     unsigned long long* counters;  // optional [4]; [3] += observations handed over
     long long row_base;
+    int stagger_ns;  // start offset between the three groups of clusters (0: none)
+    int debug;  // measurement aids (B2L_TILE_DEBUG): 2 loads only, 4 no candidate pass, 8 no exp pass (2, 4, 8: no valid results)
 };
 
 // shape part (pure arithmetic) and device part (occupancy) of the plan
-bool tile_shape(long long S, int M, int csize, TilePlan* tp);
+bool tile_shape(long long S, int M, int csize, int tw, TilePlan* tp);
 cudaError_t tile_plan(long long S, int M, TilePlan* tp);
 // 2-D tensor map of the (S, N) matrix: inner dimension = observations, box = TILE_W x box_rows
-cudaError_t tile_tensor_map(const double* ll, long long S, long long N, long long stride_s, int box_rows,
+cudaError_t tile_tensor_map(const double* ll, long long S, long long N, long long stride_s, int tw, int box_rows,
                             void* tmap_out /* CUtensorMap, 128 B */);
 cudaError_t tile_launch(const TilePlan& tp, const void* tmap, const TileParams& p, cudaStream_t st);
 cudaError_t tile_reasons(unsigned long long* out, int reset);

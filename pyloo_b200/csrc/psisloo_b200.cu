@@ -400,41 +400,61 @@ static bool tile_eligible(const double* ll, long long S, long long N, long long 
     if (!aligned16_ptr(ll) || (stride_s % 2) != 0) return false;          // TMA: 16 B aligned base and row pitch
     if ((unsigned long long)stride_s * 8ull >= (1ull << 40)) return false;  // TMA: pitch < 2^40 bytes
     TilePlan tp;
-    return tile_shape(S, M, TILE_MAXC, &tp);
+    return tile_shape(S, M, TILE_MAXC, TILE_W, &tp);
+}
+
+// scratch of the tile path inside the caller's workspace: [hand-over count][hand-over list: N][one round: headers |
+// candidate x | candidate draw index | candidate counters].  Rounds are as long as the workspace allows (up to
+// B2L_TILE_ROUND observations): a launch's fixed costs and its last, partly filled wave of clusters weigh less.
+static size_t tile_round_bytes(const SplitPlan& sp, long long P) {
+    return align_up((size_t)P * sizeof(SplitHeader), 256) + align_up((size_t)P * sp.cap * 8, 256) +
+           align_up((size_t)P * sp.cap * 2, 256) + align_up((size_t)P * 8, 256);
+}
+static size_t tile_fixed_bytes(long long N) { return 256 + align_up((size_t)std::max<long long>(N, 1) * 4, 256); }
+static long long tile_round_obs(const SplitPlan& sp, long long N, size_t avail) {
+    long long want = 148ll * 64 * 8;
+    if (const char* ev = getenv("B2L_TILE_ROUND")) want = std::max<long long>(TILE_W, atoll(ev));
+    want = std::min<long long>(want, (N + TILE_W - 1) / TILE_W * TILE_W);
+    want = want / TILE_W * TILE_W;
+    const size_t fixed = tile_fixed_bytes(N);
+    while (want > TILE_W && fixed + tile_round_bytes(sp, want) > avail) want = (want / 2 + TILE_W - 1) / TILE_W * TILE_W;
+    return (fixed + tile_round_bytes(sp, want) <= avail) ? want : 0;
 }
 
 static int launch_tiles(const RowPlan& pl, const SplitPlan& sp, const TilePlan& tp, const double* ll, long long S,
-                        long long N, long long stride_s, const RowParams& rp, void* sws, cudaStream_t st) {
+                        long long N, long long stride_s, const RowParams& rp, void* sws, long long P, cudaStream_t st) {
     alignas(64) unsigned char tmap[128];
-    CK(tile_tensor_map(ll, S, N, stride_s, tp.box_rows, tmap));
+    CK(tile_tensor_map(ll, S, N, stride_s, tp.tw, tp.box_rows, tmap));
     char* w = (char*)sws;
-    SplitHeader* hdr = reinterpret_cast<SplitHeader*>(w);
-    w += align_up((size_t)sp.batch * sizeof(SplitHeader), 256);
-    double* cx = reinterpret_cast<double*>(w);
-    w += align_up((size_t)sp.batch * sp.cap * 8, 256);
-    unsigned short* cs = reinterpret_cast<unsigned short*>(w);
-    unsigned* cnt = reinterpret_cast<unsigned*>((char*)sws + split_slot_bytes(sp));  // second slot: unused by loo
-    w = (char*)sws + 2 * split_slot_bytes(sp);
+    int* fb_count = reinterpret_cast<int*>(w);
+    w += 256;
     int* fb_list = reinterpret_cast<int*>(w);
     w += align_up((size_t)std::max<long long>(N, 1) * 4, 256);
-    int* fb_count = reinterpret_cast<int*>(w);
+    SplitHeader* hdr = reinterpret_cast<SplitHeader*>(w);
+    w += align_up((size_t)P * sizeof(SplitHeader), 256);
+    double* cx = reinterpret_cast<double*>(w);
+    w += align_up((size_t)P * sp.cap * 8, 256);
+    unsigned short* cs = reinterpret_cast<unsigned short*>(w);
+    w += align_up((size_t)P * sp.cap * 2, 256);
+    unsigned* cnt = reinterpret_cast<unsigned*>(w);
     int msq = (int)std::sqrt((double)rp.M);
     while (msq * msq > rp.M) --msq;
     while ((msq + 1) * (msq + 1) <= rp.M) ++msq;
     CK(cudaMemsetAsync(fb_count, 0, sizeof(int), st));
-    // rounds of whole tiles; equal rounds, so that the last one is not a sliver
-    const long long per_max = std::max<long long>(TILE_W, sp.batch / TILE_W * TILE_W);
-    const long long n_rounds = std::max<long long>(1, (N + per_max - 1) / per_max);
-    const long long per_round = std::min<long long>(per_max, ((N + n_rounds - 1) / n_rounds + TILE_W - 1) / TILE_W * TILE_W);
+    // equal rounds of whole tiles, so that the last one is not a sliver
+    const long long n_rounds = std::max<long long>(1, (N + P - 1) / P);
+    const long long per_round = std::min<long long>(P, ((N + n_rounds - 1) / n_rounds + TILE_W - 1) / TILE_W * TILE_W);
     for (long long i0 = 0; i0 < N; i0 += per_round) {
         const long long nb = std::min<long long>(per_round, N - i0);
         TileParams tq;
         memset(&tq, 0, sizeof(tq));
         tq.S = (int)S; tq.M = rp.M; tq.cap = sp.cap; tq.R = tp.R; tq.nbox = tp.nbox; tq.box_rows = tp.box_rows;
-        tq.q_t = tp.q_t; tq.q_l = tp.q_l; tq.n_tiles = (nb + TILE_W - 1) / TILE_W; tq.col0 = i0; tq.n_obs = nb;
+        tq.q_t = tp.q_t; tq.q_l = tp.q_l; tq.n_tiles = (nb + tp.tw - 1) / tp.tw; tq.col0 = i0; tq.n_obs = nb;
         tq.hdr = hdr; tq.cx = cx; tq.cs = cs; tq.cnt = cnt; tq.fb_list = fb_list; tq.fb_count = fb_count;
         tq.counters = rp.counters; tq.row_base = i0;
-        CK(cudaMemsetAsync(cnt, 0, (size_t)tq.n_tiles * TILE_W * 2 * sizeof(unsigned), st));
+        tq.debug = getenv("B2L_TILE_DEBUG") ? atoi(getenv("B2L_TILE_DEBUG")) : 0;
+        tq.stagger_ns = getenv("B2L_TILE_STAGGER") ? atoi(getenv("B2L_TILE_STAGGER")) : 0;
+        CK(cudaMemsetAsync(cnt, 0, (size_t)tq.n_tiles * tp.tw * 2 * sizeof(unsigned), st));
         {
             ProfScope prof(B2L_PROF_STREAM, st);
             CK(tile_launch(tp, tmap, tq, st));
@@ -446,6 +466,7 @@ static int launch_tiles(const RowPlan& pl, const SplitPlan& sp, const TilePlan& 
         q.n_rows = nb; q.S = (int)S; q.M = rp.M; q.cap = sp.cap; q.m_full = 30 + msq; q.cutoffmin = rp.cutoffmin;
         q.counters = rp.counters; q.hdr = hdr; q.cx = cx; q.cs = cs; q.fb_list = fb_list; q.fb_count = fb_count;
         q.row_base = i0; q.total_body = 1; q.ab_lists = 1;
+        if (tq.debug & ~1) continue;  // measurement aids that leave no valid results: the tile kernel alone
         const int g2 = (int)std::min<long long>(sp.grid2, (nb + TAIL_WARPS - 1) / TAIL_WARPS);
         ProfScope prof(B2L_PROF_TAIL, st);
         CK(split_tail_launch(sp.tl, MODE_LOO, g2, sp.smem2, st, q));
@@ -771,11 +792,11 @@ extern "C" int b2l_loo_dev_f64(const double* ll, int64_t S, int64_t N, int64_t s
         if (rc) return rc;
         TilePlan tp;
         CK(tile_plan(S, M, &tp));
-        const size_t need = sws_off + 2 * split_slot_bytes(sp) + align_up((size_t)N * 4, 256) + 256;
-        if (sp.ok && tp.ok && ws && ws_bytes >= need) {
+        const long long Pt = (sp.ok && tp.ok && ws && ws_bytes > sws_off) ? tile_round_obs(sp, N, ws_bytes - sws_off) : 0;
+        if (Pt > 0) {
             rp.k_out = k_i; rp.elpd_i = elpd_i; rp.lppd_i = lppd_i; rp.var_i = var_i; rp.lppdw_i = lppdw_i;
             rp.diag = diag;
-            return launch_tiles(pl, sp, tp, ll, S, N, stride_s, rp, (char*)ws + sws_off, st);
+            return launch_tiles(pl, sp, tp, ll, S, N, stride_s, rp, (char*)ws + sws_off, Pt, st);
         }
     }
     rc = plan_split(S, M, MODE_LOO, P, &sp);
