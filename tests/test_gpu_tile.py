@@ -1,0 +1,186 @@
+"""GPU parity tests of the tile path: ``pl.loo`` on the ArviZ (chain, draw, obs) layout, i.e. the
+observation-fastest ``(S, N)`` matrix read where it lies by the cluster kernel of ``csrc/b2l_tile.cu``
+(2-D TMA tiles, no transposed panels) + the tail kernel, against the CPU oracle on the same seeded inputs.
+
+Tolerances as in test_gpu_parity.py: elpd_i, lppd_i, var_i, Pareto k within 1e-10 relative (values that can
+sit at zero get an absolute floor), the cutoff value and the tail count -- hence the tail index set --
+bit-exact (pyloo/psis.py:135-141)."""
+
+import numpy as np
+import pytest
+
+from b2l_testutil import has_cuda
+
+pytestmark = pytest.mark.gpu
+
+if has_cuda():
+    import torch
+    from pyloo_b200 import engine
+
+from oracle import psis_oracle as orc
+
+RTOL = 1e-10
+
+
+def close(a, b, rtol=RTOL, atol=0.0):
+    np.testing.assert_allclose(np.asarray(a), np.asarray(b), rtol=rtol, atol=atol, equal_nan=True)
+
+
+def same_special(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    assert np.array_equal(np.isposinf(a), np.isposinf(b))
+    assert np.array_equal(np.isneginf(a), np.isneginf(b))
+
+
+def gpu_loo(ll_sn, reff, **kw):
+    res = engine.loo_cuda(torch.from_numpy(np.ascontiguousarray(ll_sn)).cuda(), reff, **kw)
+    torch.cuda.synchronize()
+    return {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in res.items() if k != "workspace"}
+
+
+def oracle_tail(ll_sn, M):
+    """(cutoff value, tail count) per observation of r = -ll, as pyloo/psis.py:134-141 defines them."""
+    cut, cnt = [], []
+    for col in ll_sn.T:
+        z = -col - (-col).max()
+        c = max(np.sort(z)[-M - 1], orc.CUTOFFMIN)
+        cut.append(c)
+        cnt.append(int((z > c).sum()))
+    return np.array(cut), np.array(cnt)
+
+
+def check_against_oracle(ll, reff, r, check_tail=True):
+    with np.errstate(all="ignore"):
+        pw = orc.loo_pointwise(ll, reff)
+        ww = orc.waic_pointwise(ll)
+    for key, ref in (("elpd_i", pw["elpd_i"]), ("pareto_k", pw["pareto_k"]), ("lppd_i", pw["lppd_i"]),
+                     ("var_i", ww["var_i"]), ("lppdw_i", ww["lppd_i"])):
+        same_special(r[key], ref)
+        close(r[key], ref, atol=1e-13)   # lppd_i and k can sit arbitrarily close to 0
+    if check_tail:
+        cut, cnt = oracle_tail(ll, engine.tail_length(ll.shape[0], reff))
+        assert np.array_equal(r["diag"][:, 1], cut)          # bit-exact cutoff => bit-exact tail index set
+        assert np.array_equal(r["diag"][:, 2].astype(int), cnt)
+
+
+@pytest.mark.parametrize("tw", ["8", "16"])
+@pytest.mark.parametrize("S,N,reff", [(4000, 702, 1.0), (4000, 64, 0.9), (2000, 250, 0.7), (1024, 40, 1.0),
+                                      (3000, 18, 1.0), (4096, 34, 1.0), (1500, 6, 0.5)])
+def test_tile_path_vs_oracle(S, N, reff, tw, monkeypatch):
+    """Ragged shapes: partial last tile (N not a multiple of the tile width), draw counts that do not divide by
+    the cluster size or by 16 draw slots, the longest supported CTA share (S = 4096)."""
+    monkeypatch.setenv("B2L_TILE_W", tw)
+    rng = np.random.default_rng(S * 7 + N)
+    ll = -1.4 + rng.normal(size=(S, N)) * rng.uniform(0.3, 2.0, size=(1, N))
+    engine.handover_reasons()
+    r = gpu_loo(ll, reff, want_diag=True)
+    check_against_oracle(ll, reff, r)
+    assert int(r["counters"][3]) == 0 and engine.handover_reasons() == {}   # nothing left the fast path
+
+
+def test_tile_path_runs_the_cluster_kernel():
+    """The eligible shapes really take the tile kernel (per-kernel timers: no transpose launch)."""
+    rng = np.random.default_rng(3)
+    ll = torch.from_numpy(-1.4 + rng.normal(size=(2048, 96))).cuda()
+    engine.profile(True)
+    engine.loo_cuda(ll, 1.0)
+    torch.cuda.synchronize()
+    prof = engine.profile_read()
+    engine.profile(False)
+    assert prof["transpose"][1] == 0 and prof["stream"][1] >= 1 and prof["tail"][1] >= 1
+
+
+def test_tile_path_special_columns_are_handed_over():
+    """NaN / +-inf / constant / very wide columns leave the fast path for the general kernel, which reads the
+    column where it lies (strided): same values as the oracle, counters as pyloo/loo.py:218-227."""
+    rng = np.random.default_rng(21)
+    S, N = 2000, 48
+    ll = -1.4 + rng.normal(size=(S, N))
+    ll[3, 2] = np.nan         # NaN -> -1e10 (loo.py:227)
+    ll[5, 4] = -np.inf        # loo keeps it (elpd NaN, k inf)
+    ll[7, 6] = np.inf
+    ll[:, 8] = -2.5           # constant column -> k = inf
+    ll[10, 9] = 1e10
+    ll[11, 10] = -1e10
+    ll[:, 20] *= 400.0        # range of ll far beyond 600: the exp(ll - min ll) sum would overflow
+    ll[100, 33] = -900.0      # one far outlier below
+    r = gpu_loo(ll, 1.0, want_diag=True)
+    with np.errstate(all="ignore"):
+        pw = orc.loo_pointwise(ll, 1.0)
+        ww = orc.waic_pointwise(ll)
+    for key, ref in (("elpd_i", pw["elpd_i"]), ("pareto_k", pw["pareto_k"]), ("lppd_i", pw["lppd_i"]),
+                     ("var_i", ww["var_i"]), ("lppdw_i", ww["lppd_i"])):
+        same_special(r[key], ref)
+        # column 9 holds a +1e10 draw: the reference's own lw + ll cancels to ~1e-6 there (see test_loo_special_values)
+        close(r[key], ref, rtol=1e-8 if key == "elpd_i" else RTOL, atol=1e-13)
+    assert r["counters"][0] == 1 and r["counters"][1] == 1 and r["counters"][2] == 1
+    assert int(r["counters"][3]) >= 6
+
+
+def test_tile_path_heavy_tails():
+    """Student-t log-likelihoods: many k > 0.7, short tails, wide columns -- fast path or hand-over, same numbers."""
+    rng = np.random.default_rng(22)
+    S, N = 4000, 128
+    ll = -np.abs(rng.standard_t(2.5, size=(S, N))) * 3.0
+    r = gpu_loo(ll, 1.0, want_diag=True)
+    check_against_oracle(ll, 1.0, r)
+    assert np.array_equal(r["pareto_k"] > 0.7, orc.loo_pointwise(ll, 1.0)["pareto_k"] > 0.7)
+
+
+def test_tile_path_autocorrelated_chains():
+    """Four chains with different locations and strong autocorrelation: the CTAs of a cluster see different
+    distributions (their draw segments are different chains); thresholds are medians over the CTAs."""
+    rng = np.random.default_rng(23)
+    S, N = 4000, 64
+    z = rng.normal(size=(S, N))
+    for s in range(1, S):
+        z[s] = 0.9 * z[s - 1] + np.sqrt(1 - 0.81) * z[s]
+    ll = -1.4 + z
+    ll[1000:2000] += 0.5
+    ll[3000:] -= 0.7
+    r = gpu_loo(ll, 1.0, want_diag=True)
+    check_against_oracle(ll, 1.0, r)
+
+
+def test_tile_path_rounds_and_positions_do_not_matter(monkeypatch):
+    """Batch invariance (pyloo/tests/base_tests/test_loo_i.py:41-58): many short rounds, one long round, the other
+    tile width and a shifted column window give the same bits for every observation."""
+    rng = np.random.default_rng(24)
+    ll = -1.4 + rng.normal(size=(2000, 1000))
+    keys = ("elpd_i", "pareto_k", "lppd_i", "var_i", "lppdw_i")
+    base = gpu_loo(ll, 1.0)
+    monkeypatch.setenv("B2L_TILE_ROUND", "64")
+    short = gpu_loo(ll, 1.0)
+    monkeypatch.delenv("B2L_TILE_ROUND")
+    monkeypatch.setenv("B2L_TILE_W", "16")
+    wide = gpu_loo(ll, 1.0)
+    monkeypatch.delenv("B2L_TILE_W")
+    window = gpu_loo(ll[:, 6:], 1.0)
+    again = gpu_loo(ll, 1.0)
+    for key in keys:
+        assert np.array_equal(base[key], short[key])
+        assert np.array_equal(base[key], wide[key])
+        assert np.array_equal(base[key][6:], window[key])
+        assert np.array_equal(base[key], again[key])
+
+
+def test_tile_path_full_size_slab_properties():
+    """BASELINE configs[2] shape on a 75 776-observation slab (S = 4000): no hand-overs on i.i.d. data, totals of
+    the statistics record equal the NumPy reductions, a strided subset equals the oracle."""
+    torch.manual_seed(5)
+    S, N = 4000, 75_776
+    ll = torch.randn(S, N, dtype=torch.float64, device="cuda") - 1.4
+    res = engine.loo_cuda(ll, 1.0)
+    st = engine.StatsRecord(engine.stats_cuda(res).cpu().numpy())
+    torch.cuda.synchronize()
+    assert int(res["counters"][3]) == 0 and st.n == N
+    e = res["elpd_i"].cpu().numpy()
+    close(st.elpd_sum, e.sum(), 1e-12)
+    close(st.lppd_sum, res["lppd_i"].cpu().numpy().sum(), 1e-12)
+    idx = np.arange(0, N, 1511)
+    sub = ll[:, torch.from_numpy(idx).cuda()].cpu().numpy()
+    pw = orc.loo_pointwise(sub, 1.0)
+    close(e[idx], pw["elpd_i"])
+    close(res["pareto_k"].cpu().numpy()[idx], pw["pareto_k"], atol=1e-13)
+    close(res["lppd_i"].cpu().numpy()[idx], pw["lppd_i"], atol=1e-13)
