@@ -1138,6 +1138,15 @@ struct Slot {
     cudaStream_t st = nullptr;
     void* buf = nullptr;
     size_t bytes = 0;
+    // pinned bounce buffers for pageable callers (NumPy arrays): host threads copy a chunk in / out of these, the
+    // DMA engines see pinned memory only (a cudaMemcpyAsync on pageable memory is staged by the driver, serially)
+    void* hin = nullptr;
+    size_t hin_bytes = 0;
+    void* hout = nullptr;
+    size_t hout_bytes = 0;
+    // psislw: a chunk of results waiting in `hout` for its copy to the caller's array
+    double* pend_dst = nullptr;
+    long long pend_rows = 0, pend_width = 0, pend_dpitch = 0;
 };
 struct DevCtx {
     std::mutex mu;  // one host pipeline at a time per device; different devices run concurrently
@@ -1185,6 +1194,44 @@ int slot_reserve(Slot& s, size_t bytes) {
     }
     return 0;
 }
+int hpin_reserve(void** p, size_t* have, size_t bytes) {
+    if (*have < bytes) {
+        if (*p) CK(cudaFreeHost(*p));
+        *p = nullptr; *have = 0;
+        CK(cudaHostAlloc(p, bytes, cudaHostAllocDefault));
+        *have = bytes;
+    }
+    return 0;
+}
+bool host_pageable(const void* p) {
+    if (const char* ev = getenv("B2L_HOST_BOUNCE")) if (atoi(ev) == 0) return false;
+    cudaPointerAttributes at;
+    const cudaError_t e = cudaPointerGetAttributes(&at, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return true; }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+int host_threads() {
+    int n = 6;
+    if (const char* ev = getenv("B2L_HOST_THREADS")) n = atoi(ev);
+    return std::max(1, std::min(n, 64));
+}
+// rows x width bytes between two pitched host buffers, the rows split over a few threads
+void par_copy_2d(char* dst, size_t dpitch, const char* src, size_t spitch, size_t width, long long rows) {
+    const int nt = (int)std::min<long long>(host_threads(), std::max<long long>(1, rows));
+    auto work = [=](int t) {
+        const long long r0 = rows * t / nt, r1 = rows * (t + 1) / nt;
+        if (dpitch == width && spitch == width) {
+            memcpy(dst + (size_t)r0 * width, src + (size_t)r0 * width, (size_t)(r1 - r0) * width);
+            return;
+        }
+        for (long long r = r0; r < r1; ++r) memcpy(dst + (size_t)r * dpitch, src + (size_t)r * spitch, width);
+    };
+    if (nt == 1) { work(0); return; }
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+}
 long long default_chunk(long long S, long long N) {
     // one chunk = one round of the split path (whole waves of the stream and tail kernels)
     long long c = 148ll * 64;
@@ -1223,14 +1270,29 @@ extern "C" int b2l_psislw_host_f64(const double* lw, int64_t S, int64_t N, int64
     b2l_workspace_bytes(S, chunk, M, (!rows_in || !rows_out) ? 1 : 0, &wsb);
     const size_t mat = align_up((size_t)chunk * (size_t)S * 8, 256);
     const size_t need = 2 * mat + align_up((size_t)chunk * 8, 256) + wsb + 1024;
+    const bool bounce_in = host_pageable(lw), bounce_out = host_pageable(lw_out);
     for (int s = 0; s < NSLOT; ++s) {
         int rc = slot_reserve(cx.slot[s], need);
         if (rc) return rc;
+        if (bounce_in) rc = hpin_reserve(&cx.slot[s].hin, &cx.slot[s].hin_bytes, mat);
+        if (rc) return rc;
+        if (bounce_out) rc = hpin_reserve(&cx.slot[s].hout, &cx.slot[s].hout_bytes, mat);
+        if (rc) return rc;
+        cx.slot[s].pend_dst = nullptr;
     }
     {
         int rc = pinned_reserve(cx, (size_t)N * 8);
         if (rc) return rc;
     }
+    // results of a slot's earlier chunk: out of the bounce buffer into the caller's array
+    auto flush_out = [&](Slot& sl) -> int {
+        if (!sl.pend_dst) return 0;
+        CK(cudaStreamSynchronize(sl.st));
+        par_copy_2d((char*)sl.pend_dst, (size_t)sl.pend_dpitch, (const char*)sl.hout, (size_t)sl.pend_width,
+                    (size_t)sl.pend_width, sl.pend_rows);
+        sl.pend_dst = nullptr;
+        return 0;
+    };
     double* pk = reinterpret_cast<double*>(cx.pinned);
     int ci = 0;
     for (long long i0 = 0; i0 < N; i0 += chunk, ++ci) {
@@ -1242,7 +1304,18 @@ extern "C" int b2l_psislw_host_f64(const double* lw, int64_t S, int64_t N, int64
         double* d_k = cv.take<double>((size_t)chunk);
         void* d_ws = cv.take<char>(wsb);
         long long dss, dsn, oss, osn;
-        if (rows_in) {  // rows [i0, i0+nc) -> dense nc x S
+        if (bounce_out) {
+            int rc = flush_out(sl);
+            if (rc) return rc;
+        }
+        if (bounce_in) {
+            CK(cudaStreamSynchronize(sl.st));  // the slot's previous chunk has left its bounce buffer
+            if (rows_in) par_copy_2d((char*)sl.hin, (size_t)S * 8, (const char*)(lw + i0 * stride_n), (size_t)stride_n * 8,
+                                     (size_t)S * 8, nc);
+            else par_copy_2d((char*)sl.hin, (size_t)nc * 8, (const char*)(lw + i0), (size_t)stride_s * 8, (size_t)nc * 8, S);
+            CK(cudaMemcpyAsync(d_in, sl.hin, (size_t)nc * S * 8, cudaMemcpyHostToDevice, sl.st));
+            if (rows_in) { dss = 1; dsn = S; } else { dss = nc; dsn = 1; }
+        } else if (rows_in) {  // rows [i0, i0+nc) -> dense nc x S
             if (stride_n == S)  // dense on the host too: one linear DMA instead of one descriptor per row
                 CK(cudaMemcpyAsync(d_in, lw + i0 * stride_n, (size_t)nc * S * 8, cudaMemcpyHostToDevice, sl.st));
             else
@@ -1258,7 +1331,11 @@ extern "C" int b2l_psislw_host_f64(const double* lw, int64_t S, int64_t N, int64
         int rc = b2l_psislw_dev_f64(d_in, S, nc, dss, dsn, M, cutoffmin, d_out, oss, osn, d_k, nullptr,
                                     d_ws, wsb, sl.st);
         if (rc) return rc;
-        if (rows_out && ostride_n == S)
+        if (bounce_out) {
+            CK(cudaMemcpyAsync(sl.hout, d_out, (size_t)nc * S * 8, cudaMemcpyDeviceToHost, sl.st));
+            if (rows_out) { sl.pend_dst = lw_out + i0 * ostride_n; sl.pend_rows = nc; sl.pend_width = S * 8; sl.pend_dpitch = ostride_n * 8; }
+            else { sl.pend_dst = lw_out + i0; sl.pend_rows = S; sl.pend_width = nc * 8; sl.pend_dpitch = ostride_s * 8; }
+        } else if (rows_out && ostride_n == S)
             CK(cudaMemcpyAsync(lw_out + i0 * ostride_n, d_out, (size_t)nc * S * 8, cudaMemcpyDeviceToHost, sl.st));
         else if (rows_out)
             CK(cudaMemcpy2DAsync(lw_out + i0 * ostride_n, (size_t)ostride_n * 8, d_out, (size_t)S * 8,
@@ -1268,7 +1345,13 @@ extern "C" int b2l_psislw_host_f64(const double* lw, int64_t S, int64_t N, int64
                                  (size_t)nc * 8, (size_t)S, cudaMemcpyDeviceToHost, sl.st));
         CK(cudaMemcpyAsync(pk + i0, d_k, (size_t)nc * 8, cudaMemcpyDeviceToHost, sl.st));
     }
-    for (int s = 0; s < NSLOT; ++s) CK(cudaStreamSynchronize(cx.slot[s].st));
+    for (int s = 0; s < NSLOT; ++s) {
+        if (bounce_out) {
+            int rc = flush_out(cx.slot[s]);
+            if (rc) return rc;
+        }
+        CK(cudaStreamSynchronize(cx.slot[s].st));
+    }
     memcpy(k_out, pk, (size_t)N * 8);
     return 0;
 }
@@ -1295,9 +1378,14 @@ extern "C" int b2l_loo_host_f64(const double* ll, int64_t S, int64_t N, int64_t 
     const size_t mat = align_up((size_t)chunk * (size_t)S * 8, 256);
     const size_t vec = align_up((size_t)chunk * 8, 256);
     const size_t need = mat + 5 * vec + 512 + wsb + 1024;
+    const bool bounce = N > 0 && host_pageable(ll);
     for (int s = 0; s < NSLOT; ++s) {
         int rc = slot_reserve(cx.slot[s], need);
         if (rc) return rc;
+        if (bounce) {
+            rc = hpin_reserve(&cx.slot[s].hin, &cx.slot[s].hin_bytes, mat);
+            if (rc) return rc;
+        }
     }
     const long long nchunks = N > 0 ? (N + chunk - 1) / chunk : 0;
     std::vector<double> recs((size_t)std::max<long long>(nchunks, 1) * B2L_STATS_LEN, 0.0);
@@ -1322,7 +1410,15 @@ extern "C" int b2l_loo_host_f64(const double* ll, int64_t S, int64_t N, int64_t 
         double* d_stats = cv.take<double>(B2L_STATS_LEN);
         void* d_ws = cv.take<char>(wsb);
         long long dss, dsn;
-        if (rows_in) {
+        if (bounce) {
+            // the slot's previous chunk (three chunks back) has left its bounce buffer once its stream is idle
+            CK(cudaStreamSynchronize(sl.st));
+            if (rows_in) par_copy_2d((char*)sl.hin, (size_t)S * 8, (const char*)(ll + i0 * stride_n), (size_t)stride_n * 8,
+                                     (size_t)S * 8, nc);
+            else par_copy_2d((char*)sl.hin, (size_t)nc * 8, (const char*)(ll + i0), (size_t)stride_s * 8, (size_t)nc * 8, S);
+            CK(cudaMemcpyAsync(d_in, sl.hin, (size_t)nc * S * 8, cudaMemcpyHostToDevice, sl.st));
+            if (rows_in) { dss = 1; dsn = S; } else { dss = nc; dsn = 1; }
+        } else if (rows_in) {
             CK(cudaMemcpy2DAsync(d_in, (size_t)S * 8, ll + i0 * stride_n, (size_t)stride_n * 8,
                                  (size_t)S * 8, (size_t)nc, cudaMemcpyHostToDevice, sl.st));
             dss = 1; dsn = S;

@@ -33,6 +33,8 @@ def combine_stats(local_record, group=None):
         return engine.StatsRecord(np.asarray(local_record.cpu() if hasattr(local_record, "cpu") else local_record))
     rec = local_record if isinstance(local_record, torch.Tensor) else torch.as_tensor(np.asarray(local_record))
     rec = rec.to(torch.float64).contiguous()
+    if rec.is_cuda and dist.get_backend(group) != "nccl":
+        rec = rec.cpu()   # gloo (the CPU tests) has no all_gather on CUDA tensors; the record is 256 bytes
     world = dist.get_world_size(group)
     gathered = [torch.empty_like(rec) for _ in range(world)]
     dist.all_gather(gathered, rec, group=group)        # the single collective of the path

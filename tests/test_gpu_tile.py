@@ -6,6 +6,8 @@ Tolerances as in test_gpu_parity.py: elpd_i, lppd_i, var_i, Pareto k within 1e-1
 sit at zero get an absolute floor), the cutoff value and the tail count -- hence the tail index set --
 bit-exact (pyloo/psis.py:135-141)."""
 
+import os
+
 import numpy as np
 import pytest
 
@@ -184,3 +186,77 @@ def test_tile_path_full_size_slab_properties():
     close(e[idx], pw["elpd_i"])
     close(res["pareto_k"].cpu().numpy()[idx], pw["pareto_k"], atol=1e-13)
     close(res["lppd_i"].cpu().numpy()[idx], pw["lppd_i"], atol=1e-13)
+
+
+# ------------------------------------------------------------------ several devices behind the host entry points
+def _device_lists():
+    n = torch.cuda.device_count() if has_cuda() else 1
+    lists = [[0, 0], [0, 0, 0]]            # shards share a device: the shard logic without needing two GPUs
+    if n >= 2:
+        lists += [[0, 1], list(range(n))]
+    return lists
+
+
+def test_host_loo_over_device_shards_equals_one_device():
+    """``pl.loo`` cuts the observation axis into one shard per device (b2l_loo_host_mgpu_f64): pointwise results are
+    the same bits as the one-device call, the merged statistics record agrees to rounding (Chan merge in shard order)."""
+    rng = np.random.default_rng(31)
+    ll = -1.4 + rng.normal(size=(2000, 3000))
+    one = engine.loo_host(ll, 1.0, device=0)
+    for devs in _device_lists():
+        many = engine.loo_host(ll, 1.0, devices=devs)
+        for key in ("elpd_i", "pareto_k", "lppd_i", "var_i", "lppdw_i"):
+            assert np.array_equal(one[key], many[key]), (devs, key)
+        assert many["stats"].n == 3000
+        close(many["stats"].elpd_sum, one["stats"].elpd_sum, 1e-13)
+        close(many["stats"].elpd_m2, one["stats"].elpd_m2, 1e-11)
+        close(many["stats"].waic_m2, one["stats"].waic_m2, 1e-11)
+        assert many["stats"].k_gt_good == one["stats"].k_gt_good
+
+
+def test_host_psislw_over_device_shards_and_memory_kinds():
+    """Row shards of ``pl.psislw`` over a device list; pageable (bounce buffers), driver-staged and pinned callers give
+    the same bits; the calling thread's current device is left alone."""
+    rng = np.random.default_rng(32)
+    x = rng.normal(size=(900, 1000))
+    lw0, k0 = engine.psislw_host(x, 0.9, device=0)
+    before = torch.cuda.current_device()
+    for devs in _device_lists():
+        lw, k = engine.psislw_host(x, 0.9, devices=devs)
+        assert np.array_equal(lw, lw0) and np.array_equal(k, k0), devs
+    assert torch.cuda.current_device() == before
+    pinned = torch.empty((900, 1000), dtype=torch.float64, pin_memory=True)
+    pinned.copy_(torch.from_numpy(x))
+    lw_p, k_p = engine.psislw_host(pinned.numpy(), 0.9, device=0)
+    assert np.array_equal(lw_p, lw0) and np.array_equal(k_p, k0)
+    os.environ["B2L_HOST_BOUNCE"] = "0"
+    try:
+        lw_s, k_s = engine.psislw_host(x, 0.9, device=0)
+        ll = -1.4 + rng.normal(size=(1200, 700))
+        a = engine.loo_host(ll, 1.0, device=0)
+    finally:
+        del os.environ["B2L_HOST_BOUNCE"]
+    b = engine.loo_host(ll, 1.0, device=0)
+    assert np.array_equal(lw_s, lw0) and np.array_equal(k_s, k0)
+    for key in ("elpd_i", "pareto_k", "lppd_i", "var_i"):
+        assert np.array_equal(a[key], b[key])
+    # column shards of an observation-fastest host matrix in psislw, chunks smaller than a shard
+    xt = np.ascontiguousarray(x.T).T
+    lw_t, k_t = engine.psislw_host(xt, 0.9, devices=[0, 0], chunk_obs=200)
+    assert np.array_equal(lw_t, lw0) and np.array_equal(k_t, k0)
+
+
+def test_host_device_selection_rules(monkeypatch):
+    """LOCAL_RANK (torchrun) beats B2L_DEVICE; explicit arguments beat both; small inputs stay on one GPU."""
+    monkeypatch.delenv("LOCAL_RANK", raising=False)
+    monkeypatch.delenv("B2L_DEVICE", raising=False)
+    monkeypatch.delenv("B2L_DEVICES", raising=False)
+    assert engine.host_devices(nbytes=1 << 20) == [0]
+    assert engine.host_devices(nbytes=1 << 40) == list(range(torch.cuda.device_count()))
+    monkeypatch.setenv("B2L_DEVICES", "0,0")
+    assert engine.host_devices(nbytes=10) == [0, 0]
+    monkeypatch.setenv("B2L_DEVICE", "3")
+    assert engine.host_devices(nbytes=1 << 40) == [3]
+    monkeypatch.setenv("LOCAL_RANK", "1")
+    assert engine.host_devices(nbytes=1 << 40) == [1] and engine.current_device() == 1
+    assert engine.host_devices(device=2) == [2] and engine.host_devices(devices=(0, 2)) == [0, 2]
