@@ -30,13 +30,17 @@ def _stub(name: str, **attrs) -> types.ModuleType:
     return mod
 
 
-def load_reference_modules(names=("utils", "psis")):
+def load_reference_modules(names=("utils", "psis"), stubs=None):
     """Load ``pyloo/<name>.py`` for each name (in order) from the reference tree under stub ``xarray`` /
     ``arviz`` modules and return ``{name: module}``.  Besides ``utils`` and ``psis`` this works for the
-    NumPy-only numerics of ``sis``, ``tis`` and ``e_loo`` (their xarray drivers are not callable)."""
+    NumPy-only numerics of ``sis``, ``tis`` and ``e_loo`` (their xarray drivers are not callable).
+    ``stubs``: ``{submodule: {attribute: object}}`` registered as ``pyloo.<submodule>`` first -- placeholders for
+    siblings that need ArviZ / PyMC and are imported but not called on the path under test (``compare.py``
+    imports ``loo``, ``waic``, ``loo_kfold``, ``loo_subsample`` and only calls them for InferenceData inputs)."""
     if not reference_available():
         raise RuntimeError(f"reference tree not found under {REFERENCE_ROOT}")
-    keys = ["xarray", "arviz", "arviz.data", "pyloo"] + [f"pyloo.{n}" for n in names]
+    stubs = stubs or {}
+    keys = ["xarray", "arviz", "arviz.data", "pyloo"] + [f"pyloo.{n}" for n in list(names) + list(stubs)]
     saved = {k: sys.modules.get(k) for k in keys}
     try:
         class _DataArray:  # placeholder type for isinstance checks only
@@ -59,6 +63,8 @@ def load_reference_modules(names=("utils", "psis")):
         pkg = types.ModuleType("pyloo")
         pkg.__path__ = [os.path.join(REFERENCE_ROOT, "pyloo")]
         sys.modules["pyloo"] = pkg
+        for short, attrs in stubs.items():
+            sys.modules[f"pyloo.{short}"] = _stub(f"pyloo.{short}", **attrs)
         mods = {}
         for short in names:
             spec = importlib.util.spec_from_file_location(

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -1210,10 +1211,16 @@ bool host_pageable(const void* p) {
     if (e != cudaSuccess) { cudaGetLastError(); return true; }
     return at.type == cudaMemoryTypeUnregistered;
 }
+std::atomic<int> g_active_pipes{0};  // host pipelines running now (one per device): they share the host cores
+struct PipeCount {
+    PipeCount() { ++g_active_pipes; }
+    ~PipeCount() { --g_active_pipes; }
+};
 int host_threads() {
-    int n = 6;
-    if (const char* ev = getenv("B2L_HOST_THREADS")) n = atoi(ev);
-    return std::max(1, std::min(n, 64));
+    if (const char* ev = getenv("B2L_HOST_THREADS")) return std::max(1, std::min(atoi(ev), 64));
+    const int hw = (int)std::thread::hardware_concurrency();
+    const int pipes = std::max(1, g_active_pipes.load());
+    return std::max(2, std::min(12, (hw > 2 ? hw - 2 : 2) / pipes));
 }
 // rows x width bytes between two pitched host buffers, the rows split over a few threads
 void par_copy_2d(char* dst, size_t dpitch, const char* src, size_t spitch, size_t width, long long rows) {
@@ -1265,6 +1272,7 @@ extern "C" int b2l_psislw_host_f64(const double* lw, int64_t S, int64_t N, int64
     DeviceGuard restore;
     CK(cudaSetDevice(device));
     SlotDrain drain(cx);
+    PipeCount pipe;
     const long long chunk = chunk_obs > 0 ? std::min<long long>(chunk_obs, N) : default_chunk(S, N);
     size_t wsb = 0;
     b2l_workspace_bytes(S, chunk, M, (!rows_in || !rows_out) ? 1 : 0, &wsb);
@@ -1371,6 +1379,7 @@ extern "C" int b2l_loo_host_f64(const double* ll, int64_t S, int64_t N, int64_t 
     DeviceGuard restore;
     CK(cudaSetDevice(device));
     SlotDrain drain(cx);
+    PipeCount pipe;
     const long long chunk = chunk_obs > 0 ? std::min<long long>(chunk_obs, std::max<long long>(N, 1))
                                           : default_chunk(S, N);
     size_t wsb = 0;
