@@ -100,6 +100,16 @@ int b2l_loo_dev_f64(const double* ll, int64_t S, int64_t N, int64_t stride_s, in
                     double* lppd_i, double* var_i, double* lppdw_i, unsigned long long* counters,
                     double* diag /* nullable, N x 8 */, void* ws, size_t ws_bytes, void* stream);
 
+/* The same call with one more, nullable output: tail_idx, N x M int32 (row-major, device).  Row i receives the draw
+ * indices of observation i's tail -- the draws with x > cutoff, pyloo/psis.py:139-141 -- ordered by decreasing x
+ * (fast path) or increasing x (general kernel), padded with -1 where the tail is shorter than M.  It is the direct
+ * evidence for "the selected tail indices are bit-exact" (compare as a set with np.where(x > x_cutoff)).            */
+int b2l_loo_dev_ex_f64(const double* ll, int64_t S, int64_t N, int64_t stride_s, int64_t stride_n,
+                       int32_t M, double cutoffmin, uint32_t flags, double* elpd_i, double* k_i,
+                       double* lppd_i, double* var_i, double* lppdw_i, unsigned long long* counters,
+                       double* diag /* nullable, N x 8 */, int32_t* tail_idx /* nullable, N x M */, void* ws,
+                       size_t ws_bytes, void* stream);
+
 /* Per-shard statistics of the pointwise outputs (device pointers): replaces the NumPy reductions
  * pyloo/loo.py:326-342 and pyloo/waic.py:147-160.  Writes B2L_STATS_LEN doubles to stats_out
  * (device).  Deterministic (fixed reduction tree).  counters may be NULL.                       */
@@ -153,8 +163,8 @@ int b2l_islw_dev_f64(const double* lw, int64_t S, int64_t N, int64_t stride_n, i
 
 /* loo(method="sis"|"tis") pointwise pass: replaces pyloo/loo.py:286-289 (weights of -ll, lw += ll),
  * :319-324 (elpd_i = logsumexp) and :329-337 (lppd_i).  ll element (s, i) at ll[s*stride_s + i*stride_n]
- * with one of the strides equal to 1 (stride_n == 1 is the ArviZ layout and goes through transposed
- * panels in the workspace); NaN -> -1e10 (loo.py:227).  counters: nullable, 3 x uint64 (+=) NaN / +inf /
+ * with one of the strides equal to 1 (stride_n == 1 is the ArviZ layout: column-form kernel, one sweep of the
+ * matrix per logsumexp, no transposed panels); NaN -> -1e10 (loo.py:227).  counters: nullable, 3 x uint64 (+=) NaN / +inf /
  * -inf inputs.  Workspace: b2l_is_workspace_bytes.                                                   */
 int b2l_is_workspace_bytes(int64_t S, int64_t N, int32_t layout_obs_fastest, size_t* out_bytes);
 int b2l_loo_is_dev_f64(const double* ll, int64_t S, int64_t N, int64_t stride_s, int64_t stride_n,

@@ -39,7 +39,7 @@ EXPORTS = [
     "b2l_split_launch_info", "b2l_handover_reasons",
     "b2l_islw_dev_f64", "b2l_is_workspace_bytes", "b2l_loo_is_dev_f64", "b2l_eloo_workspace_bytes",
     "b2l_eloo_dev_f64", "b2l_eloo_quantile_dev_f64", "b2l_group_sum_dev_f64", "b2l_gather_rows_dev_f64",
-    "b2l_loo_host_mgpu_f64", "b2l_psislw_host_mgpu_f64",
+    "b2l_loo_host_mgpu_f64", "b2l_psislw_host_mgpu_f64", "b2l_loo_dev_ex_f64",
 ]
 PROF_KINDS = ("stream", "tail", "apply", "row", "transpose", "stats", "is", "eloo")
 IS_SIS, IS_TIS = 1, 2
@@ -111,6 +111,8 @@ def _declare(lib) -> None:
     lib.b2l_psislw_dev_f64.argtypes = [vp, i64, i64, i64, i64, i32, f64, vp, i64, i64, vp, vp, vp, sz, vp]
     lib.b2l_loo_dev_f64.restype = c.c_int
     lib.b2l_loo_dev_f64.argtypes = [vp, i64, i64, i64, i64, i32, f64, u32, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.b2l_loo_dev_ex_f64.restype = c.c_int
+    lib.b2l_loo_dev_ex_f64.argtypes = [vp, i64, i64, i64, i64, i32, f64, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.b2l_stats_dev_f64.restype = c.c_int
     lib.b2l_stats_dev_f64.argtypes = [vp, vp, vp, vp, vp, i64, f64, vp, vp, vp, sz, vp]
     lib.b2l_stats_merge.restype = c.c_int

@@ -56,6 +56,9 @@ struct RowParams {
     // path, which reads the observation-fastest (S, N) matrix where it lies: in_stride = 1, in_estride = stride_s,
     // use_bulk = 0
     long long in_estride;
+    // optional [n_rows][tail_ld]: draw indices of the tail (psis.py:139-141), the rest -1 (evidence for tests)
+    int* tail_idx;
+    long long tail_ld;
 };
 
 struct RowSmemLayout {
@@ -992,6 +995,12 @@ __global__ void __launch_bounds__(NT, (NT == 128) ? 4 : ((NT == 256) ? 3 : 1)) p
             double* d = p.diag + row * DIAG_STRIDE;
             d[0] = mx; d[1] = c; d[2] = (double)n; d[3] = (double)C;
             d[4] = (double)attempts; d[5] = body; d[6] = tails; d[7] = sigma;
+        }
+        if (p.tail_idx) {  // (ts is written only on the PSIS branch, where n > 0 implies it is filled)
+            int* d = p.tail_idx + row * p.tail_ld;
+            const int nt = run_psis ? n : 0;
+            for (int i = tid; i < (int)p.tail_ld; i += NT) d[i] = (i < nt) ? ts[i] : -1;
+            __syncthreads();  // ts is reused by the next row
         }
 
         // ---------------- single-buffer mode: refill this buffer for the next row

@@ -91,6 +91,9 @@ struct SplitParams {
     // its end (only read when the tight list is shorter than M + 1 or longer than one sort)
     int total_body;
     int ab_lists;
+    // optional [n_rows][tail_ld]: draw indices of the tail (psis.py:139-141), the rest -1 (evidence for tests)
+    int* tail_idx;
+    long long tail_ld;
 };
 
 // (ExpTab, exp_poly5, scale2 and exp_tab_drop live in b2l_common.cuh: the importance-sampling kernels use them too)
@@ -1075,6 +1078,10 @@ __device__ __forceinline__ int tail_row(const SplitParams& p, long long row, con
     }
     if (__any_sync(FULL, bad)) return HO_ORDER;
 
+    if (p.tail_idx) {  // the tail's draw indices (the first n elements of the order), the rest -1
+        int* d = p.tail_idx + row * p.tail_ld;
+        for (int e = lane; e < (int)p.tail_ld; e += 32) d[e] = (e < n) ? (int)ss[e] : -1;
+    }
     const double exp_c = exp(c);  // psis.py:138
     double tsum = 0.0, traw = 0.0;
     if (!deep) {

@@ -348,6 +348,7 @@ static int launch_split(int mode, const RowPlan& pl, const SplitPlan& sp, const 
         q.n_rows = nb; q.S = rp.S; q.M = rp.M; q.cap = sp.cap; q.nbuf = sp.nbuf; q.q0 = sp.q0; q.m_full = 30 + msq;
         q.cutoffmin = rp.cutoffmin; q.counters = rp.counters; q.hdr = hdr[slot]; q.cx = cx[slot]; q.cs = cs[slot];
         q.fb_list = fb_list; q.fb_count = fb_count; q.row_base = i0; q.a_chunk = sp.a_chunk;
+        q.tail_idx = rp.tail_idx ? rp.tail_idx + i0 * rp.tail_ld : nullptr; q.tail_ld = rp.tail_ld;
         if (sp.fused && prev_rows > 0) {  // the previous batch's apply stage rides along
             q.a_in = prev.in; q.a_out = prev.out; q.a_hdr = prev.hdr; q.a_cx = prev.cx; q.a_cs = prev.cs;
             q.a_rows = prev_rows;
@@ -467,6 +468,7 @@ static int launch_tiles(const RowPlan& pl, const SplitPlan& sp, const TilePlan& 
         q.n_rows = nb; q.S = (int)S; q.M = rp.M; q.cap = sp.cap; q.m_full = 30 + msq; q.cutoffmin = rp.cutoffmin;
         q.counters = rp.counters; q.hdr = hdr; q.cx = cx; q.cs = cs; q.fb_list = fb_list; q.fb_count = fb_count;
         q.row_base = i0; q.total_body = 1; q.ab_lists = 1;
+        q.tail_idx = rp.tail_idx ? rp.tail_idx + i0 * rp.tail_ld : nullptr; q.tail_ld = rp.tail_ld;
         if (tq.debug & ~1) continue;  // measurement aids that leave no valid results: the tile kernel alone
         const int g2 = (int)std::min<long long>(sp.grid2, (nb + TAIL_WARPS - 1) / TAIL_WARPS);
         ProfScope prof(B2L_PROF_TAIL, st);
@@ -743,6 +745,15 @@ extern "C" int b2l_loo_dev_f64(const double* ll, int64_t S, int64_t N, int64_t s
                                double* elpd_i, double* k_i, double* lppd_i, double* var_i,
                                double* lppdw_i, unsigned long long* counters, double* diag, void* ws,
                                size_t ws_bytes, void* stream) {
+    return b2l_loo_dev_ex_f64(ll, S, N, stride_s, stride_n, M, cutoffmin, flags, elpd_i, k_i, lppd_i, var_i, lppdw_i,
+                              counters, diag, nullptr, ws, ws_bytes, stream);
+}
+
+extern "C" int b2l_loo_dev_ex_f64(const double* ll, int64_t S, int64_t N, int64_t stride_s,
+                                  int64_t stride_n, int32_t M, double cutoffmin, uint32_t flags,
+                                  double* elpd_i, double* k_i, double* lppd_i, double* var_i,
+                                  double* lppdw_i, unsigned long long* counters, double* diag,
+                                  int32_t* tail_idx, void* ws, size_t ws_bytes, void* stream) {
     if (!ll || !elpd_i || !k_i || !lppd_i || !var_i || !lppdw_i || N < 0)
         return fail(B2L_E_INVALID, "null pointer or negative N");
     if (N == 0) return 0;
@@ -753,6 +764,7 @@ extern "C" int b2l_loo_dev_f64(const double* ll, int64_t S, int64_t N, int64_t s
     RowParams rp;
     memset(&rp, 0, sizeof(rp));
     rp.S = (int)S; rp.M = M; rp.cutoffmin = cutoffmin; rp.counters = counters;
+    rp.tail_idx = tail_idx; rp.tail_ld = M;
     rp.waic_only = (flags & B2L_FLAG_WAIC_ONLY) ? 1 : 0;
     const size_t gro = grows_ws_bytes(S);
     if (gro) {
@@ -815,6 +827,7 @@ extern "C" int b2l_loo_dev_f64(const double* ll, int64_t S, int64_t N, int64_t s
         r.in = pa; r.in_stride = S; r.n_rows = np;
         r.k_out = k_i + i0; r.elpd_i = elpd_i + i0; r.lppd_i = lppd_i + i0; r.var_i = var_i + i0;
         r.lppdw_i = lppdw_i + i0; r.diag = diag ? diag + i0 * DIAG_STRIDE : nullptr;
+        r.tail_idx = tail_idx ? tail_idx + i0 * (long long)M : nullptr;
         r.use_bulk = (S % 2 == 0) && aligned16(pa);
         rc = process_rows(MODE_LOO, pl, sp, r, sws, st);
         if (rc) return rc;

@@ -264,7 +264,7 @@ def psislw_cuda(lw, reff: float = 1.0, *, out=None, want_diag: bool = False, wor
 
 
 def loo_cuda(ll_sn, reff: float = 1.0, *, want_diag: bool = False, workspace=None, counters=None,
-             waic_only: bool = False):
+             waic_only: bool = False, want_tail_idx: bool = False):
     """Fused pointwise PSIS-LOO + WAIC on a device-resident float64 ``(S, N)`` tensor (obs-fastest
     ArviZ layout, or a transposed view of a row-contiguous ``(N, S)`` tensor).  Asynchronous.
     Returns dict of device tensors ``elpd_i, pareto_k, lppd_i, var_i, lppdw_i, counters[, diag]``."""
@@ -285,16 +285,20 @@ def loo_cuda(ll_sn, reff: float = 1.0, *, want_diag: bool = False, workspace=Non
         counters = torch.zeros(4, dtype=torch.int64, device=dev)
     diag = torch.zeros((N, _native.DIAG_STRIDE), dtype=torch.float64, device=dev) if want_diag else None
     ws = workspace if workspace is not None else _workspace(torch, lib, S, N, M, not (ss == 1 or S == 1), dev)
+    tail_idx = torch.full((N, M), -1, dtype=torch.int32, device=dev) if want_tail_idx else None
     with torch.cuda.device(dev):
-        rc = lib.b2l_loo_dev_f64(ll_sn.data_ptr(), S, N, ss, sn, M, CUTOFFMIN,
-                                 _native.FLAG_WAIC_ONLY if waic_only else 0, *[o.data_ptr() for o in outs],
-                                 counters.data_ptr(), diag.data_ptr() if want_diag else None,
-                                 ws.data_ptr(), ws.numel(), _stream_ptr(torch, dev))
+        rc = lib.b2l_loo_dev_ex_f64(ll_sn.data_ptr(), S, N, ss, sn, M, CUTOFFMIN,
+                                    _native.FLAG_WAIC_ONLY if waic_only else 0, *[o.data_ptr() for o in outs],
+                                    counters.data_ptr(), diag.data_ptr() if want_diag else None,
+                                    tail_idx.data_ptr() if want_tail_idx else None,
+                                    ws.data_ptr(), ws.numel(), _stream_ptr(torch, dev))
     _native.check(rc)
     res = {"elpd_i": outs[0], "pareto_k": outs[1], "lppd_i": outs[2], "var_i": outs[3],
            "lppdw_i": outs[4], "counters": counters, "M": M, "n_samples": S, "workspace": ws}
     if want_diag:
         res["diag"] = diag
+    if want_tail_idx:
+        res["tail_idx"] = tail_idx   # (N, M) draw indices of each tail (psis.py:139-141), padded with -1
     return res
 
 

@@ -260,3 +260,41 @@ def test_host_device_selection_rules(monkeypatch):
     monkeypatch.setenv("LOCAL_RANK", "1")
     assert engine.host_devices(nbytes=1 << 40) == [1] and engine.current_device() == 1
     assert engine.host_devices(device=2) == [2] and engine.host_devices(devices=(0, 2)) == [0, 2]
+
+
+# ------------------------------------------------------------------ the tail index sets themselves
+def _oracle_tail_sets(x_ns, M):
+    """Per row of log ratios: the draws with x > cutoff, exactly as pyloo/psis.py:134-139 selects them."""
+    sets = []
+    for row in x_ns:
+        z = row - row.max()
+        c = max(z[np.argsort(z)[-M - 1]], orc.CUTOFFMIN)
+        sets.append(set(np.where(z > c)[0].tolist()))
+    return sets
+
+
+@pytest.mark.parametrize("name,path", [("cfg2_normal_s4000.npz", "tile"), ("cfg5_student_t_s8000.npz", "rows"),
+                                       ("cfg2_normal_s4000.npz", "rows"), ("cfg2_normal_s4000.npz", "general")])
+def test_tail_index_sets_are_bit_exact(name, path, monkeypatch):
+    """north_star: "the selected tail indices are bit-exact".  The nullable tail_idx output of b2l_loo_dev_ex_f64
+    (N x M draw indices, -1 padded) equals, as a set, np.where(x > x_cutoff) of the reference's selection on the
+    golden inputs of BASELINE configs[1] and [4] -- through the tile kernel (matrix in the (S, N) layout), the
+    split row path and the general kernel."""
+    from b2l_testutil import golden
+
+    g = golden(name)
+    x = g["x"]                                   # (N, S) raw log ratios; loo sees ll = -x
+    reff = float(g["reff"])
+    M = engine.tail_length(x.shape[1], reff)
+    if path == "general":
+        monkeypatch.setenv("B2L_FORCE_LEGACY", "1")
+    t = torch.from_numpy(np.ascontiguousarray(-x.T) if path == "tile" else np.ascontiguousarray(-x)).cuda()
+    res = engine.loo_cuda(t if path == "tile" else t.t(), reff, want_tail_idx=True)
+    torch.cuda.synchronize()
+    idx = res["tail_idx"].cpu().numpy()
+    assert idx.shape == (x.shape[0], M)
+    want = _oracle_tail_sets(x, M)
+    for i, row in enumerate(idx):
+        got = row[row >= 0]
+        assert len(got) == len(set(got.tolist()))            # no draw twice
+        assert set(got.tolist()) == want[i], i
