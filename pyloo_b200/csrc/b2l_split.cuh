@@ -94,6 +94,7 @@ struct SplitParams {
     // optional [n_rows][tail_ld]: draw indices of the tail (psis.py:139-141), the rest -1 (evidence for tests)
     int* tail_idx;
     long long tail_ld;
+    double log_S;  // np.log(n_samples), computed by the host like the reference does (utils.py:353)
 };
 
 // (ExpTab, exp_poly5, scale2 and exp_tab_drop live in b2l_common.cuh: the importance-sampling kernels use them too)
@@ -138,6 +139,7 @@ __device__ __forceinline__ void log_tab_init(double* tab, int j) {  // j < 64
     tab[64 + j] = -log(ic);
 }
 static __device__ __noinline__ double log_slow(double y) { return log(y); }
+static __device__ __noinline__ double exp_any(double x) { return exp(x); }  // (one out-of-line copy of the library exp)
 __device__ __forceinline__ double log_tab(double y, const double* tab) {
     const int hi = __double2hiint(y);
     if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return log_slow(y);
@@ -911,7 +913,6 @@ __host__ __device__ inline TailSmem tail_smem(int M, int TL, int warps) {
     return L;
 }
 
-constexpr int TAIL_WARPS = 4;
 
 struct TailStage {
     double* tb;
@@ -1035,9 +1036,12 @@ __device__ __forceinline__ bool fix_runs(const TailStage& st, int C, int M, doub
     return !__any_sync(FULL, bad);
 }
 
-// One row for one warp.  Returns false -> general kernel.
-template <int TL, int MODE>
-__device__ __forceinline__ int tail_row(const SplitParams& p, long long row, const SplitHeader& h,
+// One row for one warp, in four phases.  Returns 0, or the reason the row goes to the general kernel (-1: the warp
+// had no row).  SYNCP: the warps of the CTA meet at a block barrier between the phases (every warp of the CTA
+// must call this function the same number of times): warps of one CTA then execute the same few hundred
+// instructions at any time, which keeps the kernel's ~100 KB of code from thrashing the 32 KB instruction cache.
+template <int TL, int MODE, bool SYNCP>
+__device__ __forceinline__ int tail_row(const SplitParams& p, long long row, const SplitHeader& h, bool alive,
                                          const double* l1p, const TailStage& st, const ExpTab& tab, int lane) {
     const int S = p.S, M = p.M;
     // tile path: the tight list alone when it holds the tail and fits one sort, else both lists
@@ -1047,68 +1051,83 @@ __device__ __forceinline__ int tail_row(const SplitParams& p, long long row, con
     double* xs = st.xs;
     double* tb = st.tb;
     unsigned short* ss = st.ss;
-
     double* cx = st.gx;
     unsigned short* cs = st.gs;
-    DD nont;  // double-double: order-independent sum
     const bool total_body = p.total_body != 0;  // body = sum over all draws: nothing to add back for the non-tail candidates
-    if (C <= 32 * TL) nont = sort_and_stage<TL, TL>(C, CA, p.cap, !total_body, h.taux, st, tab, lane);
-    else nont = sort_and_stage<2 * TL, TL>(C, CA, p.cap, !total_body, h.taux, st, tab, lane);
-    if (!fix_runs<TL>(st, C, M, h.taux, lane)) return HO_RUNS;
-    // cutoff = (M+1)-th largest = element M of the order (psis.py:135-136); draws equal to it are
-    // not in the tail (psis.py:139)
-    const double xc = xs[M];
-    int n = M;
-    while (n > 0 && xs[n - 1] == xc) --n;
-    // heavy-tailed rows: the cutoff sits near / below log(DBL_MIN) and is clamped there (psis.py:136);
-    // the tail is then whatever lies above the clamp, and the table exp (no denormals) is not used
-    const bool deep = !(xc >= -690.0);
-    double c = xc;
-    if (deep) {
-        c = (xc > p.cutoffmin) ? xc : p.cutoffmin;
-        int cnt = 0;
-        for (int e = lane; e < M; e += 32) cnt += (xs[e] > c) ? 1 : 0;
-        n = warp_isum(cnt);  // the order is descending: these are the first n elements
-    }
-    // safety net: the order inside the tail must be exact (descending x, descending index on ties)
-    bool bad = false;
-    for (int e = lane; e + 1 < n; e += 32) {
-        const double a = xs[e], b = xs[e + 1];
-        if (!(a > b || (a == b && ss[e] > ss[e + 1]))) bad = true;
-    }
-    if (__any_sync(FULL, bad)) return HO_ORDER;
+    int why = alive ? 0 : -1;
+    DD nont = {0.0, 0.0};  // double-double: order-independent sum
 
-    if (p.tail_idx) {  // the tail's draw indices (the first n elements of the order), the rest -1
-        int* d = p.tail_idx + row * p.tail_ld;
-        for (int e = lane; e < (int)p.tail_ld; e += 32) d[e] = (e < n) ? (int)ss[e] : -1;
+    // ---------------- phase 1: sort the candidates, stage the head of the order, exact order inside key runs
+    if (!why) {
+        if (C <= 32 * TL) nont = sort_and_stage<TL, TL>(C, CA, p.cap, !total_body, h.taux, st, tab, lane);
+        else nont = sort_and_stage<2 * TL, TL>(C, CA, p.cap, !total_body, h.taux, st, tab, lane);
+        if (!fix_runs<TL>(st, C, M, h.taux, lane)) why = HO_RUNS;
     }
-    const double exp_c = exp(c);  // psis.py:138
-    double tsum = 0.0, traw = 0.0;
-    if (!deep) {
-        // staged candidates at or below the cutoff belong to the normaliser's body too
-#pragma unroll 1
-        if (!total_body)
-            for (int e = n + lane; e < min(C, 32 * TL); e += 32) dd_add(nont, exp_tab(xs[e], tab));
-        // t_i = exp(x_i) - exp(c) (psis.py:146-147), descending
-#pragma unroll 1
-        for (int e = lane; e < n; e += 32) {
-            const double ex = exp_tab(xs[e], tab);  // x >= c >= -690
-            const double ti = ex - exp_c;
-            tb[e] = ti;
-            tsum += ti;
-            traw += ex;
+    if (SYNCP) __syncthreads();
+
+    // ---------------- phase 2: cutoff, tail, t_i
+    double xc = 0.0, c = 0.0, exp_c = 0.0, tsum = 0.0, traw = 0.0, nont_sum = 0.0;
+    int n = 0;
+    bool deep = false;
+    if (!why) {
+        // cutoff = (M+1)-th largest = element M of the order (psis.py:135-136); draws equal to it are
+        // not in the tail (psis.py:139)
+        xc = xs[M];
+        n = M;
+        while (n > 0 && xs[n - 1] == xc) --n;
+        // heavy-tailed rows: the cutoff sits near / below log(DBL_MIN) and is clamped there (psis.py:136);
+        // the tail is then whatever lies above the clamp, and the table exp (no denormals) is not used
+        deep = !(xc >= -690.0);
+        c = xc;
+        if (deep) {
+            c = (xc > p.cutoffmin) ? xc : p.cutoffmin;
+            int cnt = 0;
+            for (int e = lane; e < M; e += 32) cnt += (xs[e] > c) ? 1 : 0;
+            n = warp_isum(cnt);  // the order is descending: these are the first n elements
         }
-    } else {
-        tail_t_literal(xs, tb, n, total_body ? n : min(C, 32 * TL), exp_c, lane, nont, tsum, traw);
+        // safety net: the order inside the tail must be exact (descending x, descending index on ties)
+        bool bad = false;
+        for (int e = lane; e + 1 < n; e += 32) {
+            const double a = xs[e], b = xs[e + 1];
+            if (!(a > b || (a == b && ss[e] > ss[e + 1]))) bad = true;
+        }
+        if (__any_sync(FULL, bad)) why = HO_ORDER;
     }
-    tsum = warp_sum(tsum);
-    traw = warp_sum(traw);
-    const double nont_sum = warp_dd_sum(nont);
-    __syncwarp();
+    if (!why) {
+        if (p.tail_idx) {  // the tail's draw indices (the first n elements of the order), the rest -1
+            int* d = p.tail_idx + row * p.tail_ld;
+            for (int e = lane; e < (int)p.tail_ld; e += 32) d[e] = (e < n) ? (int)ss[e] : -1;
+        }
+        exp_c = exp_any(c);  // psis.py:138
+        if (!deep) {
+            // staged candidates at or below the cutoff belong to the normaliser's body too
+            if (!total_body) {
+#pragma unroll 1
+                for (int e = n + lane; e < min(C, 32 * TL); e += 32) dd_add(nont, exp_tab(xs[e], tab));
+            }
+            // t_i = exp(x_i) - exp(c) (psis.py:146-147), descending
+#pragma unroll 1
+            for (int e = lane; e < n; e += 32) {
+                const double ex = exp_tab(xs[e], tab);  // x >= c >= -690
+                const double ti = ex - exp_c;
+                tb[e] = ti;
+                tsum += ti;
+                traw += ex;
+            }
+        } else {
+            tail_t_literal(xs, tb, n, total_body ? n : min(C, 32 * TL), exp_c, lane, nont, tsum, traw);
+        }
+        tsum = warp_sum(tsum);
+        traw = warp_sum(traw);
+        nont_sum = total_body ? 0.0 : warp_dd_sum(nont);
+        __syncwarp();
+    }
+    if (SYNCP) __syncthreads();
 
+    // ---------------- phase 3: Zhang-Stephens fit of the tail
     double kk = inf_f64(), sigma = nan_f64();
     bool smooth = false;
-    if (n > 4) {
+    if (!why && n > 4) {
         int m = p.m_full;
         if (n != M) {
             m = (int)sqrt((double)n);
@@ -1116,10 +1135,13 @@ __device__ __forceinline__ int tail_row(const SplitParams& p, long long row, con
             while ((m + 1) * (m + 1) <= n) ++m;
             m += 30;
         }
-        const int why = gpdfit_warp(tb, n, m, tsum, lane, tab, kk, sigma);
-        if (why) return why;
-        smooth = is_finite(kk);  // psis.py:150
+        why = gpdfit_warp(tb, n, m, tsum, lane, tab, kk, sigma);
+        smooth = !why && is_finite(kk);  // psis.py:150
     }
+    if (SYNCP) __syncthreads();
+
+    // ---------------- phase 4: smoothed tail, normaliser, outputs
+    if (why) return why;
     // smoothed tail (psis.py:153-157, _gpinv :211-222); element e has ascending rank n-1-e.
     // The smoothed values replace t in shared memory.
     double tails = traw;
@@ -1184,13 +1206,13 @@ __device__ __forceinline__ int tail_row(const SplitParams& p, long long row, con
             dmax = warp_max_sel(dm);
             double e2 = 0.0;
 #pragma unroll 1
-            for (int e = lane; e < n; e += 32) e2 += exp((tb[e] - xs[e]) - dmax);
+            for (int e = lane; e < n; e += 32) e2 += exp_any((tb[e] - xs[e]) - dmax);
             es = warp_sum(e2);
         }
-        const double tot = (double)(S - n) * exp(-dmax) + es;
-        const double elpd = ((-mx - lse) + dmax) + log(tot);
-        const double lppd = log(h.lsum) + (h.lshift - log((double)S));  // utils.py:352-357, b_inv = S
-        const double var = h.vsum / (double)S;                          // waic.py:145
+        const double tot = (double)(S - n) * exp_any(-dmax) + es;
+        const double elpd = ((-mx - lse) + dmax) + log_slow(tot);
+        const double lppd = log_slow(h.lsum) + (h.lshift - p.log_S);  // utils.py:352-357, b_inv = S
+        const double var = h.vsum / (double)S;                        // waic.py:145
         if (lane == 0) {
             p.k_out[row] = kk;
             p.elpd_i[row] = elpd;
@@ -1207,13 +1229,15 @@ __device__ __forceinline__ int tail_row(const SplitParams& p, long long row, con
     return 0;
 }
 
-template <int TL>
-constexpr int tail_min_blocks() { return TL <= 8 ? 8 : 3; }
+// warps per CTA: 4 (eight CTAs per SM, every warp on its own) or 16 / 32 with the phase barriers of tail_row
+__host__ __device__ constexpr int tail_ctas_per_sm(int warps) { return warps >= 32 ? 1 : 32 / warps; }
 
-template <int TL, int MODE>
-__global__ void __launch_bounds__(TAIL_WARPS * 32, tail_min_blocks<TL>()) psis_tail_kernel(const SplitParams p) {
+template <int TL, int MODE, int W>
+__global__ void __launch_bounds__(W * 32, (TL <= 8) ? tail_ctas_per_sm(W) : (W <= 4 ? 3 : 1))
+psis_tail_kernel(const SplitParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const TailSmem L = tail_smem(p.M, TL, TAIL_WARPS);
+    constexpr bool SYNCP = W > 4;
+    const TailSmem L = tail_smem(p.M, TL, W);
     double* l1p = reinterpret_cast<double*>(smem_raw + L.off_l1p);
     const int lane = threadIdx.x & 31;
     // broadcast: lets the compiler see that everything derived from the warp index (row, header, branch
@@ -1236,17 +1260,23 @@ __global__ void __launch_bounds__(TAIL_WARPS * 32, tail_min_blocks<TL>()) psis_t
     }
     if (threadIdx.x < 64) log_tab_init(tabm + 64, threadIdx.x);
     // per-CTA table for the smoothing step: depends only on (rank, M), psis.py:153 + :221
-    for (int i = threadIdx.x; i < p.M; i += TAIL_WARPS * 32) l1p[i] = log1p(-(((double)i + 0.5) / (double)p.M));
+    for (int i = threadIdx.x; i < p.M; i += W * 32) l1p[i] = log1p(-(((double)i + 0.5) / (double)p.M));
     __syncthreads();
-    const long long nwarps = (long long)gridDim.x * TAIL_WARPS;
+    const long long step = (long long)gridDim.x * W;
 #pragma unroll 1
-    for (long long row = (long long)blockIdx.x * TAIL_WARPS + wid; row < p.n_rows; row += nwarps) {
-        const SplitHeader h = p.hdr[row];
-        if (h.flags) continue;
-        st.gx = p.cx + (size_t)row * (size_t)p.cap;
-        st.gs = p.cs + (size_t)row * (size_t)p.cap;
-        const int why = tail_row<TL, MODE>(p, row, h, l1p, st, tab, lane);
-        if (why && lane == 0) {
+    for (long long base = (long long)blockIdx.x * W; base < p.n_rows; base += step) {  // (CTA-uniform trip count)
+        const long long row = base + wid;
+        bool alive = row < p.n_rows;
+        SplitHeader h;
+        if (alive) h = p.hdr[row];
+        else { h.C = 0; h.C2 = 0; h.flags = 1; h.mx = 0.0; h.taux = 0.0; h.body = 0.0; h.lsum = 1.0; h.vsum = 0.0; h.lshift = 0.0; h.attempts = 0; }
+        if (h.flags) alive = false;
+        if (alive) {
+            st.gx = p.cx + (size_t)row * (size_t)p.cap;
+            st.gs = p.cs + (size_t)row * (size_t)p.cap;
+        }
+        const int why = tail_row<TL, MODE, SYNCP>(p, row, h, alive, l1p, st, tab, lane);
+        if (why > 0 && lane == 0) {
             note_handover(why);
             p.hdr[row].flags = 1;  // the apply kernel skips the row
             p.fb_list[atomicAdd(p.fb_count, 1)] = (int)(p.row_base + row);

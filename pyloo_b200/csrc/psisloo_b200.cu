@@ -210,7 +210,7 @@ static int launch_rows(int mode, const RowPlan& pl, RowParams rp, cudaStream_t s
 // stream kernel (one CTA per observation, row in registers) + tail kernel (one warp per observation)
 // + the general row kernel on the rows those two hand over.  See b2l_split.cuh.
 struct SplitPlan {
-    int ok, nt, ept, tl, cap, q0, nbuf, fused, a_chunk, grid1, grid2, occ1, occ2;
+    int ok, nt, ept, tl, tw, cap, q0, nbuf, fused, a_chunk, grid1, grid2, occ1, occ2;  // tw: warps per tail CTA
     size_t smem1, smem2;
     long long batch;  // observations per stream -> tail -> fallback round
 };
@@ -252,7 +252,13 @@ static bool split_shape(long long S, int M, long long n_rows, SplitPlan* sp) {
     sp->nbuf = 2;
     if (const char* ev = getenv("B2L_SNBUF")) sp->nbuf = (atoi(ev) == 1) ? 1 : sp->nbuf;
     sp->smem1 = stream_smem((int)S, sp->nt * sp->ept, 1, 0).total;  // refined per mode in plan_split
-    sp->smem2 = tail_smem(M, sp->tl, TAIL_WARPS).total;
+    // warps per tail CTA: big CTAs whose warps pass through the phases of a row together (see tail_row)
+    sp->tw = 16;  // (measured at S = 4000, M = 190: 4 warps 1.61 ms, 16 warps 1.40 ms, 32 warps 1.45 ms per 75 776 observations)
+    if (const char* ev = getenv("B2L_TAIL_WARPS")) {
+        const int w = atoi(ev);
+        if (w == 4 || w == 16 || (w == 32 && sp->tl <= 8)) sp->tw = w;
+    }
+    sp->smem2 = tail_smem(M, sp->tl, sp->tw).total;
     return true;
 }
 
@@ -288,7 +294,7 @@ static int plan_split(long long S, int M, int mode, long long n_rows, SplitPlan*
         int occ = 0;
         CK(split_stream_setup(nt, ept, mode, sp->smem1, &occ));  // leave the chosen size as the function attribute
     }
-    CK(split_tail_setup(sp->tl, mode, sp->smem2, &sp->occ2));
+    CK(split_tail_setup(sp->tl, sp->tw, mode, sp->smem2, &sp->occ2));
     if (sp->occ1 < 1 || sp->occ2 < 1) return 0;
     sp->grid1 = sms * sp->occ1;
     sp->grid2 = sms * sp->occ2;
@@ -348,6 +354,7 @@ static int launch_split(int mode, const RowPlan& pl, const SplitPlan& sp, const 
         q.n_rows = nb; q.S = rp.S; q.M = rp.M; q.cap = sp.cap; q.nbuf = sp.nbuf; q.q0 = sp.q0; q.m_full = 30 + msq;
         q.cutoffmin = rp.cutoffmin; q.counters = rp.counters; q.hdr = hdr[slot]; q.cx = cx[slot]; q.cs = cs[slot];
         q.fb_list = fb_list; q.fb_count = fb_count; q.row_base = i0; q.a_chunk = sp.a_chunk;
+        q.log_S = std::log((double)rp.S);
         q.tail_idx = rp.tail_idx ? rp.tail_idx + i0 * rp.tail_ld : nullptr; q.tail_ld = rp.tail_ld;
         if (sp.fused && prev_rows > 0) {  // the previous batch's apply stage rides along
             q.a_in = prev.in; q.a_out = prev.out; q.a_hdr = prev.hdr; q.a_cx = prev.cx; q.a_cs = prev.cs;
@@ -363,10 +370,10 @@ static int launch_split(int mode, const RowPlan& pl, const SplitPlan& sp, const 
             CK(split_stream_launch(sp.nt, sp.ept, mode, g1, sp.smem1, st, q));
         }
         if (nb > 0) {
-            const int g2 = (int)std::min<long long>(sp.grid2, (nb + TAIL_WARPS - 1) / TAIL_WARPS);
+            const int g2 = (int)std::min<long long>(sp.grid2, (nb + sp.tw - 1) / sp.tw);
             {
                 ProfScope prof(B2L_PROF_TAIL, st);
-                CK(split_tail_launch(sp.tl, mode, g2, sp.smem2, st, q));
+                CK(split_tail_launch(sp.tl, sp.tw, mode, g2, sp.smem2, st, q));
             }
             if (mode == MODE_PSISLW && !sp.fused) {
                 ProfScope prof(B2L_PROF_APPLY, st);
@@ -467,12 +474,12 @@ static int launch_tiles(const RowPlan& pl, const SplitPlan& sp, const TilePlan& 
         q.lppdw_i = rp.lppdw_i + i0; q.diag = rp.diag ? rp.diag + i0 * DIAG_STRIDE : nullptr;
         q.n_rows = nb; q.S = (int)S; q.M = rp.M; q.cap = sp.cap; q.m_full = 30 + msq; q.cutoffmin = rp.cutoffmin;
         q.counters = rp.counters; q.hdr = hdr; q.cx = cx; q.cs = cs; q.fb_list = fb_list; q.fb_count = fb_count;
-        q.row_base = i0; q.total_body = 1; q.ab_lists = 1;
+        q.row_base = i0; q.total_body = 1; q.ab_lists = 1; q.log_S = std::log((double)S);
         q.tail_idx = rp.tail_idx ? rp.tail_idx + i0 * rp.tail_ld : nullptr; q.tail_ld = rp.tail_ld;
         if (tq.debug & ~1) continue;  // measurement aids that leave no valid results: the tile kernel alone
-        const int g2 = (int)std::min<long long>(sp.grid2, (nb + TAIL_WARPS - 1) / TAIL_WARPS);
+        const int g2 = (int)std::min<long long>(sp.grid2, (nb + sp.tw - 1) / sp.tw);
         ProfScope prof(B2L_PROF_TAIL, st);
-        CK(split_tail_launch(sp.tl, MODE_LOO, g2, sp.smem2, st, q));
+        CK(split_tail_launch(sp.tl, sp.tw, MODE_LOO, g2, sp.smem2, st, q));
     }
     // observations handed over: the general kernel reads their columns where they lie
     RowParams r = rp;
