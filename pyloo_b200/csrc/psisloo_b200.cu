@@ -612,11 +612,18 @@ __global__ void __launch_bounds__(256) stats_partial_kernel(const double* elpd, 
         partial[blockIdx.x] = t;
     }
 }
-__global__ void stats_final_kernel(const StatAcc* partial, int nparts,
-                                   const unsigned long long* counters, double* out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    StatAcc t = partial[0];
-    for (int i = 1; i < nparts; ++i) t = stat_merge(t, partial[i]);
+// stage 2: one warp merges the block partials in a fixed tree (lane l takes partials l, l + 32, ... in order, then
+// a shuffle tree over the lanes): deterministic, and ~5 merge steps deep instead of a 148-step serial chain
+__global__ void __launch_bounds__(32) stats_final_kernel(const StatAcc* partial, int nparts,
+                                                         const unsigned long long* counters, double* out) {
+    const int lane = threadIdx.x;
+    StatAcc t = stat_zero();
+    for (int i = lane; i < nparts; i += 32) t = stat_merge(t, partial[i]);
+    for (int o = 16; o > 0; o >>= 1) {
+        StatAcc b = stat_shfl_xor(t, o);
+        t = stat_merge(t, b);  // lanes >= o hold garbage merges; lane 0 holds the tree result
+    }
+    if (lane != 0) return;
     for (int i = 0; i < B2L_STATS_LEN; ++i) out[i] = 0.0;
     out[B2L_ST_N] = t.e.n; out[B2L_ST_ELPD_MEAN] = t.e.mean; out[B2L_ST_ELPD_M2] = t.e.m2;
     out[B2L_ST_ELPD_SUM] = t.esum; out[B2L_ST_LPPD_SUM] = t.lsum; out[B2L_ST_PWAIC_SUM] = t.psum;
