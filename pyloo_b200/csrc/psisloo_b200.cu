@@ -1411,7 +1411,9 @@ extern "C" int b2l_loo_host_f64(const double* ll, int64_t S, int64_t N, int64_t 
                                           : default_chunk(S, N);
     size_t wsb = 0;
     b2l_workspace_bytes(S, chunk, M, rows_in ? 0 : 1, &wsb);
-    const size_t mat = align_up((size_t)chunk * (size_t)S * 8, 256);
+    // device pitch of a chunk of the (S, N) layout: even, so that an odd last chunk still meets the 16-byte pitch
+    // rule of the 2-D TMA tiles (the tile path) -- the pad column is never read
+    const size_t mat = align_up((size_t)(chunk + 1) * (size_t)S * 8, 256);
     const size_t vec = align_up((size_t)chunk * 8, 256);
     const size_t need = mat + 5 * vec + 512 + wsb + 1024;
     const bool bounce = N > 0 && host_pageable(ll);
@@ -1436,7 +1438,8 @@ extern "C" int b2l_loo_host_f64(const double* ll, int64_t S, int64_t N, int64_t 
         const long long nc = std::min<long long>(chunk, N - i0);
         Slot& sl = cx.slot[ci % NSLOT];
         Carve cv(sl.buf);
-        double* d_in = cv.take<double>((size_t)chunk * S);
+        double* d_in = cv.take<double>((size_t)(chunk + 1) * S);
+        const long long pitch = rows_in ? nc : ((nc > 1) ? ((nc + 1) & ~1ll) : nc);
         double* d_e = cv.take<double>((size_t)chunk);
         double* d_k = cv.take<double>((size_t)chunk);
         double* d_l = cv.take<double>((size_t)chunk);
@@ -1451,17 +1454,17 @@ extern "C" int b2l_loo_host_f64(const double* ll, int64_t S, int64_t N, int64_t 
             CK(cudaStreamSynchronize(sl.st));
             if (rows_in) par_copy_2d((char*)sl.hin, (size_t)S * 8, (const char*)(ll + i0 * stride_n), (size_t)stride_n * 8,
                                      (size_t)S * 8, nc);
-            else par_copy_2d((char*)sl.hin, (size_t)nc * 8, (const char*)(ll + i0), (size_t)stride_s * 8, (size_t)nc * 8, S);
-            CK(cudaMemcpyAsync(d_in, sl.hin, (size_t)nc * S * 8, cudaMemcpyHostToDevice, sl.st));
-            if (rows_in) { dss = 1; dsn = S; } else { dss = nc; dsn = 1; }
+            else par_copy_2d((char*)sl.hin, (size_t)pitch * 8, (const char*)(ll + i0), (size_t)stride_s * 8, (size_t)nc * 8, S);
+            CK(cudaMemcpyAsync(d_in, sl.hin, (size_t)(rows_in ? nc : pitch) * S * 8, cudaMemcpyHostToDevice, sl.st));
+            if (rows_in) { dss = 1; dsn = S; } else { dss = pitch; dsn = 1; }
         } else if (rows_in) {
             CK(cudaMemcpy2DAsync(d_in, (size_t)S * 8, ll + i0 * stride_n, (size_t)stride_n * 8,
                                  (size_t)S * 8, (size_t)nc, cudaMemcpyHostToDevice, sl.st));
             dss = 1; dsn = S;
         } else {
-            CK(cudaMemcpy2DAsync(d_in, (size_t)nc * 8, ll + i0, (size_t)stride_s * 8, (size_t)nc * 8,
+            CK(cudaMemcpy2DAsync(d_in, (size_t)pitch * 8, ll + i0, (size_t)stride_s * 8, (size_t)nc * 8,
                                  (size_t)S, cudaMemcpyHostToDevice, sl.st));
-            dss = nc; dsn = 1;
+            dss = pitch; dsn = 1;
         }
         CK(cudaMemsetAsync(d_cnt, 0, 4 * sizeof(unsigned long long), sl.st));
         int rc = b2l_loo_dev_f64(d_in, S, nc, dss, dsn, M, cutoffmin, flags, d_e, d_k, d_l, d_v, d_lw, d_cnt,

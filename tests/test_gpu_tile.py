@@ -298,3 +298,27 @@ def test_tail_index_sets_are_bit_exact(name, path, monkeypatch):
         got = row[row >= 0]
         assert len(got) == len(set(got.tolist()))            # no draw twice
         assert set(got.tolist()) == want[i], i
+
+
+def test_host_loo_with_an_odd_number_of_observations_takes_the_tile_path():
+    """ArviZ data has any N.  The host entry pads the device pitch of its chunks to an even number of doubles (the
+    2-D TMA tiles need a 16-byte pitch), so an odd N -- and odd chunks -- still run the tile kernel."""
+    rng = np.random.default_rng(41)
+    S, N = 2000, 701
+    ll = -1.4 + rng.normal(size=(S, N)) * rng.uniform(0.5, 1.5, size=(1, N))
+    engine.profile(True)
+    r = engine.loo_host(ll, 1.0, device=0, chunk_obs=333)       # chunks of 333, 333, 35 observations
+    prof = engine.profile_read()
+    engine.profile(False)
+    assert prof["transpose"][1] == 0 and prof["stream"][1] == 3 and prof["tail"][1] == 3
+    pw = orc.loo_pointwise(ll, 1.0)
+    ww = orc.waic_pointwise(ll)
+    close(r["elpd_i"], pw["elpd_i"])
+    close(r["pareto_k"], pw["pareto_k"], atol=1e-13)
+    close(r["lppd_i"], pw["lppd_i"], atol=1e-13)
+    close(r["var_i"], ww["var_i"])
+    pinned = torch.empty((S, N), dtype=torch.float64, pin_memory=True)
+    pinned.copy_(torch.from_numpy(ll))
+    r2 = engine.loo_host(pinned.numpy(), 1.0, device=0, chunk_obs=333)
+    for key in ("elpd_i", "pareto_k", "lppd_i", "var_i"):
+        assert np.array_equal(r[key], r2[key])
