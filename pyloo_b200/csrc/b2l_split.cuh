@@ -764,8 +764,8 @@ __device__ __forceinline__ int gpdfit_warp(const double* t, int n, int m, double
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
         const bool live = (lane + 32 * r) < m;
-        const double kj = ks[r] * inv_n;
-        Lj[r] = live ? (double)n * (log_tab(-(b[r] / kj), ltab) - kj - 1.0) : -inf_f64();
+        const double kj = live ? ks[r] * inv_n : -1.0;
+        Lj[r] = live ? (double)n * (log_tab(-((live ? b[r] : 1.0) / kj), ltab) - kj - 1.0) : -inf_f64();
         if (live) {
             fin = fin && is_finite(Lj[r]);
             lm = (Lj[r] > lm) ? Lj[r] : lm;

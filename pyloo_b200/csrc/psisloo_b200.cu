@@ -253,10 +253,10 @@ static bool split_shape(long long S, int M, long long n_rows, SplitPlan* sp) {
     if (const char* ev = getenv("B2L_SNBUF")) sp->nbuf = (atoi(ev) == 1) ? 1 : sp->nbuf;
     sp->smem1 = stream_smem((int)S, sp->nt * sp->ept, 1, 0).total;  // refined per mode in plan_split
     // warps per tail CTA: big CTAs whose warps pass through the phases of a row together (see tail_row)
-    sp->tw = 16;  // (measured at S = 4000, M = 190: 4 warps 1.61 ms, 16 warps 1.40 ms, 32 warps 1.45 ms per 75 776 observations)
+    sp->tw = 8;  // (measured at S = 4000, M = 190, per 2 x 75 776 observations: 4 warps 1.61 ms, 8 warps 1.36 ms, 16 warps 1.40 ms, 32 warps 1.45 ms)
     if (const char* ev = getenv("B2L_TAIL_WARPS")) {
         const int w = atoi(ev);
-        if (w == 4 || w == 16 || (w == 32 && sp->tl <= 8)) sp->tw = w;
+        if (w == 4 || w == 8 || w == 16 || (w == 32 && sp->tl <= 8)) sp->tw = w;
     }
     sp->smem2 = tail_smem(M, sp->tl, sp->tw).total;
     return true;
