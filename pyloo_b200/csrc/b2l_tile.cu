@@ -276,19 +276,6 @@ __global__ void __launch_bounds__(16 * TW, 48 / TW) loo_tile_kernel(const __grid
     };
 
     long long t = cluster_id;
-    // Clusters that start together would stay in step -- all loading, then all computing, HBM and the SMs taking
-    // turns.  A start offset by thirds of a tile time keeps a third of the resident clusters loading at any time.
-    if (p.stagger_ns > 0) {
-        const unsigned wait_ns = (unsigned)(cluster_id % 3) * (unsigned)p.stagger_ns;
-        if (wait_ns) {
-            unsigned long long t0, t1;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-            do {
-                __nanosleep(256);
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            } while (t1 - t0 < wait_ns);
-        }
-    }
     if (tid == 0 && t < p.n_tiles) issue(t);
     int it = 0;
     for (; t < p.n_tiles; t += n_clusters, ++it) {

@@ -39,7 +39,6 @@ struct TileParams {
     int* fb_count;
     unsigned long long* counters;  // optional [4]; [3] += observations handed over
     long long row_base;
-    int stagger_ns;  // start offset between the three groups of clusters (0: none)
     int debug;  // measurement aids (B2L_TILE_DEBUG): 2 loads only, 4 no candidate pass, 8 no exp pass (2, 4, 8: no valid results)
 };
 
