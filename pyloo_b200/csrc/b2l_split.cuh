@@ -1233,7 +1233,7 @@ __device__ __forceinline__ int tail_row(const SplitParams& p, long long row, con
 __host__ __device__ constexpr int tail_ctas_per_sm(int warps) { return warps >= 32 ? 1 : 32 / warps; }
 
 template <int TL, int MODE, int W>
-__global__ void __launch_bounds__(W * 32, (TL <= 8) ? tail_ctas_per_sm(W) : (W <= 4 ? 3 : 1))
+__global__ void __launch_bounds__(W * 32, (TL <= 8) ? tail_ctas_per_sm(W) : (W <= 4 ? 3 : (W <= 8 ? 2 : 1)))
 psis_tail_kernel(const SplitParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr bool SYNCP = W > 4;

@@ -97,6 +97,21 @@ __device__ __forceinline__ void st_async_16(uint32_t dst, uint64_t a, uint64_t b
                  "l"(a), "l"(b), "r"(bar)
                  : "memory");
 }
+// wait for a phase completed by the peers' st.async stores: acquire at cluster scope, so that what the other
+// CTAs wrote into this CTA's shared memory is visible to the loads that follow
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAITC_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONEC_%=;\n\t"
+        "bra WAITC_%=;\n\t"
+        "DONEC_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -422,7 +437,7 @@ __global__ void __launch_bounds__(16 * TW, 48 / TW) loo_tile_kernel(const __grid
         }
 
         // ---------------- receive: column minimum, lower / upper median of the CTAs' thresholds
-        mbar_wait(&bar_x[w * 2 + par], xph);
+        mbar_wait_cluster(&bar_x[w * 2 + par], xph);
         double llmin, t_t, t_l;
         {
             const int r = slot & 7;  // lanes 8..15 of each half mirror lanes 0..7
@@ -534,7 +549,7 @@ __global__ void __launch_bounds__(16 * TW, 48 / TW) loo_tile_kernel(const __grid
         const uint32_t xph = (uint32_t)((it >> 1) & 1);
         if (lane == 0 && own_cols) mbar_expect_tx(&bar_x[w * 2 + par], (uint32_t)(own_cols * csize * 48));
         send_partials(par);
-        if (own_cols) mbar_wait(&bar_x[w * 2 + par], xph);
+        if (own_cols) mbar_wait_cluster(&bar_x[w * 2 + par], xph);
         write_header(t_prev, par, p_llmin, p_tl);
     }
     // (a CTA's shared memory must outlive the peers' last stores into it: every warp has waited for all it expects)
