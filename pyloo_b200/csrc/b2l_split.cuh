@@ -1175,8 +1175,10 @@ __device__ __forceinline__ int tail_row(const SplitParams& p, long long row, con
     // tile path: h.body is the sum over all S draws, so the body is what remains without the raw tail terms;
     // when the tail carries (almost) the whole sum the difference is rounding noise -- harmless as long as the
     // smoothed tail is of the same order, else the row goes to the general kernel
+    // (the total carries the table exponential's error, up to 4e-14 relative; the difference inherits it
+    // amplified by total / (body + tails), and 1e-3 keeps that below 4e-11 of the result)
     const double body = total_body ? h.body - traw : h.body + nont_sum;
-    if (total_body && !(body + tails > 1e-6 * h.body)) return HO_CANCEL;
+    if (total_body && !(body + tails > 1e-3 * h.body)) return HO_CANCEL;
     const double lse = log_tab(body + tails, tab.t + 64);  // psis.py:158
 
     if (MODE == MODE_PSISLW) {

@@ -130,6 +130,35 @@ def test_tile_path_heavy_tails():
     assert np.array_equal(r["pareto_k"] > 0.7, orc.loo_pointwise(ll, 1.0)["pareto_k"] > 0.7)
 
 
+@pytest.mark.parametrize("kind", ["t3", "ties", "two_chains", "scaled_t5", "few_values"])
+@pytest.mark.parametrize("seed", [1, 2])
+def test_tile_path_awkward_columns_vs_oracle(kind, seed):
+    """Random shapes with the distributions that stress the fast path: heavy tails whose raw tail carries nearly the
+    whole normaliser (the all-draw total minus the raw tail cancels -- such columns must be handed over before the
+    rounding of the total shows in elpd_i), exact ties at the cutoff, chains with different locations, columns with
+    a handful of distinct values."""
+    rng = np.random.default_rng(100 * seed + len(kind))
+    S = int(rng.integers(1024, 4097))
+    N = 2 * int(rng.integers(100, 300))
+    reff = float(rng.choice([1.0, 0.9, 0.8, 0.72]))
+    z = rng.normal(size=(S, N))
+    if kind == "t3":
+        z = rng.standard_t(3, size=(S, N))
+    elif kind == "ties":
+        z = np.round(z, 2)
+    elif kind == "two_chains":
+        z[: S // 2] += 0.8
+        z[S // 2:] *= 1.7
+    elif kind == "scaled_t5":
+        z = rng.standard_t(5, size=(S, N)) * rng.uniform(0.2, 4.0, size=(1, N))
+    elif kind == "few_values":
+        z = np.round(rng.standard_t(4, size=(S, N)), 1)
+        z[:, ::7] = np.floor(z[:, ::7])
+    ll = -1.4 + z
+    r = gpu_loo(ll, reff, want_diag=True)
+    check_against_oracle(ll, reff, r)
+
+
 def test_tile_path_autocorrelated_chains():
     """Four chains with different locations and strong autocorrelation: the CTAs of a cluster see different
     distributions (their draw segments are different chains); thresholds are medians over the CTAs."""
