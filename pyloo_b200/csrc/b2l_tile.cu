@@ -580,15 +580,22 @@ bool tile_shape(long long S, int M, int csize, int tw, TilePlan* tp) {
     // at or below the q-th smallest bin minimum of a CTA (lower / upper median over the CTAs) number about
     // K(q) = -0.9 B ln(1 - q / 32) with a spread of ~8 % (balls in bins; the 0.9 is measured).  Tight rank: K in
     // the middle of [M + 1, one sort of the tail kernel]; loose rank: K ~ 1.65 (M + 1), far from M + 1 and from cap.
+    // Long tails (M + 1 > 0.9 B: reff well below 1) need ranks near 32, where the count follows the harmonic form
+    // B (H_32 - H_(32 - q)) of the exponential order statistics, times 0.91 (lower median, tight) / 0.93 (upper
+    // median, loose) -- simulated: q = 28: 453 / 482, q = 31: 670 / 719 of 4000 draws, spread 8-9 %.  Rank 31 must
+    // still cover M + 1 with three spreads to spare.
     const double B = 32.0 * csize;
-    if ((double)(M + 1) > 0.9 * B) return false;
-    auto K_of = [&](int q) { return -0.9 * B * std::log(1.0 - (double)q / 32.0); };
+    auto h_of = [](int q) { double s = 0.0; for (int i = 32 - q + 1; i <= 32; ++i) s += 1.0 / i; return s; };
+    const bool long_tail = (double)(M + 1) > 0.9 * B;
+    if ((double)(M + 1) > 0.70 * 0.93 * B * h_of(31)) return false;
+    auto K_t = [&](int q) { return long_tail ? 0.91 * B * h_of(q) : -0.9 * B * std::log(1.0 - (double)q / 32.0); };
+    auto K_l = [&](int q) { return long_tail ? 0.93 * B * h_of(q) : -0.9 * B * std::log(1.0 - (double)q / 32.0); };
     const int tl = (M + 2 <= 128) ? 4 : ((M + 2 <= 256) ? 8 : 16);  // the tail kernel's registers per lane (split_shape)
     const double want_t = 0.5 * ((double)(M + 1) + 32.0 * tl), want_l = std::min(1.65 * (M + 1), 0.8 * 64.0 * tl);
     int qt = 1, ql = 1;
     for (int q = 1; q <= 31; ++q) {
-        if (std::fabs(K_of(q) - want_t) < std::fabs(K_of(qt) - want_t)) qt = q;
-        if (std::fabs(K_of(q) - want_l) < std::fabs(K_of(ql) - want_l)) ql = q;
+        if (std::fabs(K_t(q) - want_t) < std::fabs(K_t(qt) - want_t)) qt = q;
+        if (std::fabs(K_l(q) - want_l) < std::fabs(K_l(ql) - want_l)) ql = q;
     }
     if (const char* ev = getenv("B2L_TILE_QT")) qt = atoi(ev);
     if (const char* ev = getenv("B2L_TILE_QL")) ql = atoi(ev);

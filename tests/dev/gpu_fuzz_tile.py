@@ -13,7 +13,7 @@ fails = []
 for case in range(n_cases):
     S = int(rng.integers(1024, 4097))
     N = 2 * int(rng.integers(4, 1500))
-    reff = float(rng.choice([1.0, 0.9, 0.8, 0.72]))
+    reff = float(rng.choice([float(v) for v in os.environ.get("REFFS", "1.0,0.9,0.8,0.72").split(",")]))
     kind = case % 6
     z = rng.normal(size=(S, N))
     if kind == 1:

@@ -81,6 +81,26 @@ def test_tile_path_vs_oracle(S, N, reff, tw, monkeypatch):
     assert int(r["counters"][3]) == 0 and engine.handover_reasons() == {}   # nothing left the fast path
 
 
+@pytest.mark.parametrize("S,N,reff", [(4000, 300, 0.5), (4000, 200, 0.3), (4000, 120, 0.2), (2000, 100, 0.3),
+                                      (3000, 64, 0.16), (4096, 50, 0.15), (1100, 40, 0.25)])
+def test_tile_path_long_tails_vs_oracle(S, N, reff):
+    """Relative efficiencies well below 1 (what pl.loo derives from the ESS of a multi-chain posterior,
+    pyloo/loo.py:204-216): M = 3 sqrt(S / reff) grows to several hundred draws, more than one per threshold bin;
+    the tile path serves M + 2 <= 512 with threshold ranks near the top of the 32 bin minima."""
+    M = engine.tail_length(S, reff)
+    assert 230 <= M + 1 <= 511 or S < 4000
+    rng = np.random.default_rng(S + N)
+    ll = -1.4 + rng.normal(size=(S, N)) * rng.uniform(0.3, 2.0, size=(1, N))
+    engine.profile(True)
+    engine.handover_reasons()
+    r = gpu_loo(ll, reff, want_diag=True)
+    prof = engine.profile_read()
+    engine.profile(False)
+    check_against_oracle(ll, reff, r)
+    assert prof["transpose"][1] == 0 and prof["stream"][1] >= 1           # the cluster kernel, no panels
+    assert int(r["counters"][3]) <= max(1, N // 50), engine.handover_reasons(reset=False)
+
+
 def test_tile_path_runs_the_cluster_kernel():
     """The eligible shapes really take the tile kernel (per-kernel timers: no transpose launch)."""
     rng = np.random.default_rng(3)
