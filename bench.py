@@ -501,6 +501,29 @@ def other_configs(args, torch, engine, dev, local, gen, peak, warmup):
         torch.cuda.synchronize()
         return ev0.elapsed_time(ev1) / steps, r
 
+    # ---- the headline path at the relative efficiencies pl.loo derives from a multi-chain posterior's ESS
+    # (pyloo/loo.py:204-216): M = 3 sqrt(S / reff) grows from 190 (reff 1) to 425 draws (reff 0.2)
+    S, n_rs = S_DRAWS, 148 * 64 * 8 * 2
+    llr = torch.randn(S, n_rs, dtype=torch.float64, device=dev, generator=gen) - 1.4
+    sweep = {}
+    for reff_ in (0.5, 0.3, 0.2):
+        wsr = engine.workspace_for(S, n_rs, reff_, True, dev)
+        engine.handover_reasons()
+        ms_, r_ = timed(lambda: engine.loo_cuda(llr, reff_, workspace=wsr), args.steps)
+        hand = engine.handover_reasons()
+        idx = torch.arange(0, n_rs, n_rs // 6, device=dev)[:6]
+        pw = orc.loo_pointwise(llr[:, idx].cpu().numpy(), reff_)
+        gbs = n_rs * (8 * S + 40) / (ms_ * 1e-3) / 1e9
+        sweep[f"reff_{reff_}"] = {"tail_length": engine.tail_length(S, reff_), "value": n_rs / (ms_ * 1e-3), "unit": "obs/s",
+                                  "ms_per_step": ms_, "path_frac": gbs / peak,
+                                  "handed_over_per_step": int(sum(hand.values())) // (args.steps + 3),
+                                  "max_rel_err_elpd_i_vs_oracle(6 obs)":
+                                      float(np.max(np.abs(r_["elpd_i"][idx].cpu().numpy() - pw["elpd_i"]) / np.abs(pw["elpd_i"])))}
+        del wsr, r_
+    out["loo_low_reff"] = {"workload": f"pl.loo S={S} x N={n_rs}, (S, N) layout, device resident, r_eff 0.5 / 0.3 / 0.2", **sweep}
+    del llr
+    torch.cuda.empty_cache()
+
     # ---- configs[1]: pl.psislw, S = 4000 x N = 100 000, r_eff = 0.9, rows contiguous
     S, N = S_DRAWS, N_PSISLW
     x = torch.randn(N, S, dtype=torch.float64, device=dev, generator=gen)
