@@ -563,7 +563,7 @@ bool tile_shape(long long S, int M, int csize, int tw, TilePlan* tp) {
     if (csize > tw) return false;
     tp->tw = tw;
     if (csize < 1 || csize > TILE_MAXC || (csize & (csize - 1)) != 0) return false;
-    if (S < 1024 || S > SPLIT_MAX_S) return false;
+    if (S < 512 || S > SPLIT_MAX_S) return false;
     const long long per = (S + csize - 1) / csize;  // draws a CTA owns
     if (per > TILE_MAX_R) return false;
     // boxes of the CTA's draws: <= 256 rows each, a multiple of 8 rows (every box starts on a 1024-byte swizzle
@@ -638,9 +638,21 @@ cudaError_t tile_plan(long long S, int M, TilePlan* tp) {
     // 8-observation tiles (64 B of a draw, 4 warps, 6 CTAs / SM) measure ~10 % faster than 16-observation ones
     // (128 B, 8 warps, 3 CTAs / SM): more, smaller CTAs hide each other's waits better
     int csize = TILE_MAXC, tw = 8;
-    if (const char* ev = getenv("B2L_TILE_CSIZE")) csize = atoi(ev);
     if (const char* ev = getenv("B2L_TILE_W")) tw = atoi(ev);
     if (const char* ev = getenv("B2L_TILE")) if (atoi(ev) == 0) { memset(tp, 0, sizeof(*tp)); return cudaSuccess; }
+    // Cluster size: the fewest CTAs that hold the draws of a tile (<= 512 each) -- short posteriors in clusters of
+    // 8 leave a thread 4 to 8 draws per pass and the per-tile exchange dominates (S = 1000, 606 208 observations:
+    // 5.08 ms with 8 CTAs, 3.45 ms with 4; S = 512: 4.69 / 2.85 / 1.93 ms with 8 / 4 / 2) -- as long as the
+    // thresholds stay reliable: medians over few CTAs of ranks near 32 are noisy (S = 1000 in clusters of 2,
+    // 1.5 tail draws per bin: 0.5 % of the columns handed over), so at most 1.2 tail draws per bin.
+    if (const char* ev = getenv("B2L_TILE_CSIZE")) {
+        csize = atoi(ev);
+    } else {
+        for (int c = 2; c <= TILE_MAXC; c <<= 1) {
+            TilePlan probe;
+            if (tile_shape(S, M, c, tw, &probe) && (double)(M + 1) <= 1.2 * 32.0 * c) { csize = c; break; }
+        }
+    }
     if (!tile_shape(S, M, csize, tw, tp)) return cudaSuccess;
     int dev = 0, smem_optin = 0;
     cudaError_t e = cudaGetDevice(&dev);

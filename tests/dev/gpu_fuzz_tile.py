@@ -11,7 +11,7 @@ n_cases = int(os.environ.get("CASES", 24))
 worst = {"elpd": 0.0, "k": 0.0, "lppd": 0.0, "var": 0.0}
 fails = []
 for case in range(n_cases):
-    S = int(rng.integers(1024, 4097))
+    S = 2 * int(rng.integers(256, 2049))
     N = 2 * int(rng.integers(4, 1500))
     reff = float(rng.choice([float(v) for v in os.environ.get("REFFS", "1.0,0.9,0.8,0.72").split(",")]))
     kind = case % 6

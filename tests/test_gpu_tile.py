@@ -101,6 +101,34 @@ def test_tile_path_long_tails_vs_oracle(S, N, reff):
     assert int(r["counters"][3]) <= max(1, N // 50), engine.handover_reasons(reset=False)
 
 
+@pytest.mark.parametrize("S,N,reff", [(512, 40, 1.0), (600, 30, 0.8), (1000, 200, 1.0), (1000, 64, 0.5), (1022, 18, 1.0),
+                                      (800, 50, 0.3)])
+def test_tile_path_short_posteriors_vs_oracle(S, N, reff):
+    """4 chains x 250 draws and the like: 64 to 128 draws per CTA of the cluster, 4 to 8 per thread."""
+    rng = np.random.default_rng(3 * S + N)
+    ll = -1.4 + rng.normal(size=(S, N)) * rng.uniform(0.3, 2.0, size=(1, N))
+    engine.profile(True)
+    engine.handover_reasons()
+    r = gpu_loo(ll, reff, want_diag=True)
+    prof = engine.profile_read()
+    engine.profile(False)
+    check_against_oracle(ll, reff, r)
+    assert prof["transpose"][1] == 0 and prof["stream"][1] >= 1
+    assert int(r["counters"][3]) <= max(1, N // 50), engine.handover_reasons(reset=False)
+
+
+@pytest.mark.parametrize("csize", ["2", "4", "8"])
+@pytest.mark.parametrize("S,N,reff", [(2000, 100, 1.0), (700, 60, 1.0)])
+def test_tile_path_cluster_sizes_vs_oracle(S, N, reff, csize, monkeypatch):
+    """The library picks the cluster size from S and M (2, 4 or 8 CTAs per tile); every size gives the oracle's
+    numbers (sums differ in rounding only, the tail set not at all)."""
+    monkeypatch.setenv("B2L_TILE_CSIZE", csize)
+    rng = np.random.default_rng(S + int(csize))
+    ll = -1.4 + rng.normal(size=(S, N)) * rng.uniform(0.3, 2.0, size=(1, N))
+    r = gpu_loo(ll, reff, want_diag=True)
+    check_against_oracle(ll, reff, r)
+
+
 def test_tile_path_runs_the_cluster_kernel():
     """The eligible shapes really take the tile kernel (per-kernel timers: no transpose launch)."""
     rng = np.random.default_rng(3)
