@@ -36,7 +36,7 @@ __device__ __forceinline__ void note_handover(int reason) { atomicAdd(&g_handove
 constexpr int KEY_IDX_BITS = 14;               // draw indices travel as 16-bit values: S <= 2^14
 constexpr int SPLIT_MAX_S = 1 << KEY_IDX_BITS;
 
-struct __align__(16) SplitHeader {  // 80 B per observation: stream kernel -> tail kernel -> apply kernel
+struct __align__(16) SplitHeader {  // 96 B per observation: stream kernel -> tail kernel -> apply kernel
     double mx;      // max_s r_s
     double body;    // sum of exp(x_s) over the draws that are NOT candidates
     double lsum;    // LOO: sum_s exp(ll_s - lshift)
@@ -50,8 +50,11 @@ struct __align__(16) SplitHeader {  // 80 B per observation: stream kernel -> ta
     int n_patch;    // tail kernel -> apply kernel: smoothed draws to patch in (0: none)
     int C2;         // tile path: candidates of the looser second list, stored from the END of the row's scratch
     int pad_;
+    double vmax;    // chunked tile path: every draw that is NOT a candidate has x < vmax (the largest of the chunks'
+                    // thresholds); the list holds the tail only if its (M + 1)-th largest x reaches vmax
+    double pad2_;
 };
-static_assert(sizeof(SplitHeader) == 80, "SplitHeader is 80 bytes");
+static_assert(sizeof(SplitHeader) == 96, "SplitHeader is 96 bytes");
 
 struct SplitParams {
     const double* in;      // row i = in + i * in_stride (PSISLW: r = log weight; LOO: ll, r = -ll)
@@ -91,6 +94,8 @@ struct SplitParams {
     // its end (only read when the tight list is shorter than M + 1 or longer than one sort)
     int total_body;
     int ab_lists;
+    int chunked;  // tile path, long posteriors: ONE list of raw r = -ll (x = fl(r - max r) is formed here, psis.py:134), valid only if
+                  // the cutoff reaches SplitHeader.vmax
     // optional [n_rows][tail_ld]: draw indices of the tail (psis.py:139-141), the rest -1 (evidence for tests)
     int* tail_idx;
     long long tail_ld;
@@ -936,8 +941,8 @@ __device__ __forceinline__ unsigned quant_key(double x, double taux) {
 // further down can never be in the tail: their exp goes straight to the normaliser (returned).
 // Equal quantised values leave a short run in unspecified order; fix_runs() orders it exactly.
 template <int CAPL, int TL>
-__device__ __forceinline__ DD sort_and_stage(int C, int CA, int cap, bool need_rest, double taux, const TailStage& st,
-                                             const ExpTab& tab, int lane) {
+__device__ __forceinline__ DD sort_and_stage(int C, int CA, int cap, bool need_rest, double taux, double xoff,
+                                             const TailStage& st, const ExpTab& tab, int lane) {
     constexpr int PB = (TL == 4) ? 8 : ((TL == 8) ? 9 : 10);  // bits of a candidate slot (cap = 64 TL)
     constexpr int QB = 32 - PB;
     // candidate e of the (tight ++ loose) order -> slot of the row's scratch: the tight list grows from the
@@ -947,7 +952,8 @@ __device__ __forceinline__ DD sort_and_stage(int C, int CA, int cap, bool need_r
 #pragma unroll
     for (int i = 0; i < CAPL; ++i) {
         const int e = 32 * i + lane;
-        k[i] = (e < C) ? ((quant_key<QB>(st.gx[slot_of(e)], taux) << PB) | (unsigned)e) : 0xffffffffu;
+        // (xoff: 0, or max r when the scratch holds raw r -- x - 0.0 is x, bit for bit)
+        k[i] = (e < C) ? ((quant_key<QB>(st.gx[slot_of(e)] - xoff, taux) << PB) | (unsigned)e) : 0xffffffffu;
     }
     warp_bitonic_sort32<CAPL>(k, lane);
     // exact value and draw index of every element of the order: gathered by slot from the row's scratch
@@ -958,11 +964,11 @@ __device__ __forceinline__ DD sort_and_stage(int C, int CA, int cap, bool need_r
         const int e = 32 * i + lane;
         const int pidx = slot_of((int)(k[i] & ((1u << PB) - 1u)));
         if (i < TL) {
-            st.xs[e] = (e < C) ? st.gx[pidx] : -inf_f64();
+            st.xs[e] = (e < C) ? st.gx[pidx] - xoff : -inf_f64();
             st.ss[e] = (e < C) ? st.gs[pidx] : (unsigned short)0;
         } else if (need_rest && 32 * i < C) {
             if (e < C) {
-                const double x = st.gx[pidx];
+                const double x = st.gx[pidx] - xoff;
                 if (x >= -700.0) dd_add(rest, exp_tab(x, tab));
             }
         }
@@ -1059,8 +1065,9 @@ __device__ __forceinline__ int tail_row(const SplitParams& p, long long row, con
 
     // ---------------- phase 1: sort the candidates, stage the head of the order, exact order inside key runs
     if (!why) {
-        if (C <= 32 * TL) nont = sort_and_stage<TL, TL>(C, CA, p.cap, !total_body, h.taux, st, tab, lane);
-        else nont = sort_and_stage<2 * TL, TL>(C, CA, p.cap, !total_body, h.taux, st, tab, lane);
+        const double xoff = p.chunked ? mx : 0.0;
+        if (C <= 32 * TL) nont = sort_and_stage<TL, TL>(C, CA, p.cap, !total_body, h.taux, xoff, st, tab, lane);
+        else nont = sort_and_stage<2 * TL, TL>(C, CA, p.cap, !total_body, h.taux, xoff, st, tab, lane);
         if (!fix_runs<TL>(st, C, M, h.taux, lane)) why = HO_RUNS;
     }
     if (SYNCP) __syncthreads();
@@ -1073,6 +1080,9 @@ __device__ __forceinline__ int tail_row(const SplitParams& p, long long row, con
         // cutoff = (M+1)-th largest = element M of the order (psis.py:135-136); draws equal to it are
         // not in the tail (psis.py:139)
         xc = xs[M];
+        // chunked lists are unions of per-chunk threshold sets: they hold the column's M + 1 largest only if none of
+        // the draws left out (x <= vmax) can exceed the cutoff found
+        if (p.chunked && !(xc >= h.vmax)) why = HO_RETRY;
         n = M;
         while (n > 0 && xs[n - 1] == xc) --n;
         // heavy-tailed rows: the cutoff sits near / below log(DBL_MIN) and is clamped there (psis.py:136);

@@ -163,7 +163,9 @@ __device__ __forceinline__ void half_sort32_f(float& a, float& b, int slot) {
 }
 
 // ---------------------------------------------------------------- the kernel
-template <int TW>  // observations per tile: 16 (128 B of a draw, 8 warps, 3 CTAs / SM) or 8 (64 B, 4 warps, 6 CTAs / SM)
+// TW: observations per tile: 16 (128 B of a draw, 8 warps, 3 CTAs / SM) or 8 (64 B, 4 warps, 6 CTAs / SM)
+// CHUNKED: work units are (tile, chunk) pairs (a separate build: the plain one carries none of its bookkeeping)
+template <int TW, bool CHUNKED>
 __global__ void __launch_bounds__(16 * TW, 48 / TW) loo_tile_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                     const TileParams p) {
     constexpr int NW = TW / 2;       // warps: two columns each
@@ -208,11 +210,17 @@ __global__ void __launch_bounds__(16 * TW, 48 / TW) loo_tile_kernel(const __grid
     __syncthreads();
     cluster_sync_all();  // every CTA of the cluster runs and has its barriers initialised
 
-    auto issue = [&](long long t) {  // one thread: the CTA's draws of tile t, nbox boxes on one mbarrier
+    // work unit u = tile * n_chunks + chunk (n_chunks = 1 unless the draw axis is longer than one cluster holds):
+    // S is then the chunk length and the unit's draws start at row chunk * S of the matrix
+    const int nch = CHUNKED ? p.n_chunks : 1;
+    const long long n_units = p.n_tiles * nch;
+    auto issue = [&](long long u) {  // one thread: the CTA's draws of unit u, nbox boxes on one mbarrier
+        const unsigned tl_ = (unsigned)u / (unsigned)nch;  // (a round has far fewer than 2^31 units)
+        const int ch = (int)((unsigned)u - tl_ * (unsigned)nch);
         mbar_expect_tx(bar_full, tile_tx);
         for (int b = 0; b < p.nbox; ++b)
-            tma_load_2d(tile + (size_t)b * p.box_rows * TW, &tmap, (int)(p.col0 + t * TW),
-                        row0 + b * p.box_rows, bar_full);
+            tma_load_2d(tile + (size_t)b * p.box_rows * TW, &tmap, (int)(p.col0 + (long long)tl_ * TW),
+                        ch * S + row0 + b * p.box_rows, bar_full);
     };
     // this thread's draws: row 16 k + slot; the warp's 16-byte chunk w of the row sits at chunk w ^ (row & 7)
     // (128-byte rows, 128-byte swizzle) or w ^ ((row >> 1) & 3) (64-byte rows, 64-byte swizzle); half hf of the chunk
@@ -229,7 +237,7 @@ __global__ void __launch_bounds__(16 * TW, 48 / TW) loo_tile_kernel(const __grid
     long long t_prev = -1;
 
     // the owner's share of the exchange: rescale and add the CTAs' partial sums, write the header
-    auto write_header = [&](long long tt, int par, double llmin_, double tl_) {
+    auto write_header = [&](long long tt, int par, double llmin_, double tl_v) {
         const int r = slot & 7;
         const bool have = own && r < csize;
         double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0, um = 0.0;
@@ -253,7 +261,16 @@ __global__ void __launch_bounds__(16 * TW, 48 / TW) loo_tile_kernel(const __grid
             q3 += __shfl_xor_sync(FULL, q3, o);
             um = fmax(um, __shfl_xor_sync(FULL, um, o));
         }
-        const long long oo = tt * TW + col;
+        const unsigned tl_ = (unsigned)tt / (unsigned)nch;
+        const long long oo = (long long)tl_ * TW + col;
+        if (nch > 1) {  // chunked: the raw record; tile_merge_kernel folds a column's chunks and decides
+            if (own && slot == 0 && oo < p.n_obs) {
+                ChunkHeader c;
+                c.llmin = llmin_; c.q0 = q0; c.q1 = q1; c.q2 = q2; c.q3 = q3; c.um = um; c.tl = tl_v; c.pad_ = 0.0;
+                p.chdr[oo * nch + ((unsigned)tt - tl_ * (unsigned)nch)] = c;
+            }
+            return;
+        }
         if (own && slot == 0 && oo < p.n_obs) {
             const int ca = (int)atomicAdd(&p.cnt[2 * oo], 0u), cb = (int)atomicAdd(&p.cnt[2 * oo + 1], 0u);
             const bool special = !(is_finite(q2) && is_finite(q3) && is_finite(q0) && is_finite(q1));
@@ -267,7 +284,7 @@ __global__ void __launch_bounds__(16 * TW, 48 / TW) loo_tile_kernel(const __grid
             h.vsum = q3 - q2 * q2 / (double)S;  // sum (ll - mean)^2 taken about the minimum
             if (h.vsum < 0.0) h.vsum = 0.0;
             h.lshift = llmin_;
-            h.taux = llmin_ - tl_;  // every candidate has ll <= t_l, i.e. x = fl(min ll - ll) >= taux
+            h.taux = llmin_ - tl_v;  // every candidate has ll <= t_l, i.e. x = fl(min ll - ll) >= taux
             h.lse = 0.0;
             h.C = ca; h.flags = ok ? 0 : 1; h.attempts = 0; h.n_patch = 0; h.C2 = cb; h.pad_ = 0;
             p.hdr[oo] = h;
@@ -290,10 +307,10 @@ __global__ void __launch_bounds__(16 * TW, 48 / TW) loo_tile_kernel(const __grid
         }
     };
 
-    long long t = cluster_id;
-    if (tid == 0 && t < p.n_tiles) issue(t);
+    long long t = cluster_id;  // (a work unit: a tile, or a (tile, chunk) pair)
+    if (tid == 0 && t < n_units) issue(t);
     int it = 0;
-    for (; t < p.n_tiles; t += n_clusters, ++it) {
+    for (; t < n_units; t += n_clusters, ++it) {
         const int par = it & 1;
         const uint32_t xph = (uint32_t)((it >> 1) & 1);
         if (lane == 0 && !(p.debug & 2))
@@ -302,7 +319,7 @@ __global__ void __launch_bounds__(16 * TW, 48 / TW) loo_tile_kernel(const __grid
         if (p.debug & 2) {  // measurement aid: the loads alone
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty);
-            if (tid == 0 && t + n_clusters < p.n_tiles) {
+            if (tid == 0 && t + n_clusters < n_units) {
                 mbar_wait(bar_empty, (uint32_t)(it & 1));
                 fence_proxy_async();
                 issue(t + n_clusters);
@@ -460,6 +477,7 @@ __global__ void __launch_bounds__(16 * TW, 48 / TW) loo_tile_kernel(const __grid
             const unsigned bl = __ballot_sync(FULL, have && rl == csize / 2) & mine;
             t_t = (double)__shfl_sync(FULL, st, __ffs(bt) - 1);
             t_l = (double)__shfl_sync(FULL, sl, __ffs(bl) - 1);
+            if (nch > 1) t_t = t_l;  // chunked: one list (a chunk's tight list alone proves nothing about the column)
             llmin = mn;
         }
         // the previous tile's header (its partial sums came with this exchange)
@@ -506,7 +524,9 @@ __global__ void __launch_bounds__(16 * TW, 48 / TW) loo_tile_kernel(const __grid
                 const unsigned v = __shfl_up_sync(FULL, inc, o, 16);
                 if (slot >= o) inc += v;
             }
-            const long long o = t * TW + col;
+            const unsigned tl_ = (unsigned)t / (unsigned)nch;
+            const int draw0 = (int)((unsigned)t - tl_ * (unsigned)nch) * S + row0;  // matrix row of this CTA's first draw
+            const long long o = (long long)tl_ * TW + col;
             unsigned baseA = 0, baseB = 0;
             if (slot == 15 && o < p.n_obs) {
                 if (inc & 0xffffu) baseA = atomicAdd(&p.cnt[2 * o], inc & 0xffffu);
@@ -524,8 +544,10 @@ __global__ void __launch_bounds__(16 * TW, 48 / TW) loo_tile_kernel(const __grid
                     const unsigned pos = isA ? posA++ : posB++;
                     if (pos < (unsigned)cap) {  // (an overflowing column is flagged by its owner and never read)
                         const unsigned sl_ = isA ? pos : (unsigned)cap - 1u - pos;
-                        dx[sl_] = llmin - pcol[b * KSTEP];  // x = fl(r - max r), exactly (psis.py:134)
-                        ds[sl_] = (unsigned short)(row0 + 16 * b + slot);
+                        // x = fl(r - max r), exactly (psis.py:134); chunked: r = -ll, the tail kernel subtracts max r
+                        const double v = pcol[b * KSTEP];
+                        dx[sl_] = (nch > 1) ? -v : llmin - v;
+                        ds[sl_] = (unsigned short)(draw0 + 16 * b + slot);
                     }
                 }
             }
@@ -533,7 +555,7 @@ __global__ void __launch_bounds__(16 * TW, 48 / TW) loo_tile_kernel(const __grid
         // this warp is done with the tile; the last one lets the producer refill it
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_empty);
-        if (tid == 0 && t + n_clusters < p.n_tiles) {
+        if (tid == 0 && t + n_clusters < n_units) {
             mbar_wait(bar_empty, (uint32_t)(it & 1));
             fence_proxy_async();
             issue(t + n_clusters);
@@ -557,13 +579,27 @@ __global__ void __launch_bounds__(16 * TW, 48 / TW) loo_tile_kernel(const __grid
 }
 
 // ---------------------------------------------------------------- host side
-bool tile_shape(long long S, int M, int csize, int tw, TilePlan* tp) {
+bool tile_shape(long long S_total, int M, int csize, int tw, TilePlan* tp) {
     memset(tp, 0, sizeof(*tp));
     if (tw != 8 && tw != 16) return false;
     if (csize > tw) return false;
     tp->tw = tw;
     if (csize < 1 || csize > TILE_MAXC || (csize & (csize - 1)) != 0) return false;
-    if (S < 512 || S > SPLIT_MAX_S) return false;
+    if (S_total < 512 || S_total > SPLIT_MAX_S) return false;
+    // a draw axis longer than one cluster holds (8 x 512) is cut into 2, 3 or 4 equal chunks
+    int nch = 1;
+    if (S_total > (long long)TILE_MAX_R * TILE_MAXC) {
+        nch = 0;
+        for (int c = 2; c <= 4 && !nch; ++c)
+            if (S_total % c == 0 && S_total / c <= (long long)TILE_MAX_R * TILE_MAXC) nch = c;
+        if (!nch) return false;
+    }
+    if (const char* ev = getenv("B2L_TILE_CHUNKS")) {  // (tests: chunked units on short posteriors)
+        const int c = atoi(ev);
+        if (c >= 1 && c <= 4 && S_total % c == 0 && S_total / c >= 512 && S_total / c <= (long long)TILE_MAX_R * TILE_MAXC) nch = c;
+    }
+    const long long S = S_total / nch;
+    tp->n_chunks = nch; tp->chunk_len = (int)S;
     const long long per = (S + csize - 1) / csize;  // draws a CTA owns
     if (per > TILE_MAX_R) return false;
     // boxes of the CTA's draws: <= 256 rows each, a multiple of 8 rows (every box starts on a 1024-byte swizzle
@@ -587,13 +623,25 @@ bool tile_shape(long long S, int M, int csize, int tw, TilePlan* tp) {
     const double B = 32.0 * csize;
     auto h_of = [](int q) { double s = 0.0; for (int i = 32 - q + 1; i <= 32; ++i) s += 1.0 / i; return s; };
     const bool long_tail = (double)(M + 1) > 0.9 * B;
-    if ((double)(M + 1) > 0.70 * 0.93 * B * h_of(31)) return false;
+    if (nch == 1 && (double)(M + 1) > 0.70 * 0.93 * B * h_of(31)) return false;
     auto K_t = [&](int q) { return long_tail ? 0.91 * B * h_of(q) : -0.9 * B * std::log(1.0 - (double)q / 32.0); };
     auto K_l = [&](int q) { return long_tail ? 0.93 * B * h_of(q) : -0.9 * B * std::log(1.0 - (double)q / 32.0); };
     const int tl = (M + 2 <= 128) ? 4 : ((M + 2 <= 256) ? 8 : 16);  // the tail kernel's registers per lane (split_shape)
-    const double want_t = 0.5 * ((double)(M + 1) + 32.0 * tl), want_l = std::min(1.65 * (M + 1), 0.8 * 64.0 * tl);
+    double want_t = 0.5 * ((double)(M + 1) + 32.0 * tl), want_l = std::min(1.65 * (M + 1), 0.8 * 64.0 * tl);
+    if (nch > 1) {
+        // chunked: ONE list; a chunk's threshold must admit every draw of the chunk that belongs to the column's
+        // tail.  Its share of the M + 1 extreme draws is binomial (mean (M + 1) / n_chunks, spread ~9 % at M = 380)
+        // and the count at a threshold rank spreads ~8 %: 1.6 shares per chunk leave 3.4 joint spreads.
+        want_t = want_l = 1.6 * (double)(M + 1) / nch;
+        if (want_l > 0.70 * 0.93 * B * h_of(31) || 1.6 * (double)(M + 1) > 0.9 * 64.0 * tl) return false;
+    }
+    auto K_c = [&](int q) { return 0.93 * B * h_of(q); };
     int qt = 1, ql = 1;
     for (int q = 1; q <= 31; ++q) {
+        if (nch > 1) {
+            if (std::fabs(K_c(q) - want_l) < std::fabs(K_c(ql) - want_l)) qt = ql = q;
+            continue;
+        }
         if (std::fabs(K_t(q) - want_t) < std::fabs(K_t(qt) - want_t)) qt = q;
         if (std::fabs(K_l(q) - want_l) < std::fabs(K_l(ql) - want_l)) ql = q;
     }
@@ -605,14 +653,14 @@ bool tile_shape(long long S, int M, int csize, int tw, TilePlan* tp) {
     return true;
 }
 
-template <int TW>
+template <int TW, bool CHUNKED>
 static cudaError_t tile_occupancy(TilePlan* tp) {
-    cudaError_t e = cudaFuncSetAttribute(loo_tile_kernel<TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp->smem);
+    cudaError_t e = cudaFuncSetAttribute(loo_tile_kernel<TW, CHUNKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp->smem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(loo_tile_kernel<TW>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(loo_tile_kernel<TW, CHUNKED>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              (int)cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tp->occ, loo_tile_kernel<TW>, 16 * TW, tp->smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tp->occ, loo_tile_kernel<TW, CHUNKED>, 16 * TW, tp->smem);
     if (e != cudaSuccess) return e;
     if (tp->occ < 1) return cudaSuccess;
     cudaLaunchConfig_t cfg;
@@ -628,7 +676,7 @@ static cudaError_t tile_occupancy(TilePlan* tp) {
     cfg.attrs = at;
     cfg.numAttrs = 1;
     int nc = 0;
-    e = cudaOccupancyMaxActiveClusters(&nc, loo_tile_kernel<TW>, &cfg);
+    e = cudaOccupancyMaxActiveClusters(&nc, loo_tile_kernel<TW, CHUNKED>, &cfg);
     if (e != cudaSuccess) return e;
     tp->max_clusters = nc;
     return cudaSuccess;
@@ -650,7 +698,7 @@ cudaError_t tile_plan(long long S, int M, TilePlan* tp) {
     } else {
         for (int c = 2; c <= TILE_MAXC; c <<= 1) {
             TilePlan probe;
-            if (tile_shape(S, M, c, tw, &probe) && (double)(M + 1) <= 1.2 * 32.0 * c) { csize = c; break; }
+            if (tile_shape(S, M, c, tw, &probe) && probe.n_chunks == 1 && (double)(M + 1) <= 1.2 * 32.0 * c) { csize = c; break; }
         }
     }
     if (!tile_shape(S, M, csize, tw, tp)) return cudaSuccess;
@@ -660,7 +708,8 @@ cudaError_t tile_plan(long long S, int M, TilePlan* tp) {
     e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e != cudaSuccess) return e;
     if (tp->smem > (size_t)smem_optin) return cudaSuccess;
-    e = (tw == 16) ? tile_occupancy<16>(tp) : tile_occupancy<8>(tp);
+    if (tp->n_chunks > 1) e = (tw == 16) ? tile_occupancy<16, true>(tp) : tile_occupancy<8, true>(tp);
+    else e = (tw == 16) ? tile_occupancy<16, false>(tp) : tile_occupancy<8, false>(tp);
     if (e != cudaSuccess) return e;
     if (tp->occ < 1 || tp->max_clusters < 1) return cudaSuccess;
     tp->ok = 1;
@@ -694,7 +743,7 @@ cudaError_t tile_tensor_map(const double* ll, long long S, long long N, long lon
 
 cudaError_t tile_launch(const TilePlan& tp, const void* tmap, const TileParams& p, cudaStream_t st) {
     if (p.n_tiles <= 0) return cudaSuccess;
-    const long long nc = std::min<long long>(tp.max_clusters, p.n_tiles);
+    const long long nc = std::min<long long>(tp.max_clusters, p.n_tiles * std::max(1, p.n_chunks));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)(nc * tp.csize));
@@ -709,8 +758,65 @@ cudaError_t tile_launch(const TilePlan& tp, const void* tmap, const TileParams& 
     cfg.attrs = at;
     cfg.numAttrs = 1;
     const CUtensorMap& tm = *reinterpret_cast<const CUtensorMap*>(tmap);
-    return (tp.tw == 16) ? cudaLaunchKernelEx(&cfg, loo_tile_kernel<16>, tm, p)
-                         : cudaLaunchKernelEx(&cfg, loo_tile_kernel<8>, tm, p);
+    if (p.n_chunks > 1)
+        return (tp.tw == 16) ? cudaLaunchKernelEx(&cfg, loo_tile_kernel<16, true>, tm, p)
+                             : cudaLaunchKernelEx(&cfg, loo_tile_kernel<8, true>, tm, p);
+    return (tp.tw == 16) ? cudaLaunchKernelEx(&cfg, loo_tile_kernel<16, false>, tm, p)
+                         : cudaLaunchKernelEx(&cfg, loo_tile_kernel<8, false>, tm, p);
+}
+
+// Chunked rounds: one thread per observation folds the chunk records into the SplitHeader the tail kernel reads
+// (sums re-centred about the column minimum exactly as the owner CTA does for a tile's CTAs) and decides what is
+// handed over.
+static __global__ void __launch_bounds__(128) tile_merge_kernel(const TileParams p, const double S_total) {
+    const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= p.n_obs) return;
+    const int nch = p.n_chunks;
+    const ChunkHeader* c = p.chdr + o * nch;
+    double llmin = c[0].llmin;
+    for (int i = 1; i < nch; ++i) llmin = min_sel(llmin, c[i].llmin);
+    const double n_r = (double)p.S;
+    double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0, um = 0.0, vmax = -inf_f64(), vmin = inf_f64();
+    for (int i = 0; i < nch; ++i) {
+        const ChunkHeader e = c[i];
+        const double d = e.llmin - llmin;  // >= 0
+        q0 += e.q0 * exp(-d);
+        q1 += e.q1 * exp(d);
+        q2 += fma(n_r, d, e.q2);
+        q3 += fma(d, fma(n_r, d, 2.0 * e.q2), e.q3);
+        um = fmax(um, e.um + d);
+        const double v = llmin - e.tl;  // the chunk's candidates have x >= v, its other draws x <= v
+        vmax = fmax(vmax, v);
+        vmin = fmin(vmin, v);
+    }
+    const int ca = (int)p.cnt[2 * o];
+    const bool special = !(is_finite(q2) && is_finite(q3) && is_finite(q0) && is_finite(q1));
+    const bool wide = !(um <= 600.0);
+    const bool count_bad = (ca < p.M + 1) || (ca > p.cap);
+    const bool ok = !special && !wide && !count_bad;
+    SplitHeader h;
+    h.mx = -llmin;
+    h.body = q0;
+    h.lsum = q1;
+    h.vsum = q3 - q2 * q2 / S_total;
+    if (h.vsum < 0.0) h.vsum = 0.0;
+    h.lshift = llmin;
+    h.taux = vmin;
+    h.lse = 0.0;
+    h.C = ca; h.flags = ok ? 0 : 1; h.attempts = 0; h.n_patch = 0; h.C2 = 0; h.pad_ = 0;
+    h.vmax = vmax; h.pad2_ = 0.0;
+    p.hdr[o] = h;
+    if (!ok) {
+        p.fb_list[atomicAdd(p.fb_count, 1)] = (int)(p.row_base + o);
+        if (p.counters) atomicAdd(&p.counters[3], 1ull);
+        note_handover(special ? HO_SPECIAL : (wide ? HO_RANGE : HO_RETRY));
+    }
+}
+
+cudaError_t tile_merge_launch(const TileParams& p, long long S_total, cudaStream_t st) {
+    if (p.n_obs <= 0 || p.n_chunks <= 1) return cudaSuccess;
+    tile_merge_kernel<<<(unsigned)((p.n_obs + 127) / 128), 128, 0, st>>>(p, (double)S_total);
+    return cudaGetLastError();
 }
 
 cudaError_t tile_reasons(unsigned long long* out, int reset) {

@@ -12,8 +12,23 @@ constexpr int TILE_W = 16;      // default observations per tile: 128 B of every
 constexpr int TILE_MAXC = 8;    // largest (portable) cluster
 constexpr int TILE_MAX_R = 512; // draws per CTA: one 32-bit candidate mask per thread (16 draw slots x 32)
 
+// Long posteriors (S > 4096): the draw axis is cut into n_chunks equal chunks of at most 4096 draws and every
+// (tile, chunk) pair is one unit of work of the same kernel -- own minimum, own threshold, sums about its own
+// minimum, candidates appended to the column's one list as raw r = -ll.  tile_merge_kernel folds the chunk records
+// of a column into its SplitHeader (b2l_tile.cu).
+struct __align__(16) ChunkHeader {  // 64 B per (observation, chunk)
+    double llmin;           // min of ll over the chunk
+    double q0, q1, q2, q3;  // about llmin: sum exp(-(ll - llmin)), sum exp(ll - llmin), sum (ll - llmin), sum (ll - llmin)^2
+    double um;              // upper bound of max (ll - llmin)
+    double tl;              // the chunk's candidate threshold: its candidates are the draws with ll <= tl
+    double pad_;
+};
+static_assert(sizeof(ChunkHeader) == 64, "ChunkHeader is 64 bytes");
+
 struct TilePlan {
     int ok;
+    int n_chunks;   // 1, or the equal chunks a long draw axis is cut into
+    int chunk_len;  // draws per chunk (S when n_chunks = 1): the S the shape below is planned for
     int tw;        // observations per tile (16 or 8); threads per CTA = 16 * tw
     int csize;     // CTAs per cluster = segments of the draw axis
     int R;         // draws a CTA owns: ceil(S / csize)
@@ -39,6 +54,8 @@ struct TileParams {
     int* fb_count;
     unsigned long long* counters;  // optional [4]; [3] += observations handed over
     long long row_base;
+    int n_chunks;        // > 1: S above is the chunk length, work units are (tile, chunk) pairs, n_tiles still counts tiles
+    ChunkHeader* chdr;   // [n_tiles * tw][n_chunks] (chunked only; hdr is then written by tile_merge_kernel)
     int debug;  // measurement aids (B2L_TILE_DEBUG): 2 loads only, 4 no candidate pass, 8 no exp pass (2, 4, 8: no valid results)
 };
 
@@ -49,6 +66,8 @@ cudaError_t tile_plan(long long S, int M, TilePlan* tp);
 cudaError_t tile_tensor_map(const double* ll, long long S, long long N, long long stride_s, int tw, int box_rows,
                             void* tmap_out /* CUtensorMap, 128 B */);
 cudaError_t tile_launch(const TilePlan& tp, const void* tmap, const TileParams& p, cudaStream_t st);
+// chunked rounds: fold the chunk records into the round's SplitHeaders (S_total = all draws), flag what must be handed over
+cudaError_t tile_merge_launch(const TileParams& p, long long S_total, cudaStream_t st);
 cudaError_t tile_reasons(unsigned long long* out, int reset);
 
 }  // namespace b2l

@@ -417,7 +417,8 @@ static bool tile_eligible(const double* ll, long long S, long long N, long long 
 // B2L_TILE_ROUND observations): a launch's fixed costs and its last, partly filled wave of clusters weigh less.
 static size_t tile_round_bytes(const SplitPlan& sp, long long P) {
     return align_up((size_t)P * sizeof(SplitHeader), 256) + align_up((size_t)P * sp.cap * 8, 256) +
-           align_up((size_t)P * sp.cap * 2, 256) + align_up((size_t)P * 8, 256);
+           align_up((size_t)P * sp.cap * 2, 256) + align_up((size_t)P * 8, 256) +
+           align_up((size_t)P * 4 * sizeof(ChunkHeader), 256);  // (chunk records: up to 4 per observation)
 }
 static size_t tile_fixed_bytes(long long N) { return 256 + align_up((size_t)std::max<long long>(N, 1) * 4, 256); }
 static long long tile_round_obs(const SplitPlan& sp, long long N, size_t avail) {
@@ -446,6 +447,9 @@ static int launch_tiles(const RowPlan& pl, const SplitPlan& sp, const TilePlan& 
     unsigned short* cs = reinterpret_cast<unsigned short*>(w);
     w += align_up((size_t)P * sp.cap * 2, 256);
     unsigned* cnt = reinterpret_cast<unsigned*>(w);
+    w += align_up((size_t)P * 8, 256);
+    ChunkHeader* chdr = reinterpret_cast<ChunkHeader*>(w);
+    const bool chunked = tp.n_chunks > 1;
     int msq = (int)std::sqrt((double)rp.M);
     while (msq * msq > rp.M) --msq;
     while ((msq + 1) * (msq + 1) <= rp.M) ++msq;
@@ -457,7 +461,8 @@ static int launch_tiles(const RowPlan& pl, const SplitPlan& sp, const TilePlan& 
         const long long nb = std::min<long long>(per_round, N - i0);
         TileParams tq;
         memset(&tq, 0, sizeof(tq));
-        tq.S = (int)S; tq.M = rp.M; tq.cap = sp.cap; tq.R = tp.R; tq.nbox = tp.nbox; tq.box_rows = tp.box_rows;
+        tq.S = tp.chunk_len; tq.n_chunks = tp.n_chunks; tq.chdr = chdr;
+        tq.M = rp.M; tq.cap = sp.cap; tq.R = tp.R; tq.nbox = tp.nbox; tq.box_rows = tp.box_rows;
         tq.q_t = tp.q_t; tq.q_l = tp.q_l; tq.n_tiles = (nb + tp.tw - 1) / tp.tw; tq.col0 = i0; tq.n_obs = nb;
         tq.hdr = hdr; tq.cx = cx; tq.cs = cs; tq.cnt = cnt; tq.fb_list = fb_list; tq.fb_count = fb_count;
         tq.counters = rp.counters; tq.row_base = i0;
@@ -466,6 +471,7 @@ static int launch_tiles(const RowPlan& pl, const SplitPlan& sp, const TilePlan& 
         {
             ProfScope prof(B2L_PROF_STREAM, st);
             CK(tile_launch(tp, tmap, tq, st));
+            if (chunked && !(tq.debug & ~1)) CK(tile_merge_launch(tq, S, st));
         }
         SplitParams q;
         memset(&q, 0, sizeof(q));
@@ -473,7 +479,8 @@ static int launch_tiles(const RowPlan& pl, const SplitPlan& sp, const TilePlan& 
         q.lppdw_i = rp.lppdw_i + i0; q.diag = rp.diag ? rp.diag + i0 * DIAG_STRIDE : nullptr;
         q.n_rows = nb; q.S = (int)S; q.M = rp.M; q.cap = sp.cap; q.m_full = 30 + msq; q.cutoffmin = rp.cutoffmin;
         q.counters = rp.counters; q.hdr = hdr; q.cx = cx; q.cs = cs; q.fb_list = fb_list; q.fb_count = fb_count;
-        q.row_base = i0; q.total_body = 1; q.ab_lists = 1; q.log_S = std::log((double)S);
+        q.row_base = i0; q.total_body = 1; q.ab_lists = chunked ? 0 : 1; q.chunked = chunked ? 1 : 0;
+        q.log_S = std::log((double)S);
         q.tail_idx = rp.tail_idx ? rp.tail_idx + i0 * rp.tail_ld : nullptr; q.tail_ld = rp.tail_ld;
         if (tq.debug & ~1) continue;  // measurement aids that leave no valid results: the tile kernel alone
         const int g2 = (int)std::min<long long>(sp.grid2, (nb + sp.tw - 1) / sp.tw);

@@ -11,7 +11,9 @@ n_cases = int(os.environ.get("CASES", 24))
 worst = {"elpd": 0.0, "k": 0.0, "lppd": 0.0, "var": 0.0}
 fails = []
 for case in range(n_cases):
-    S = 2 * int(rng.integers(256, 2049))
+    S = 2 * int(rng.integers(256, int(os.environ.get("SMAX", 4096)) // 2 + 1))
+    if S > 4096:
+        S = S // 12 * 12   # divisible by 2, 3, 4: takes the chunked units
     N = 2 * int(rng.integers(4, 1500))
     reff = float(rng.choice([float(v) for v in os.environ.get("REFFS", "1.0,0.9,0.8,0.72").split(",")]))
     kind = case % 6

@@ -129,6 +129,53 @@ def test_tile_path_cluster_sizes_vs_oracle(S, N, reff, csize, monkeypatch):
     check_against_oracle(ll, reff, r)
 
 
+@pytest.mark.parametrize("S,N,reff", [(8000, 60, 1.0), (16000, 40, 1.0), (6000, 34, 0.8), (12000, 24, 1.0), (10000, 30, 0.7),
+                                      (16384, 18, 1.0), (5000, 50, 1.0)])
+def test_tile_path_long_posteriors_vs_oracle(S, N, reff):
+    """More than 4096 draws (BASELINE configs[3] has 16 000): the draw axis is cut into 2, 3 or 4 equal chunks, every
+    (tile, chunk) pair is a work unit of the cluster kernel, the column's chunks are folded by tile_merge_kernel and
+    the tail kernel forms x = fl(r - max r) from the raw candidates.  One read of HBM, no transposed panels."""
+    rng = np.random.default_rng(S + N)
+    ll = -1.4 + rng.normal(size=(S, N)) * rng.uniform(0.3, 2.0, size=(1, N))
+    engine.profile(True)
+    engine.handover_reasons()
+    r = gpu_loo(ll, reff, want_diag=True)
+    prof = engine.profile_read()
+    engine.profile(False)
+    check_against_oracle(ll, reff, r)
+    assert prof["transpose"][1] == 0 and prof["stream"][1] >= 1
+    assert int(r["counters"][3]) <= max(1, N // 25), engine.handover_reasons(reset=False)
+
+
+@pytest.mark.parametrize("chunks", ["2", "4"])
+def test_tile_path_chunked_units_on_a_short_posterior(chunks, monkeypatch):
+    """The chunked units forced onto S = 4000 (B2L_TILE_CHUNKS): same numbers as the oracle, the same tail index
+    sets as the plain units, chains of different location as chunks (more hand-overs, same values)."""
+    rng = np.random.default_rng(31)
+    S, N = 4000, 120
+    ll = -1.4 + rng.normal(size=(S, N)) * rng.uniform(0.3, 2.0, size=(1, N))
+    ll[1000:2000, ::3] += 0.6          # one "chain" sits higher in every third column
+    ll[5, 7] = np.nan
+    ll[3000, 9] = -np.inf
+    ll[:, 11] = -2.0
+    plain = gpu_loo(ll, 1.0, want_diag=True, want_tail_idx=True)
+    monkeypatch.setenv("B2L_TILE_CHUNKS", chunks)
+    engine.handover_reasons()
+    r = gpu_loo(ll, 1.0, want_diag=True, want_tail_idx=True)
+    with np.errstate(all="ignore"):
+        pw = orc.loo_pointwise(ll, 1.0)
+        ww = orc.waic_pointwise(ll)
+    for key, ref in (("elpd_i", pw["elpd_i"]), ("pareto_k", pw["pareto_k"]), ("lppd_i", pw["lppd_i"]),
+                     ("var_i", ww["var_i"]), ("lppdw_i", ww["lppd_i"])):
+        same_special(r[key], ref)
+        close(r[key], ref, atol=1e-13)
+    ok = np.isfinite(pw["pareto_k"])
+    a = np.sort(plain["tail_idx"][ok], axis=1)
+    b = np.sort(r["tail_idx"][ok], axis=1)
+    assert np.array_equal(a, b)
+    assert np.array_equal(plain["diag"][ok, 1], r["diag"][ok, 1])   # the cutoff, bit for bit
+
+
 def test_tile_path_runs_the_cluster_kernel():
     """The eligible shapes really take the tile kernel (per-kernel timers: no transpose launch)."""
     rng = np.random.default_rng(3)
