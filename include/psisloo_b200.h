@@ -35,6 +35,11 @@ extern "C" {
 
 /* flags for the loo entry points */
 #define B2L_FLAG_WAIC_ONLY 1u /* skip PSIS: only lppd_i / var_i / lppdw_i (pyloo/waic.py path) */
+#define B2L_FLAG_NO_TILE 2u   /* (S, N) layout: take the transposed-panel route even where the cluster kernel could read the
+                                 matrix in place.  Same results; for inputs whose columns the cluster kernel hands to the
+                                 general kernel wholesale (log-likelihoods with Student-t(3)-like tails: the normaliser is
+                                 carried by a few draws).  The host entry points set it themselves once more than a fifth
+                                 of a chunk's observations were handed over. */
 
 /* fixed per-shard statistics record (doubles); combined across GPUs by b2l_stats_merge */
 #define B2L_STATS_LEN 32

@@ -819,7 +819,7 @@ extern "C" int b2l_loo_dev_ex_f64(const double* ll, int64_t S, int64_t N, int64_
     }
     const long long P = panel_obs(S, N);
     const size_t panel_bytes = align_up((size_t)P * (size_t)S * 8, 256);
-    if (!rp.waic_only && !gro && tile_eligible(ll, S, N, stride_s, M)) {
+    if (!rp.waic_only && !gro && !(flags & B2L_FLAG_NO_TILE) && tile_eligible(ll, S, N, stride_s, M)) {
         // the matrix is read where it lies (2-D TMA tiles, one pass over HBM): no panels
         rc = plan_split(S, M, MODE_LOO, P, &sp);  // same scratch slots as the panel path sizes (b2l_workspace_bytes)
         if (rc) return rc;
@@ -1455,6 +1455,13 @@ extern "C" int b2l_loo_host_f64(const double* ll, int64_t S, int64_t N, int64_t 
         double* d_stats = cv.take<double>(B2L_STATS_LEN);
         void* d_ws = cv.take<char>(wsb);
         long long dss, dsn;
+        if (ci >= NSLOT && !rows_in && !(flags & (B2L_FLAG_NO_TILE | B2L_FLAG_WAIC_ONLY))) {
+            // the slot's previous chunk (three chunks back): if the cluster kernel handed more than a fifth of it to
+            // the general kernel (heavy-tailed columns), the rest of the matrix takes the transposed-panel route
+            CK(cudaStreamSynchronize(sl.st));
+            const double* rec = prec + (size_t)(ci - NSLOT) * B2L_STATS_LEN;
+            if (rec[B2L_ST_N_FALLBACK] > 0.2 * rec[B2L_ST_N]) flags |= B2L_FLAG_NO_TILE;
+        }
         if (bounce) {
             // the slot's previous chunk (three chunks back) has left its bounce buffer once its stream is idle
             CK(cudaStreamSynchronize(sl.st));

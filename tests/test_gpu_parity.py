@@ -462,7 +462,10 @@ def test_heavy_tailed_rows_stay_on_the_split_path():
     the general kernel are counted) and agree with the oracle."""
     rng = np.random.default_rng(56)
     x = rng.standard_t(1.5, size=(256, 8000))
-    r = gpu_loo(np.ascontiguousarray(-x.T), 1.0)
+    # observation rows contiguous: the (S, N) view of an (N, S) matrix takes the row route (stream + tail kernels)
+    res = engine.loo_cuda(torch.from_numpy(np.ascontiguousarray(-x)).cuda().T, 1.0)
+    torch.cuda.synchronize()
+    r = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in res.items() if k != "workspace"}
     with np.errstate(all="ignore"):
         pw = orc.loo_pointwise(-x.T, 1.0)
     close(r["pareto_k"], pw["pareto_k"], atol=1e-13)

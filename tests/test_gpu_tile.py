@@ -176,6 +176,27 @@ def test_tile_path_chunked_units_on_a_short_posterior(chunks, monkeypatch):
     assert np.array_equal(plain["diag"][ok, 1], r["diag"][ok, 1])   # the cutoff, bit for bit
 
 
+def test_host_loo_leaves_the_cluster_kernel_when_it_hands_over_most_columns():
+    """Student-t(3) log-likelihoods: the normaliser of most columns is carried by a few draws, the cluster kernel hands
+    them to the general kernel one by one.  The host pipeline notices (statistics record of a finished chunk) and sends
+    the remaining chunks down the transposed-panel route; the values do not depend on the route.  B2L_FLAG_NO_TILE on
+    the device entry point does the same on request."""
+    rng = np.random.default_rng(41)
+    S, N = 2000, 3072
+    ll = -1.4 + rng.standard_t(3, size=(S, N))
+    engine.profile(True)
+    r = engine.loo_host(ll, 1.0, chunk_obs=256, device=0)
+    prof = engine.profile_read()
+    engine.profile(False)
+    assert prof["stream"][1] >= 3 and prof["transpose"][1] >= 1       # both routes ran
+    with np.errstate(all="ignore"):
+        pw = orc.loo_pointwise(ll, 1.0)
+    for key in ("elpd_i", "pareto_k", "lppd_i"):
+        same_special(r[key], pw[key])
+        close(r[key], pw[key], atol=1e-13)
+    assert r["stats"].n == N
+
+
 def test_tile_path_runs_the_cluster_kernel():
     """The eligible shapes really take the tile kernel (per-kernel timers: no transpose launch)."""
     rng = np.random.default_rng(3)
