@@ -1066,9 +1066,14 @@ __device__ __forceinline__ int tail_row(const SplitParams& p, long long row, con
     // ---------------- phase 1: sort the candidates, stage the head of the order, exact order inside key runs
     if (!why) {
         const double xoff = p.chunked ? mx : 0.0;
-        if (C <= 32 * TL) nont = sort_and_stage<TL, TL>(C, CA, p.cap, !total_body, h.taux, xoff, st, tab, lane);
-        else nont = sort_and_stage<2 * TL, TL>(C, CA, p.cap, !total_body, h.taux, xoff, st, tab, lane);
-        if (!fix_runs<TL>(st, C, M, h.taux, lane)) why = HO_RUNS;
+        if (C <= 32 * TL) {
+            nont = sort_and_stage<TL, TL>(C, CA, p.cap, !total_body, h.taux, xoff, st, tab, lane);
+        } else {
+            // (TL = 32, tails of 511 to ~800 draws: one 1024-key sort is all there is; longer lists are handed over)
+            if constexpr (TL < 32) nont = sort_and_stage<2 * TL, TL>(C, CA, p.cap, !total_body, h.taux, xoff, st, tab, lane);
+            else why = HO_RETRY;
+        }
+        if (!why && !fix_runs<TL>(st, C, M, h.taux, lane)) why = HO_RUNS;
     }
     if (SYNCP) __syncthreads();
 

@@ -16,7 +16,7 @@ static cudaError_t setup1(size_t smem, int* occ) {
 
 // (registers per lane of the sort, warps per CTA): 4 warps = every warp on its own, 8 CTAs / SM; 16 or 32 warps =
 // one or two big CTAs per SM whose warps move through the phases of a row together (instruction-cache locality)
-#define B2L_TAIL_CASES(X) X(4, 4) X(4, 8) X(4, 16) X(4, 32) X(8, 4) X(8, 8) X(8, 16) X(8, 32) X(16, 4) X(16, 8) X(16, 16)
+#define B2L_TAIL_CASES(X) X(4, 4) X(4, 8) X(4, 16) X(4, 32) X(8, 4) X(8, 8) X(8, 16) X(8, 32) X(16, 4) X(16, 8) X(16, 16) X(32, 4) X(32, 8)
 
 cudaError_t split_tail_setup(int tl, int warps, int mode, size_t smem, int* occ) {
 #define X(TL_, W_)                                                                                 \

@@ -626,14 +626,15 @@ bool tile_shape(long long S_total, int M, int csize, int tw, TilePlan* tp) {
     if (nch == 1 && (double)(M + 1) > 0.70 * 0.93 * B * h_of(31)) return false;
     auto K_t = [&](int q) { return long_tail ? 0.91 * B * h_of(q) : -0.9 * B * std::log(1.0 - (double)q / 32.0); };
     auto K_l = [&](int q) { return long_tail ? 0.93 * B * h_of(q) : -0.9 * B * std::log(1.0 - (double)q / 32.0); };
-    const int tl = (M + 2 <= 128) ? 4 : ((M + 2 <= 256) ? 8 : 16);  // the tail kernel's registers per lane (split_shape)
-    double want_t = 0.5 * ((double)(M + 1) + 32.0 * tl), want_l = std::min(1.65 * (M + 1), 0.8 * 64.0 * tl);
+    const int tl = (M + 2 <= 128) ? 4 : ((M + 2 <= 256) ? 8 : ((M + 2 <= 512) ? 16 : 32));  // the tail kernel's registers per lane (split_shape)
+    const double two_sorts = (tl == 32) ? 1024.0 : 64.0 * tl;  // the longest list the tail kernel sorts
+    double want_t = 0.5 * ((double)(M + 1) + 32.0 * tl), want_l = std::min(1.65 * (M + 1), 0.8 * two_sorts);
     if (nch > 1) {
         // chunked: ONE list; a chunk's threshold must admit every draw of the chunk that belongs to the column's
         // tail.  Its share of the M + 1 extreme draws is binomial (mean (M + 1) / n_chunks, spread ~9 % at M = 380)
         // and the count at a threshold rank spreads ~8 %: 1.6 shares per chunk leave 3.4 joint spreads.
         want_t = want_l = 1.6 * (double)(M + 1) / nch;
-        if (want_l > 0.70 * 0.93 * B * h_of(31) || 1.6 * (double)(M + 1) > 0.9 * 64.0 * tl) return false;
+        if (want_l > 0.70 * 0.93 * B * h_of(31) || 1.6 * (double)(M + 1) > 0.9 * two_sorts) return false;
     }
     auto K_c = [&](int q) { return 0.93 * B * h_of(q); };
     int qt = 1, ql = 1;

@@ -220,7 +220,8 @@ static bool split_shape(long long S, int M, long long n_rows, SplitPlan* sp) {
     memset(sp, 0, sizeof(*sp));
     if (const char* ev = getenv("B2L_SPLIT")) if (atoi(ev) == 0) return false;
     if (getenv("B2L_FORCE_LEGACY")) return false;
-    if (S % 2 != 0 || S < 64 || S > SPLIT_MAX_S || M < 5 || M + 2 > 512 || (long long)M + 1 > S / 2) return false;
+    // (tails beyond 510 draws -- r_eff < 0.14 at S = 4000, < 0.55 at S = 16 000 -- sort 1024 keys per lane-set: M + 2 <= 800)
+    if (S % 2 != 0 || S < 64 || S > SPLIT_MAX_S || M < 5 || M + 2 > 800 || (long long)M + 1 > S / 2) return false;
     static const int shapes[8][2] = {{128, 8}, {128, 16}, {256, 8}, {256, 16}, {512, 8}, {512, 16}, {1024, 8}, {1024, 16}};
     int nt = 0, ept = 0;
     for (auto& sh : shapes) {
@@ -231,7 +232,7 @@ static bool split_shape(long long S, int M, long long n_rows, SplitPlan* sp) {
     }
     if (!nt) return false;
     sp->nt = nt; sp->ept = ept;
-    sp->tl = (M + 2 <= 128) ? 4 : ((M + 2 <= 256) ? 8 : 16);
+    sp->tl = (M + 2 <= 128) ? 4 : ((M + 2 <= 256) ? 8 : ((M + 2 <= 512) ? 16 : 32));
     sp->cap = 64 * sp->tl;
     {
         const double ratio = (double)(M + 1) / nt;
@@ -253,10 +254,11 @@ static bool split_shape(long long S, int M, long long n_rows, SplitPlan* sp) {
     if (const char* ev = getenv("B2L_SNBUF")) sp->nbuf = (atoi(ev) == 1) ? 1 : sp->nbuf;
     sp->smem1 = stream_smem((int)S, sp->nt * sp->ept, 1, 0).total;  // refined per mode in plan_split
     // warps per tail CTA: big CTAs whose warps pass through the phases of a row together (see tail_row)
-    sp->tw = 8;  // (measured at S = 4000, M = 190, per 2 x 75 776 observations: 4 warps 1.61 ms, 8 warps 1.36 ms, 16 warps 1.40 ms, 32 warps 1.45 ms)
+    sp->tw = (sp->tl == 32) ? 4 : 8;  // (TL = 32: 18 KB of staging per warp; measured at S = 4000, M = 190, per 2 x 75 776 observations: 4 warps 1.61 ms, 8 warps 1.36 ms, 16 warps 1.40 ms, 32 warps 1.45 ms)
     if (const char* ev = getenv("B2L_TAIL_WARPS")) {
         const int w = atoi(ev);
-        if (w == 4 || w == 8 || w == 16 || (w == 32 && sp->tl <= 8)) sp->tw = w;
+        if (sp->tl == 32) { if (w == 4 || w == 8) sp->tw = w; }
+        else if (w == 4 || w == 8 || w == 16 || (w == 32 && sp->tl <= 8)) sp->tw = w;
     }
     sp->smem2 = tail_smem(M, sp->tl, sp->tw).total;
     return true;

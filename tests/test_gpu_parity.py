@@ -140,6 +140,31 @@ def test_psislw_vs_oracle(S, N, reff, scale):
     assert np.array_equal(diag[:, 2].astype(int), cnt)
 
 
+@pytest.mark.parametrize("S,N,reff", [(4000, 96, 0.12), (4000, 64, 0.08), (6000, 48, 0.1), (16000, 20, 0.3)])
+def test_tails_beyond_510_draws(S, N, reff):
+    """r_eff far below 1: M = 3 sqrt(S / r_eff) passes the 510 draws two 512-key sorts cover; the tail kernel's
+    1024-key build (TL = 32) serves M + 2 <= 800 on the row route (psislw, and loo on shapes the cluster kernel does
+    not take)."""
+    M = orc.tail_length(S, reff)
+    assert 510 < M <= 798
+    rng = np.random.default_rng(S + N)
+    x = 1.3 * rng.normal(size=(N, S))
+    engine.handover_reasons()
+    lw, k, diag = gpu_psislw(x, reff, diag=True)
+    hand = engine.handover_reasons()
+    ref_lw, ref_k = orc.psislw(x, reff)
+    close(k, ref_k, atol=1e-13)
+    close(lw, ref_lw, atol=1e-12)
+    cut, cnt = oracle_tail(x, M)
+    assert np.array_equal(diag[:, 1], cut) and np.array_equal(diag[:, 2].astype(int), cnt)
+    assert sum(hand.values()) <= max(2, N // 10), hand          # the split path did the work, not the general kernel
+    r = gpu_loo(np.ascontiguousarray(-x.T), reff)
+    pw = orc.loo_pointwise(-x.T, reff)
+    close(r["elpd_i"], pw["elpd_i"])
+    close(r["pareto_k"], pw["pareto_k"], atol=1e-13)
+    close(r["lppd_i"], pw["lppd_i"])
+
+
 def test_psislw_heavy_tail_stress_cfg5_shape():
     rng = np.random.default_rng(55)
     x = rng.standard_t(1.5, size=(384, 8000))

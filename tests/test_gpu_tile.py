@@ -130,7 +130,7 @@ def test_tile_path_cluster_sizes_vs_oracle(S, N, reff, csize, monkeypatch):
 
 
 @pytest.mark.parametrize("S,N,reff", [(8000, 60, 1.0), (16000, 40, 1.0), (6000, 34, 0.8), (12000, 24, 1.0), (10000, 30, 0.7),
-                                      (16384, 18, 1.0), (5000, 50, 1.0)])
+                                      (16384, 18, 1.0), (5000, 50, 1.0), (16000, 30, 0.5), (8000, 40, 0.25)])
 def test_tile_path_long_posteriors_vs_oracle(S, N, reff):
     """More than 4096 draws (BASELINE configs[3] has 16 000): the draw axis is cut into 2, 3 or 4 equal chunks, every
     (tile, chunk) pair is a work unit of the cluster kernel, the column's chunks are folded by tile_merge_kernel and
