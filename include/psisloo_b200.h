@@ -99,7 +99,12 @@ int b2l_psislw_dev_f64(const double* lw, int64_t S, int64_t N, int64_t stride_s,
  *   elpd_i  : N  log-scale elpd_loo_i      k_i     : N  Pareto k
  *   lppd_i  : N  log mean exp ll (loo)     var_i   : N  var_s(ll), ddof 0 (waic policy)
  *   lppdw_i : N  log mean exp ll (waic policy; equals lppd_i unless the row holds +-inf)
- *   counters: nullable, 4 x uint64 device counters (NaN, +inf, -inf inputs; fallback rows), +=   */
+ *   counters: nullable, 4 x uint64 device counters (NaN, +inf, -inf inputs; fallback rows), +=
+ * Routes (same results on every one): stride_n == 1 (the ArviZ (chain, draw, obs) layout) with a 16-byte aligned
+ * base, an even stride_s, S even and 512 <= S <= 16384 (above 4096: divisible into 2, 3 or 4 chunks of <= 4096
+ * draws), M + 1 <= 510 is read where it lies by the cluster kernel (one pass over HBM, 2-D TMA tiles); otherwise
+ * the matrix goes through transposed row panels; stride_s == 1 (rows contiguous) takes the row kernels directly.
+ * B2L_FLAG_NO_TILE forces the panel route.                                                          */
 int b2l_loo_dev_f64(const double* ll, int64_t S, int64_t N, int64_t stride_s, int64_t stride_n,
                     int32_t M, double cutoffmin, uint32_t flags, double* elpd_i, double* k_i,
                     double* lppd_i, double* var_i, double* lppdw_i, unsigned long long* counters,
@@ -241,7 +246,8 @@ int b2l_profile_read(double* ms_out /* [B2L_PROF_KINDS] */, int64_t* launches_ou
 /* Diagnostics: why observations were handed from the split path to the general kernel on the current
  * device since the last reset; out16[reason]: 1 NaN/inf row, 2 range > 1e7, 3 threshold retries exhausted,
  * 4 long run of equal sort keys, 5 order check, 6-9 GPD fit (quantile <= 0, factor overflow, product,
- * non-finite profile).  Synchronises the device.                                                    */
+ * non-finite profile), 10 body cancellation (cluster kernel: the all-draw sum minus the raw tail leaves less
+ * than 1e-3 of it).  Synchronises the device.                                                    */
 int b2l_handover_reasons(uint64_t* out16, int32_t reset);
 
 /* Launch shape of the split path for (S, M): info[16] = ok, stream threads, draws per thread, tail
