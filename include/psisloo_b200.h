@@ -255,6 +255,12 @@ int b2l_handover_reasons(uint64_t* out16, int32_t reset);
  * stream CTAs/SM, tail CTAs/SM, stream smem, tail smem, observations per round, stream block size. */
 int b2l_split_launch_info(int64_t S, int32_t M, int32_t mode, int64_t n_rows, int32_t* info);
 
+/* Shape of the cluster kernel's plan for pl.loo on the (chain, draw, obs) layout (pure arithmetic, no device call):
+ * info[16] = eligible, observations per tile, CTAs per cluster, chunks of the draw axis, draws per chunk, draws per
+ * CTA, TMA boxes per CTA, draws per box, tight / loose threshold rank, shared memory per CTA, tail-kernel registers
+ * per lane, candidate capacity per observation, 0, 0, 0.  (Alignment of the caller's matrix is checked per call.) */
+int b2l_tile_shape_info(int64_t S, int32_t M, int32_t* info);
+
 /* Launch-shape introspection for benchmarks / DESIGN.md (grid, block, smem, occupancy). */
 int b2l_row_launch_info(int64_t S, int32_t M, int32_t mode /*0 psislw, 1 loo*/, int32_t* grid,
                         int32_t* block, int32_t* smem_bytes, int32_t* ctas_per_sm, int32_t* nbuf);

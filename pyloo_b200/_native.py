@@ -36,7 +36,7 @@ EXPORTS = [
     "b2l_version", "b2l_last_error", "b2l_device_count", "b2l_workspace_bytes",
     "b2l_psislw_dev_f64", "b2l_loo_dev_f64", "b2l_stats_dev_f64", "b2l_stats_merge",
     "b2l_psislw_host_f64", "b2l_loo_host_f64", "b2l_row_launch_info", "b2l_profile", "b2l_profile_read",
-    "b2l_split_launch_info", "b2l_handover_reasons",
+    "b2l_split_launch_info", "b2l_tile_shape_info", "b2l_handover_reasons",
     "b2l_islw_dev_f64", "b2l_is_workspace_bytes", "b2l_loo_is_dev_f64", "b2l_eloo_workspace_bytes",
     "b2l_eloo_dev_f64", "b2l_eloo_quantile_dev_f64", "b2l_group_sum_dev_f64", "b2l_gather_rows_dev_f64",
     "b2l_loo_host_mgpu_f64", "b2l_psislw_host_mgpu_f64", "b2l_loo_dev_ex_f64",
@@ -133,6 +133,8 @@ def _declare(lib) -> None:
     lib.b2l_handover_reasons.argtypes = [vp, i32]
     lib.b2l_split_launch_info.restype = c.c_int
     lib.b2l_split_launch_info.argtypes = [i64, i32, i32, i64, vp]
+    lib.b2l_tile_shape_info.restype = c.c_int
+    lib.b2l_tile_shape_info.argtypes = [i64, i32, vp]
     lib.b2l_islw_dev_f64.restype = c.c_int
     lib.b2l_islw_dev_f64.argtypes = [vp, i64, i64, i64, i32, vp, i64, vp, vp]
     lib.b2l_is_workspace_bytes.restype = c.c_int

@@ -683,12 +683,11 @@ static cudaError_t tile_occupancy(TilePlan* tp) {
     return cudaSuccess;
 }
 
-cudaError_t tile_plan(long long S, int M, TilePlan* tp) {
-    // 8-observation tiles (64 B of a draw, 4 warps, 6 CTAs / SM) measure ~10 % faster than 16-observation ones
-    // (128 B, 8 warps, 3 CTAs / SM): more, smaller CTAs hide each other's waits better
+// Shape of the plan without the device part: observations per tile, cluster size, chunks (pure arithmetic)
+bool tile_pick(long long S, int M, TilePlan* tp) {
     int csize = TILE_MAXC, tw = 8;
     if (const char* ev = getenv("B2L_TILE_W")) tw = atoi(ev);
-    if (const char* ev = getenv("B2L_TILE")) if (atoi(ev) == 0) { memset(tp, 0, sizeof(*tp)); return cudaSuccess; }
+    if (const char* ev = getenv("B2L_TILE")) if (atoi(ev) == 0) { memset(tp, 0, sizeof(*tp)); return false; }
     // Cluster size: the fewest CTAs that hold the draws of a tile (<= 512 each) -- short posteriors in clusters of
     // 8 leave a thread 4 to 8 draws per pass and the per-tile exchange dominates (S = 1000, 606 208 observations:
     // 5.08 ms with 8 CTAs, 3.45 ms with 4; S = 512: 4.69 / 2.85 / 1.93 ms with 8 / 4 / 2) -- as long as the
@@ -702,7 +701,14 @@ cudaError_t tile_plan(long long S, int M, TilePlan* tp) {
             if (tile_shape(S, M, c, tw, &probe) && probe.n_chunks == 1 && (double)(M + 1) <= 1.2 * 32.0 * c) { csize = c; break; }
         }
     }
-    if (!tile_shape(S, M, csize, tw, tp)) return cudaSuccess;
+    return tile_shape(S, M, csize, tw, tp);
+}
+
+cudaError_t tile_plan(long long S, int M, TilePlan* tp) {
+    // 8-observation tiles (64 B of a draw, 4 warps, 6 CTAs / SM) measure ~10 % faster than 16-observation ones
+    // (128 B, 8 warps, 3 CTAs / SM): more, smaller CTAs hide each other's waits better
+    if (!tile_pick(S, M, tp)) return cudaSuccess;
+    const int tw = tp->tw;
     int dev = 0, smem_optin = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;

@@ -61,6 +61,7 @@ struct TileParams {
 
 // shape part (pure arithmetic) and device part (occupancy) of the plan
 bool tile_shape(long long S, int M, int csize, int tw, TilePlan* tp);
+bool tile_pick(long long S, int M, TilePlan* tp);  // tile_shape with the library's choice of tile width and cluster size
 cudaError_t tile_plan(long long S, int M, TilePlan* tp);
 // 2-D tensor map of the (S, N) matrix: inner dimension = observations, box = TILE_W x box_rows
 cudaError_t tile_tensor_map(const double* ll, long long S, long long N, long long stride_s, int tw, int box_rows,

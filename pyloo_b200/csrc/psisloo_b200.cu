@@ -1153,6 +1153,17 @@ extern "C" int b2l_split_launch_info(int64_t S, int32_t M, int32_t mode, int64_t
     return 0;
 }
 
+extern "C" int b2l_tile_shape_info(int64_t S, int32_t M, int32_t* info) {
+    if (!info) return fail(B2L_E_INVALID, "null pointer");
+    TilePlan tp;
+    SplitPlan sp;
+    const bool ok = tile_pick(S, M, &tp) && split_shape(S, M, 1ll << 30, &sp);  // (the tail kernel must serve M too)
+    info[0] = ok ? 1 : 0; info[1] = tp.tw; info[2] = tp.csize; info[3] = tp.n_chunks; info[4] = tp.chunk_len;
+    info[5] = tp.R; info[6] = tp.nbox; info[7] = tp.box_rows; info[8] = tp.q_t; info[9] = tp.q_l;
+    info[10] = (int)tp.smem; info[11] = ok ? sp.tl : 0; info[12] = ok ? sp.cap : 0; info[13] = 0; info[14] = 0; info[15] = 0;
+    return 0;
+}
+
 extern "C" int b2l_row_launch_info(int64_t S, int32_t M, int32_t mode, int32_t* grid, int32_t* block,
                                    int32_t* smem_bytes, int32_t* ctas_per_sm, int32_t* nbuf) {
     RowPlan pl;

@@ -234,6 +234,16 @@ def split_launch_info(S: int, M: int, mode: str = "psislw", n_rows: int = 1 << 3
     return {k: int(v) for k, v in zip(keys, info)}
 
 
+def tile_shape_info(S: int, M: int) -> dict:
+    """Plan of the cluster kernel that serves ``loo`` on the ``(chain, draw, obs)`` layout for ``S`` draws and a tail
+    of ``M``: pure arithmetic in the library, no GPU needed.  ``eligible`` = 0: the shape takes the panel route."""
+    info = np.zeros(16, dtype=np.int32)
+    _native.check(_native.load().b2l_tile_shape_info(S, M, info.ctypes.data))
+    keys = ("eligible", "obs_per_tile", "cluster_size", "n_chunks", "chunk_len", "draws_per_cta", "boxes_per_cta",
+            "draws_per_box", "rank_tight", "rank_loose", "smem_bytes", "tail_regs_per_lane", "candidate_cap")
+    return {k: int(v) for k, v in zip(keys, info)}
+
+
 def psislw_cuda(lw, reff: float = 1.0, *, out=None, want_diag: bool = False, workspace=None):
     """PSIS on a device-resident float64 tensor ``(N, S)`` (any unit-stride layout); asynchronous
     on the current stream.  Returns ``(lw_out, k[, diag])`` tensors."""
