@@ -32,7 +32,9 @@ Printed JSON (one line, rank 0):
 from __future__ import annotations
 
 import argparse
+import datetime
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -235,7 +237,8 @@ def main():
         saved_out = os.dup(1)
         os.dup2(2, 1)
         try:
-            dist.init_process_group("nccl", device_id=dev)
+            # (a step's collectives finish in milliseconds; the CPU baseline on rank 0 keeps the others waiting ~1 min)
+            dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
             dist.barrier()
             torch.cuda.synchronize()
         finally:
@@ -292,11 +295,18 @@ def main():
     for _ in range(warmup):
         step()
     barrier()
+    # untimed steps around the timed region (below): their NUMBER must be the same on every rank -- a step holds a
+    # collective -- so it comes from one measured step time, maximum over the ranks, not from each rank's own clock
+    ev0.record()
+    step()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms_est = max(max_over_ranks(ev0.elapsed_time(ev1)), 0.05)
+    n_pre, n_post = int(min(2000, math.ceil(600.0 / ms_est))), int(min(1000, math.ceil(300.0 / ms_est)))
     with ClockSampler(local) as clk:
         # nvidia-smi needs ~0.3 s to start: keep the same step running (untimed) around the timed region so that
         # every clock / throttle sample is taken under this load
-        t_pre = time.perf_counter()
-        while time.perf_counter() - t_pre < 0.6:
+        for _ in range(n_pre):
             step()
             torch.cuda.synchronize()
         barrier()
@@ -305,8 +315,7 @@ def main():
             res, recs = step()
         ev1.record()
         barrier()
-        t_post = time.perf_counter()
-        while time.perf_counter() - t_post < 0.3:
+        for _ in range(n_post):
             step()
             torch.cuda.synchronize()
     ms_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
