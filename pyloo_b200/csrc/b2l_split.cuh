@@ -1223,12 +1223,15 @@ __device__ __forceinline__ int tail_row(const SplitParams& p, long long row, con
             dmax = warp_max_sel(dm);
             double e2 = 0.0;
 #pragma unroll 1
-            for (int e = lane; e < n; e += 32) e2 += exp_any((tb[e] - xs[e]) - dmax);
+            // (arguments <= 0; the table exponential is good to 4e-15 down to -36 and never worse than 8e-14, on
+            // terms that small next to the exp(0) of the largest: elpd_i moves by < 1e-14)
+            for (int e = lane; e < n; e += 32) e2 += exp_tab_drop((tb[e] - xs[e]) - dmax, tab, false);
             es = warp_sum(e2);
         }
+        const double* ltab2 = tab.t + 64;
         const double tot = (double)(S - n) * exp_any(-dmax) + es;
-        const double elpd = ((-mx - lse) + dmax) + log_slow(tot);
-        const double lppd = log_slow(h.lsum) + (h.lshift - p.log_S);  // utils.py:352-357, b_inv = S
+        const double elpd = ((-mx - lse) + dmax) + log_tab(tot, ltab2);
+        const double lppd = log_tab(h.lsum, ltab2) + (h.lshift - p.log_S);  // utils.py:352-357, b_inv = S
         const double var = h.vsum / (double)S;                        // waic.py:145
         if (lane == 0) {
             p.k_out[row] = kk;
