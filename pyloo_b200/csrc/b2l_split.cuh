@@ -903,17 +903,20 @@ struct TailSmem {
 // shared memory does not cap the resident warps): xs[32 TL] exact x of the head of the order,
 // tb[32 TL] t_i, then the smoothed values; ss[32 TL] draw indices.
 __host__ __device__ inline TailSmem tail_smem(int M, int TL, int warps) {
+    // per-warp staging first, at offsets that are compile-time constants of the kernel's template parameters (the
+    // M-dependent table goes last): the compiler rematerialises these addresses all over the row loop, and with the
+    // table in front every copy re-derived the offset from M (~220 instructions per row)
     TailSmem L;
-    L.off_l1p = 0;
-    size_t o = align_up((size_t)(M + 1) * 8, 16);
-    L.off_tab = o;   // 64 doubles exp table + 128 doubles log table
-    o += (64 + 128) * 8;
-    L.off_w = o;
+    L.off_w = 0;
     L.off_x = 0;
     L.off_t = (size_t)32 * TL * 8;
     L.off_s = (size_t)32 * TL * 16;
     L.w_stride = (size_t)32 * TL * 18;
-    o += L.w_stride * warps;
+    size_t o = L.w_stride * warps;
+    L.off_tab = o;   // 64 doubles exp table + 128 doubles log table
+    o += (64 + 128) * 8;
+    L.off_l1p = o;
+    o += align_up((size_t)(M + 1) * 8, 16);
     L.total = align_up(o, 128);
     return L;
 }
@@ -1229,7 +1232,7 @@ __device__ __forceinline__ int tail_row(const SplitParams& p, long long row, con
             es = warp_sum(e2);
         }
         const double* ltab2 = tab.t + 64;
-        const double tot = (double)(S - n) * exp_any(-dmax) + es;
+        const double tot = (double)(S - n) * exp_tab_drop(-dmax, tab, false) + es;
         const double elpd = ((-mx - lse) + dmax) + log_tab(tot, ltab2);
         const double lppd = log_tab(h.lsum, ltab2) + (h.lshift - p.log_S);  // utils.py:352-357, b_inv = S
         const double var = h.vsum / (double)S;                        // waic.py:145
