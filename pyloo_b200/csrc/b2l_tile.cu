@@ -54,11 +54,13 @@ struct RSum {  // one per (source CTA, owned column) and tile
 };
 static_assert(sizeof(XMsg) == 16 && sizeof(RSum) == 48, "exchange records");
 struct TileSmemLayout {
-    size_t off_tab, off_xch, off_rsum, off_bar, total;
+    size_t off_tab, off_xch, off_rsum, off_bar, off_tile, total;
 };
+// The small structures first, at offsets that depend on the template parameter only (compile-time constants inside
+// the kernel); the tile follows on the next 1024-byte boundary of the shared window (its swizzle atom).
 __host__ __device__ inline TileSmemLayout tile_smem(int rows_load, int tw) {
     TileSmemLayout L;
-    size_t o = 1024 + (size_t)rows_load * tw * 8;  // slack to align the tile to the 1024-byte swizzle atom
+    size_t o = 0;
     L.off_tab = o;   // 64 x (2^(j/64), 2^(-j/64))
     o += 64 * 16;
     L.off_xch = o;   // [parity][source CTA][column], written by the peers
@@ -67,7 +69,8 @@ __host__ __device__ inline TileSmemLayout tile_smem(int rows_load, int tw) {
     o += 2 * tw * sizeof(RSum);
     L.off_bar = o;   // tile full, tile empty, per warp and parity: exchange complete
     o += (2 + tw) * 8;
-    L.total = align_up(o, 128);
+    L.off_tile = o;  // (+ up to 1023 bytes of alignment slack)
+    L.total = align_up(o + 1023 + (size_t)rows_load * tw * 8, 128);
     return L;
 }
 
@@ -171,11 +174,11 @@ __global__ void __launch_bounds__(16 * TW, 48 / TW) loo_tile_kernel(const __grid
     constexpr int NW = TW / 2;       // warps: two columns each
     constexpr int KSTEP = 16 * TW;   // doubles between a thread's consecutive draws (16 rows of TW observations)
     extern __shared__ unsigned char smem_dyn[];
+    const TileSmemLayout L = tile_smem(0, TW);  // (the offsets do not depend on the tile's size)
+    unsigned char* aux = smem_dyn;
     // the swizzled tile starts on a 1024-byte boundary of the shared window
-    unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
-    const TileSmemLayout L = tile_smem(p.nbox * p.box_rows, TW);
+    unsigned char* smem_raw = smem_dyn + L.off_tile + ((1024u - ((smem_u32(smem_dyn) + (unsigned)L.off_tile) & 1023u)) & 1023u);
     double* tile = reinterpret_cast<double*>(smem_raw);
-    unsigned char* aux = smem_dyn;  // (offsets below are relative to the unaligned base + the 1024-byte slack)
     double2* etab = reinterpret_cast<double2*>(aux + L.off_tab);
     XMsg* xch = reinterpret_cast<XMsg*>(aux + L.off_xch);       // [2][TILE_MAXC][TW]
     RSum* rsum = reinterpret_cast<RSum*>(aux + L.off_rsum);     // [2][TW]: index src * nslot + slot
