@@ -539,8 +539,9 @@ __global__ void __launch_bounds__(16 * TW, 48 / TW) loo_tile_kernel(const __grid
             baseB = __shfl_sync(FULL, baseB, 15, 16);
             unsigned posA = baseA + (inc & 0xffffu) - nA, posB = baseB + (inc >> 16) - nB;
             if (mask && o < p.n_obs) {
-                double* dx = p.cx + (size_t)o * (size_t)cap;
-                unsigned short* ds = p.cs + (size_t)o * (size_t)cap;
+                const unsigned ob = (unsigned)o * (unsigned)cap;  // (a round's scratch has far fewer than 2^32 slots)
+                double* const dx = p.cx;
+                unsigned short* const ds = p.cs;
                 for (unsigned m = mask; m; m &= m - 1) {
                     const int b = __ffs((int)m) - 1;
                     const bool isA = (maskA >> b) & 1u;
@@ -549,8 +550,8 @@ __global__ void __launch_bounds__(16 * TW, 48 / TW) loo_tile_kernel(const __grid
                         const unsigned sl_ = isA ? pos : (unsigned)cap - 1u - pos;
                         // x = fl(r - max r), exactly (psis.py:134); chunked: r = -ll, the tail kernel subtracts max r
                         const double v = pcol[b * KSTEP];
-                        dx[sl_] = (nch > 1) ? -v : llmin - v;
-                        ds[sl_] = (unsigned short)(draw0 + 16 * b + slot);
+                        dx[ob + sl_] = (nch > 1) ? -v : llmin - v;
+                        ds[ob + sl_] = (unsigned short)(draw0 + 16 * b + slot);
                     }
                 }
             }
