@@ -559,7 +559,9 @@ __global__ void __launch_bounds__(IS_NT, 3) eloo_row_kernel(const ElooParams p) 
                 sexx += e * (xv * xv);
                 see += e * e;
                 if (need_hr) {
-                    const double hr = (sq ? xv * xv : xv) * (same ? e : exp_sum(LR[s] - lrmax, tb));
+                    // (library exp: these products are ranked, differenced against their cutoff and fitted --
+                    // e_loo.py:368-383 -- where the table exponential's 4e-15 would be amplified by a crowded tail)
+                    const double hr = (sq ? xv * xv : xv) * exp((same ? LW[s] : LR[s]) - (same ? lwmax : lrmax));
                     HR[s] = hr;
                     m_hi = sel_max(m_hi, hr);
                     m_lo = sel_max(m_lo, -hr);
