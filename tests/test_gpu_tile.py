@@ -197,6 +197,20 @@ def test_host_loo_leaves_the_cluster_kernel_when_it_hands_over_most_columns():
     assert r["stats"].n == N
 
 
+@pytest.mark.parametrize("S,reff", [(512, 1.0), (1000, 0.5), (2000, 0.25), (4000, 1.0), (8000, 0.5), (16000, 1.0)])
+def test_tile_path_very_few_observations(S, reff):
+    """Fewer observations than a tile holds, fewer work units than clusters, partial last tiles -- on every kind of
+    plan (clusters of 2 / 4 / 8 CTAs, chunked units, long tails): the launch completes and matches the oracle."""
+    rng = np.random.default_rng(S)
+    for N in (2, 6, 10, 18, 34):
+        ll = -1.4 + rng.normal(size=(S, N))
+        r = gpu_loo(ll, reff)
+        pw = orc.loo_pointwise(ll[:, :6], reff)
+        close(r["elpd_i"][:6], pw["elpd_i"][:6])
+        close(r["pareto_k"][:6], pw["pareto_k"][:6], atol=1e-13)
+        assert np.isfinite(r["elpd_i"]).all()
+
+
 def test_tile_path_runs_the_cluster_kernel():
     """The eligible shapes really take the tile kernel (per-kernel timers: no transpose launch)."""
     rng = np.random.default_rng(3)
